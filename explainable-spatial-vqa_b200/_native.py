@@ -1,0 +1,243 @@
+"""ctypes binding of libb200vqa.so (include/b200vqa.h).
+
+This is the only place Python touches the C ABI.  There is no CPU or PyTorch fallback: if the shared
+library is missing or the device is not an sm_100 GPU every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200vqa.so")
+
+MODEL_IQAP = 0
+MODEL_FA = 1
+
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class NativeError(RuntimeError):
+    """A libb200vqa call returned a negative status."""
+
+
+class MhaWeights(C.Structure):
+    _fields_ = [("in_proj_weight", _vp), ("in_proj_bias", _vp), ("out_proj_weight", _vp), ("out_proj_bias", _vp)]
+
+
+class EncoderLayerWeights(C.Structure):
+    _fields_ = [("self_attn", MhaWeights),
+                ("linear1_weight", _vp), ("linear1_bias", _vp), ("linear2_weight", _vp), ("linear2_bias", _vp),
+                ("norm1_weight", _vp), ("norm1_bias", _vp), ("norm2_weight", _vp), ("norm2_bias", _vp)]
+
+
+class DecoderLayerWeights(C.Structure):
+    _fields_ = [("self_attn", MhaWeights), ("multihead_attn", MhaWeights),
+                ("linear1_weight", _vp), ("linear1_bias", _vp), ("linear2_weight", _vp), ("linear2_bias", _vp),
+                ("norm1_weight", _vp), ("norm1_bias", _vp), ("norm2_weight", _vp), ("norm2_bias", _vp),
+                ("norm3_weight", _vp), ("norm3_bias", _vp)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("d_model", C.c_int32), ("img_feat_dim", C.c_int32), ("n_img_tokens", C.c_int32),
+                ("nhead", C.c_int32), ("n_enc_layers", C.c_int32), ("n_dec_layers", C.c_int32), ("dim_ff", C.c_int32),
+                ("enc_vocab", C.c_int32), ("dec_vocab", C.c_int32), ("max_q_len", C.c_int32),
+                ("pe_enc_len", C.c_int32), ("pe_dec_len", C.c_int32), ("answer_hidden", C.c_int32),
+                ("num_classes", C.c_int32), ("layer_norm_eps", C.c_float),
+                ("image_proj_weight", _vp), ("image_proj_bias", _vp), ("cls_token", _vp),
+                ("enc_embedding", _vp), ("dec_embedding", _vp), ("pe_enc", _vp), ("pe_dec", _vp),
+                ("enc_layers", C.POINTER(EncoderLayerWeights)), ("dec_layers", C.POINTER(DecoderLayerWeights)),
+                ("enc_final_norm_weight", _vp), ("enc_final_norm_bias", _vp),
+                ("dec_final_norm_weight", _vp), ("dec_final_norm_bias", _vp),
+                ("head_weight", _vp), ("head_bias", _vp),
+                ("answer_w0", _vp), ("answer_b0", _vp), ("answer_w1", _vp), ("answer_b1", _vp)]
+
+
+class DbgGemmArgs(C.Structure):
+    _fields_ = [("epilogue", C.c_int32), ("tf32", C.c_int32), ("block_n", C.c_int32),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("A", _vp), ("W", _vp), ("bias", _vp), ("out", _vp), ("ldc", C.c_int32),
+                ("residual", _vp), ("gamma", _vp), ("beta", _vp), ("out_f32", _vp),
+                ("rows_in", C.c_int32), ("rows_out", C.c_int32), ("row_off", C.c_int32), ("pe_off", C.c_int32),
+                ("pe", _vp)]
+
+
+# name -> (restype, argtypes); the not-gpu test-suite checks every symbol of include/b200vqa.h is here and exported
+SIGNATURES = {
+    "b200vqa_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int, C.POINTER(_vp)]),
+    "b200vqa_destroy": (None, [_vp]),
+    "b200vqa_refresh_weights": (C.c_int, [_vp, C.POINTER(ModelDesc)]),
+    "b200vqa_workspace_bytes": (C.c_size_t, [_vp, C.c_int]),
+    "b200vqa_last_error": (C.c_char_p, []),
+    "b200vqa_version": (C.c_char_p, []),
+    "b200vqa_launch_count": (C.c_uint64, [_vp]),
+    "b200vqa_iqap_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "b200vqa_fa_project_images": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "b200vqa_fa_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "b200vqa_fa_forward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "b200vqa_fa_run_chain": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
+                                       _vp, _vp]),
+    "b200vqa_dbg_gemm": (C.c_int, [C.POINTER(DbgGemmArgs), _vp]),
+    "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Loads libb200vqa.so (built in-tree by `__graft_entry__.build()` / `make -C .../csrc`)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU / PyTorch fallback for the executor path)")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().b200vqa_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f"{what} failed with status {rc}: {last_error()}")
+
+
+def ptr(t):
+    """Raw device (or host) pointer of a tensor, NULL for None."""
+    return _vp(0) if t is None else _vp(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NativeError(f"{what} lives on {t.device}: the executor path runs on an sm_100 GPU only (no CPU fallback); "
+                          "move the module with .cuda()")
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+class Handle:
+    """Owns one b200vqa_handle: packed weights + activation workspace on one GPU."""
+
+    def __init__(self, desc_builder, device: torch.device):
+        self._lib = lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NativeError(f"device {self.device}: libb200vqa needs an sm_100 GPU (no CPU fallback)")
+        self._h = _vp(0)
+        desc, keep = desc_builder()
+        self._keep = keep
+        out = _vp(0)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()  # parameter writes must be visible to the packer
+            check(self._lib.b200vqa_create(C.byref(desc), self.device.index or 0, C.byref(out)), "b200vqa_create")
+        self._h = out
+
+    @property
+    def raw(self):
+        return self._h
+
+    def refresh(self, desc_builder):
+        desc, keep = desc_builder()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            check(self._lib.b200vqa_refresh_weights(self._h, C.byref(desc)), "b200vqa_refresh_weights")
+        self._keep = keep
+
+    def launch_count(self) -> int:
+        return int(self._lib.b200vqa_launch_count(self._h))
+
+    def workspace_bytes(self, B: int) -> int:
+        return int(self._lib.b200vqa_workspace_bytes(self._h, int(B)))
+
+    def close(self):
+        if self._h:
+            self._lib.b200vqa_destroy(self._h)
+            self._h = _vp(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mha_weights(mha, keep) -> MhaWeights:
+    w = MhaWeights()
+    for name in ("in_proj_weight", "in_proj_bias"):
+        t = _dev_f32(getattr(mha, name), name)
+        keep.append(t)
+        setattr(w, name, t.data_ptr())
+    t = _dev_f32(mha.out_proj.weight, "out_proj.weight"); keep.append(t); w.out_proj_weight = t.data_ptr()
+    t = _dev_f32(mha.out_proj.bias, "out_proj.bias"); keep.append(t); w.out_proj_bias = t.data_ptr()
+    return w
+
+
+def _set(struct, keep, **tensors):
+    for name, t in tensors.items():
+        if t is None:
+            setattr(struct, name, None)
+            continue
+        t = _dev_f32(t, name)
+        keep.append(t)
+        setattr(struct, name, t.data_ptr())
+
+
+def encoder_layer_weights(layer, keep) -> EncoderLayerWeights:
+    w = EncoderLayerWeights()
+    w.self_attn = mha_weights(layer.self_attn, keep)
+    _set(w, keep, linear1_weight=layer.linear1.weight, linear1_bias=layer.linear1.bias,
+         linear2_weight=layer.linear2.weight, linear2_bias=layer.linear2.bias,
+         norm1_weight=layer.norm1.weight, norm1_bias=layer.norm1.bias,
+         norm2_weight=layer.norm2.weight, norm2_bias=layer.norm2.bias)
+    return w
+
+
+def decoder_layer_weights(layer, keep) -> DecoderLayerWeights:
+    w = DecoderLayerWeights()
+    w.self_attn = mha_weights(layer.self_attn, keep)
+    w.multihead_attn = mha_weights(layer.multihead_attn, keep)
+    _set(w, keep, linear1_weight=layer.linear1.weight, linear1_bias=layer.linear1.bias,
+         linear2_weight=layer.linear2.weight, linear2_bias=layer.linear2.bias,
+         norm1_weight=layer.norm1.weight, norm1_bias=layer.norm1.bias,
+         norm2_weight=layer.norm2.weight, norm2_bias=layer.norm2.bias,
+         norm3_weight=layer.norm3.weight, norm3_bias=layer.norm3.bias)
+    return w
+
+
+def check_layer_contract(layer, what: str) -> None:
+    """The kernels implement torch's defaults the reference relies on: post-norm, ReLU."""
+    import torch.nn.functional as F
+    if getattr(layer, "norm_first", False):
+        raise NativeError(f"{what}: norm_first=True is not implemented (the reference uses post-norm)")
+    act = getattr(layer, "activation", F.relu)
+    if act is not F.relu and not isinstance(act, torch.nn.ReLU):
+        raise NativeError(f"{what}: only the ReLU activation of the reference is implemented")
+
+
+def weights_version(module: torch.nn.Module):
+    """Changes whenever a parameter/buffer is modified in place or replaced (load_state_dict, .to(), .cuda())."""
+    return tuple((id(t), t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))

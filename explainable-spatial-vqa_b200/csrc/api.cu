@@ -1,0 +1,1099 @@
+// C-ABI layer of libb200vqa.so (include/b200vqa.h): handle lifetime, weight packing, the activation
+// workspace in HBM, and the kernel sequences that replace
+//   VQAModel.forward + autoregressive_program_generation          (IQAP:136-241)
+//   MultiModalTransformer.forward / greedy_decode                 (FA:45-58, 126-146)
+//   run_inference_chain with the inference cache resident in HBM  (FA:83-124)
+// Everything is enqueued on the caller's stream; only the *_host entry points synchronise.
+//
+// HBM layout (per handle, sized for `cap` questions, all row-major):
+//   x, attn, x1, mem   bf16 [cap*256, 256]   encoder rows of question b live at [b*256, b*256+len)
+//   qkv                bf16 [cap*256, 768]   packed q|k|v like torch's in_proj
+//   hid                bf16 [cap*256, ff]
+//   ckv[l]             bf16 [cap*256, 512]   decoder layer l cross-attention K|V of the memory (once per question)
+//   kc[l], vc[l]       bf16 [cap, T, 256]    decoder self-attention KV cache
+//   d*                 bf16 [cap, *]         one decode position per question
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+#include <tuple>
+#include <vector>
+
+#include "host_util.h"
+#include "kernels.h"
+
+using namespace b200vqa;
+
+namespace {
+
+constexpr int kMaxDecodeLen = 64;
+
+struct MhaPacked {
+  __nv_bfloat16* w_in = nullptr;   // [3d, d]
+  float* b_in = nullptr;           // [3d]
+  __nv_bfloat16* w_out = nullptr;  // [d, d]
+  float* b_out = nullptr;
+};
+struct LayerPacked {
+  MhaPacked self_attn, cross_attn;
+  __nv_bfloat16* w1 = nullptr;  // [ff, d]
+  float* b1 = nullptr;
+  __nv_bfloat16* w2 = nullptr;  // [d, ff]
+  float* b2 = nullptr;
+  float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr;
+};
+
+// Bump allocator over one cudaMalloc'ed arena (first pass measures, second pass assigns).
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Workspace {
+  int cap = 0;
+  int t_max = 0;
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *x1 = nullptr, *hid = nullptr, *mem = nullptr;
+  int32_t* lens = nullptr;
+  std::vector<__nv_bfloat16*> ckv, kc, vc;
+  __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dx1 = nullptr, *dq = nullptr, *dx2 = nullptr,
+                *dhid = nullptr, *dxo[2] = {nullptr, nullptr};
+  float* dout = nullptr;
+  __nv_bfloat16* img_t = nullptr;  // FA: transposed + cast image features [cap*196, 1024]
+};
+
+using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t>;
+
+}  // namespace
+
+struct b200vqa_handle {
+  int device = 0;
+  int num_sms = 148;
+  b200vqa_model_desc d{};
+  std::vector<b200vqa_encoder_layer_weights> enc_src;
+  std::vector<b200vqa_decoder_layer_weights> dec_src;
+
+  uint8_t* wbase = nullptr;
+  size_t wbytes = 0;
+  float* img_w_f32 = nullptr;           // IQAP: tf32 operand [d, 1024]
+  __nv_bfloat16* img_w_bf16 = nullptr;  // FA: bf16 operand
+  float *img_b = nullptr, *cls = nullptr, *enc_emb = nullptr, *dec_emb = nullptr, *pe_enc = nullptr, *pe_dec = nullptr;
+  std::vector<LayerPacked> enc, dec;
+  float *enc_fn_w = nullptr, *enc_fn_b = nullptr, *dec_fn_w = nullptr, *dec_fn_b = nullptr;
+  float *head_wt = nullptr, *head_b = nullptr;  // [d, V] transposed
+  float *ans_w0t = nullptr, *ans_b0 = nullptr, *ans_w1 = nullptr, *ans_b1 = nullptr;
+
+  Workspace ws;
+  std::map<TmapKey, CUtensorMap> tmaps;
+  uint64_t launches = 0;
+
+  // host-buffer entry point
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  uint8_t* stage = nullptr;
+  size_t stage_bytes = 0;
+};
+
+namespace {
+
+int default_cap(const b200vqa_handle* h) { return h->d.kind == B200VQA_MODEL_IQAP ? 512 : 1024; }
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+void layout_mha(Arena& a, MhaPacked& m, int d) {
+  m.w_in = a.take<__nv_bfloat16>(size_t(3) * d * d);
+  m.b_in = a.take<float>(size_t(3) * d);
+  m.w_out = a.take<__nv_bfloat16>(size_t(d) * d);
+  m.b_out = a.take<float>(d);
+}
+
+void layout_weights(b200vqa_handle* h, Arena& a) {
+  const auto& d = h->d;
+  const int D = d.d_model;
+  if (d.kind == B200VQA_MODEL_IQAP) h->img_w_f32 = a.take<float>(size_t(D) * d.img_feat_dim);
+  else h->img_w_bf16 = a.take<__nv_bfloat16>(size_t(D) * d.img_feat_dim);
+  h->img_b = a.take<float>(D);
+  h->cls = d.cls_token ? a.take<float>(D) : nullptr;
+  h->enc_emb = a.take<float>(size_t(d.enc_vocab) * D);
+  h->dec_emb = a.take<float>(size_t(d.dec_vocab) * D);
+  h->pe_enc = a.take<float>(size_t(d.pe_enc_len) * D);
+  h->pe_dec = a.take<float>(size_t(d.pe_dec_len) * D);
+  h->enc.resize(d.n_enc_layers);
+  h->dec.resize(d.n_dec_layers);
+  for (auto& L : h->enc) {
+    layout_mha(a, L.self_attn, D);
+    L.w1 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
+    L.b1 = a.take<float>(d.dim_ff);
+    L.w2 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
+    L.b2 = a.take<float>(D);
+    L.n1w = a.take<float>(D); L.n1b = a.take<float>(D); L.n2w = a.take<float>(D); L.n2b = a.take<float>(D);
+  }
+  for (auto& L : h->dec) {
+    layout_mha(a, L.self_attn, D);
+    layout_mha(a, L.cross_attn, D);
+    L.w1 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
+    L.b1 = a.take<float>(d.dim_ff);
+    L.w2 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
+    L.b2 = a.take<float>(D);
+    L.n1w = a.take<float>(D); L.n1b = a.take<float>(D); L.n2w = a.take<float>(D); L.n2b = a.take<float>(D);
+    L.n3w = a.take<float>(D); L.n3b = a.take<float>(D);
+  }
+  if (d.enc_final_norm_weight) { h->enc_fn_w = a.take<float>(D); h->enc_fn_b = a.take<float>(D); }
+  if (d.dec_final_norm_weight) { h->dec_fn_w = a.take<float>(D); h->dec_fn_b = a.take<float>(D); }
+  h->head_wt = a.take<float>(size_t(D) * d.dec_vocab);
+  h->head_b = a.take<float>(d.dec_vocab);
+  if (d.kind == B200VQA_MODEL_IQAP) {
+    h->ans_w0t = a.take<float>(size_t(D) * d.answer_hidden);
+    h->ans_b0 = a.take<float>(d.answer_hidden);
+    h->ans_w1 = a.take<float>(size_t(d.num_classes) * d.answer_hidden);
+    h->ans_b1 = a.take<float>(d.num_classes);
+  }
+}
+
+#define PACK_OK(expr)                       \
+  do {                                      \
+    cudaError_t e_ = (expr);                \
+    if (e_ != cudaSuccess) return e_;       \
+  } while (0)
+
+cudaError_t copy_f32(float* dst, const float* src, size_t n, cudaStream_t s) {
+  return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+}
+
+cudaError_t pack_mha(const b200vqa_mha_weights& w, MhaPacked& m, int D, cudaStream_t s) {
+  PACK_OK(launch_cast_bf16(w.in_proj_weight, m.w_in, size_t(3) * D * D, s));
+  PACK_OK(copy_f32(m.b_in, w.in_proj_bias, size_t(3) * D, s));
+  PACK_OK(launch_cast_bf16(w.out_proj_weight, m.w_out, size_t(D) * D, s));
+  PACK_OK(copy_f32(m.b_out, w.out_proj_bias, D, s));
+  return cudaSuccess;
+}
+
+cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
+  const auto& d = h->d;
+  const int D = d.d_model;
+  if (h->img_w_f32) PACK_OK(copy_f32(h->img_w_f32, d.image_proj_weight, size_t(D) * d.img_feat_dim, s));
+  else PACK_OK(launch_cast_bf16(d.image_proj_weight, h->img_w_bf16, size_t(D) * d.img_feat_dim, s));
+  PACK_OK(copy_f32(h->img_b, d.image_proj_bias, D, s));
+  if (h->cls) PACK_OK(copy_f32(h->cls, d.cls_token, D, s));
+  PACK_OK(copy_f32(h->enc_emb, d.enc_embedding, size_t(d.enc_vocab) * D, s));
+  PACK_OK(copy_f32(h->dec_emb, d.dec_embedding, size_t(d.dec_vocab) * D, s));
+  PACK_OK(copy_f32(h->pe_enc, d.pe_enc, size_t(d.pe_enc_len) * D, s));
+  PACK_OK(copy_f32(h->pe_dec, d.pe_dec, size_t(d.pe_dec_len) * D, s));
+  for (int l = 0; l < d.n_enc_layers; ++l) {
+    const auto& w = h->enc_src[l];
+    auto& L = h->enc[l];
+    PACK_OK(pack_mha(w.self_attn, L.self_attn, D, s));
+    PACK_OK(launch_cast_bf16(w.linear1_weight, L.w1, size_t(d.dim_ff) * D, s));
+    PACK_OK(copy_f32(L.b1, w.linear1_bias, d.dim_ff, s));
+    PACK_OK(launch_cast_bf16(w.linear2_weight, L.w2, size_t(d.dim_ff) * D, s));
+    PACK_OK(copy_f32(L.b2, w.linear2_bias, D, s));
+    PACK_OK(copy_f32(L.n1w, w.norm1_weight, D, s)); PACK_OK(copy_f32(L.n1b, w.norm1_bias, D, s));
+    PACK_OK(copy_f32(L.n2w, w.norm2_weight, D, s)); PACK_OK(copy_f32(L.n2b, w.norm2_bias, D, s));
+  }
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    const auto& w = h->dec_src[l];
+    auto& L = h->dec[l];
+    PACK_OK(pack_mha(w.self_attn, L.self_attn, D, s));
+    PACK_OK(pack_mha(w.multihead_attn, L.cross_attn, D, s));
+    PACK_OK(launch_cast_bf16(w.linear1_weight, L.w1, size_t(d.dim_ff) * D, s));
+    PACK_OK(copy_f32(L.b1, w.linear1_bias, d.dim_ff, s));
+    PACK_OK(launch_cast_bf16(w.linear2_weight, L.w2, size_t(d.dim_ff) * D, s));
+    PACK_OK(copy_f32(L.b2, w.linear2_bias, D, s));
+    PACK_OK(copy_f32(L.n1w, w.norm1_weight, D, s)); PACK_OK(copy_f32(L.n1b, w.norm1_bias, D, s));
+    PACK_OK(copy_f32(L.n2w, w.norm2_weight, D, s)); PACK_OK(copy_f32(L.n2b, w.norm2_bias, D, s));
+    PACK_OK(copy_f32(L.n3w, w.norm3_weight, D, s)); PACK_OK(copy_f32(L.n3b, w.norm3_bias, D, s));
+  }
+  if (h->enc_fn_w) {
+    PACK_OK(copy_f32(h->enc_fn_w, d.enc_final_norm_weight, D, s));
+    PACK_OK(copy_f32(h->enc_fn_b, d.enc_final_norm_bias, D, s));
+  }
+  if (h->dec_fn_w) {
+    PACK_OK(copy_f32(h->dec_fn_w, d.dec_final_norm_weight, D, s));
+    PACK_OK(copy_f32(h->dec_fn_b, d.dec_final_norm_bias, D, s));
+  }
+  PACK_OK(launch_transpose_f32(d.head_weight, h->head_wt, d.dec_vocab, D, s));
+  PACK_OK(copy_f32(h->head_b, d.head_bias, d.dec_vocab, s));
+  if (d.kind == B200VQA_MODEL_IQAP) {
+    PACK_OK(launch_transpose_f32(d.answer_w0, h->ans_w0t, d.answer_hidden, D, s));
+    PACK_OK(copy_f32(h->ans_b0, d.answer_b0, d.answer_hidden, s));
+    PACK_OK(copy_f32(h->ans_w1, d.answer_w1, size_t(d.num_classes) * d.answer_hidden, s));
+    PACK_OK(copy_f32(h->ans_b1, d.answer_b1, d.num_classes, s));
+  }
+  return cudaSuccess;
+}
+
+int validate_desc(const b200vqa_model_desc* d) {
+  B200VQA_REQUIRE(d != nullptr, "model descriptor is NULL");
+  B200VQA_REQUIRE(d->kind == B200VQA_MODEL_IQAP || d->kind == B200VQA_MODEL_FA, "unknown model kind %d", d->kind);
+  if (d->d_model != kD) {
+    set_error("d_model %d: the sm_100a kernels are specialised for d_model = %d", d->d_model, kD);
+    return B200VQA_ERR_UNSUPPORTED_SHAPE;
+  }
+  if (d->nhead != 2 && d->nhead != 4) {
+    set_error("nhead %d: supported head counts are 2 and 4 (head dim 128 / 64)", d->nhead);
+    return B200VQA_ERR_UNSUPPORTED_SHAPE;
+  }
+  if (d->dim_ff <= 0 || d->dim_ff % 256 != 0 || d->img_feat_dim % 32 != 0 || d->n_img_tokens <= 0 ||
+      d->n_img_tokens > 200) {
+    set_error("unsupported shape: dim_ff %d (multiple of 256), img_feat_dim %d (multiple of 32), n_img_tokens %d",
+              d->dim_ff, d->img_feat_dim, d->n_img_tokens);
+    return B200VQA_ERR_UNSUPPORTED_SHAPE;
+  }
+  B200VQA_REQUIRE(d->n_enc_layers >= 1 && d->n_enc_layers <= 16 && d->n_dec_layers >= 1 && d->n_dec_layers <= 16,
+                  "layer counts out of range (%d encoder, %d decoder)", d->n_enc_layers, d->n_dec_layers);
+  B200VQA_REQUIRE(d->enc_vocab > 0 && d->dec_vocab > 0 && d->pe_enc_len > 0 && d->pe_dec_len > 0,
+                  "vocabulary / positional table sizes must be positive");
+  B200VQA_REQUIRE(d->image_proj_weight && d->image_proj_bias && d->enc_embedding && d->dec_embedding && d->pe_enc &&
+                      d->pe_dec && d->enc_layers && d->dec_layers && d->head_weight && d->head_bias,
+                  "a required weight pointer is NULL");
+  if (d->kind == B200VQA_MODEL_IQAP) {
+    B200VQA_REQUIRE(d->cls_token && d->answer_w0 && d->answer_b0 && d->answer_w1 && d->answer_b1,
+                    "IQAP needs cls_token and the answer classifier weights");
+    B200VQA_REQUIRE(d->answer_hidden > 0 && d->answer_hidden <= 1024 && d->num_classes > 0,
+                    "answer head sizes out of range (hidden %d, classes %d)", d->answer_hidden, d->num_classes);
+    if (1 + d->n_img_tokens + d->max_q_len > kLP || d->pe_enc_len < 1 + d->n_img_tokens + d->max_q_len) {
+      set_error("IQAP sequence 1+%d+%d exceeds %d rows or the positional table (%d)", d->n_img_tokens, d->max_q_len,
+                kLP, d->pe_enc_len);
+      return B200VQA_ERR_UNSUPPORTED_SHAPE;
+    }
+  } else {
+    B200VQA_REQUIRE(d->pe_enc_len > d->n_img_tokens, "FA positional table shorter than the image tokens");
+  }
+  return B200VQA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, int t_max) {
+  const auto& d = h->d;
+  const size_t rows = size_t(cap) * kLP;
+  w.cap = cap;
+  w.t_max = t_max;
+  w.x = a.take<__nv_bfloat16>(rows * kD);
+  w.qkv = a.take<__nv_bfloat16>(rows * 3 * kD);
+  w.attn = a.take<__nv_bfloat16>(rows * kD);
+  w.x1 = a.take<__nv_bfloat16>(rows * kD);
+  w.hid = a.take<__nv_bfloat16>(rows * d.dim_ff);
+  w.mem = a.take<__nv_bfloat16>(rows * kD);
+  w.lens = a.take<int32_t>(cap);
+  w.ckv.resize(d.n_dec_layers);
+  w.kc.resize(d.n_dec_layers);
+  w.vc.resize(d.n_dec_layers);
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    w.ckv[l] = a.take<__nv_bfloat16>(rows * 2 * kD);
+    w.kc[l] = a.take<__nv_bfloat16>(size_t(cap) * t_max * kD);
+    w.vc[l] = a.take<__nv_bfloat16>(size_t(cap) * t_max * kD);
+  }
+  // decode rows are padded to a whole 128-row tile so TMA boxes stay inside the allocation
+  const size_t drows = (size_t(cap) + 127) / 128 * 128;
+  w.dx = a.take<__nv_bfloat16>(drows * kD);
+  w.dqkv = a.take<__nv_bfloat16>(drows * 3 * kD);
+  w.dattn = a.take<__nv_bfloat16>(drows * kD);
+  w.dx1 = a.take<__nv_bfloat16>(drows * kD);
+  w.dq = a.take<__nv_bfloat16>(drows * kD);
+  w.dx2 = a.take<__nv_bfloat16>(drows * kD);
+  w.dhid = a.take<__nv_bfloat16>(drows * d.dim_ff);
+  w.dxo[0] = a.take<__nv_bfloat16>(drows * kD);
+  w.dxo[1] = a.take<__nv_bfloat16>(drows * kD);
+  w.dout = a.take<float>(drows * kD);
+  if (d.kind == B200VQA_MODEL_FA) w.img_t = a.take<__nv_bfloat16>(size_t(cap) * d.n_img_tokens * d.img_feat_dim);
+}
+
+int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
+  const int cap_want = std::min(B, default_cap(h));
+  if (h->ws.base && h->ws.cap >= cap_want && h->ws.t_max >= t_max) return B200VQA_OK;
+  const int cap = std::max(cap_want, h->ws.cap);
+  const int tm = std::max(t_max, h->ws.t_max);
+  if (h->ws.base) {
+    B200VQA_CUDA_OK(cudaDeviceSynchronize());
+    B200VQA_CUDA_OK(cudaFree(h->ws.base));
+    h->ws = Workspace{};
+    h->tmaps.clear();
+  }
+  Arena measure;
+  Workspace tmp;
+  layout_workspace(h, tmp, measure, cap, tm);
+  uint8_t* base = nullptr;
+  B200VQA_CUDA_OK(cudaMalloc(&base, measure.off + 256));
+  // finite contents everywhere: padding rows feed tensor-core tiles whose results are discarded
+  B200VQA_CUDA_OK(cudaMemset(base, 0, measure.off + 256));
+  Arena a;
+  a.base = base;
+  layout_workspace(h, h->ws, a, cap, tm);
+  h->ws.base = base;
+  h->ws.bytes = measure.off + 256;
+  return B200VQA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM helpers
+// ---------------------------------------------------------------------------------------------
+int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
+             uint32_t box_rows, const CUtensorMap** out) {
+  TmapKey key{base, int(type), rows, cols, ld, box_rows};
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    CUtensorMap m;
+    int rc = make_tmap_2d(&m, base, type, rows, cols, ld, box_rows);
+    if (rc != B200VQA_OK) return rc;
+    it = h->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return B200VQA_OK;
+}
+
+#define RC_OK(expr)                   \
+  do {                                \
+    int rc_ = (expr);                 \
+    if (rc_ != B200VQA_OK) return rc_; \
+  } while (0)
+
+#define LAUNCH_OK(h, expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+      return B200VQA_ERR_CUDA;                                                                    \
+    }                                                                                             \
+    ++(h)->launches;                                                                              \
+  } while (0)
+
+// out = epilogue(A[M,K] . W[N,K]^T + bias), A/W bf16 (or fp32 for tf32) row-major
+int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int lda, const void* W, int N,
+         GemmParams p, cudaStream_t s) {
+  if (M <= 0) return B200VQA_OK;
+  const TmapType ty = tf32 ? TmapType::kF32 : TmapType::kBF16;
+  const int bn = 256;
+  const CUtensorMap *ta, *tw;
+  // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
+  RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(K), uint64_t(lda), 128, &ta));
+  RC_OK(get_tmap(h, W, ty, uint64_t(N), uint64_t(K), uint64_t(K), bn, &tw));
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, p, h->num_sms, s));
+  return B200VQA_OK;
+}
+
+int gemm_bias(b200vqa_handle* h, bool relu, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int N,
+              const float* bias, __nv_bfloat16* out, cudaStream_t s) {
+  GemmParams p;
+  p.bias = bias;
+  p.out = out;
+  p.ldc = N;
+  return gemm(h, relu ? kEpiBiasRelu : kEpiBias, false, A, M, K, K, W, N, p, s);
+}
+
+int gemm_res_ln(b200vqa_handle* h, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
+                const __nv_bfloat16* residual, const float* gamma, const float* beta, __nv_bfloat16* out,
+                float* out_f32, cudaStream_t s) {
+  GemmParams p;
+  p.bias = bias;
+  p.out = out;
+  p.ldc = kD;
+  p.residual = residual;
+  p.ldr = kD;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.eps = h->d.layer_norm_eps;
+  p.out_f32 = out_f32;
+  return gemm(h, kEpiBiasResLN, false, A, M, K, K, W, kD, p, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder: x (bf16 rows, [B*256,256]) -> memory; returns the buffer that holds the memory
+// ---------------------------------------------------------------------------------------------
+int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __nv_bfloat16** memory,
+                cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  const int M = B * kLP;
+  __nv_bfloat16* in = w.x;
+  __nv_bfloat16* out = w.mem;
+  for (int l = 0; l < d.n_enc_layers; ++l) {
+    const LayerPacked& L = h->enc[l];
+    RC_OK(gemm_bias(h, false, in, M, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.qkv, s));
+    {
+      const CUtensorMap *tq, *tkv;
+      RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 128, &tq));
+      RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 256, &tkv));
+      EncAttnParams ap;
+      ap.B = B;
+      ap.nhead = d.nhead;
+      ap.lens = lens;
+      ap.const_len = const_len;
+      ap.out = w.attn;
+      ap.scale = 1.f / sqrtf(float(kD / d.nhead));
+      LAUNCH_OK(h, launch_enc_attention(*tq, *tkv, w.qkv, ap, s));
+    }
+    RC_OK(gemm_res_ln(h, w.attn, M, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.x1, nullptr, s));
+    RC_OK(gemm_bias(h, true, w.x1, M, kD, L.w1, d.dim_ff, L.b1, w.hid, s));
+    RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s));
+    std::swap(in, out);
+  }
+  // `in` now holds the last layer's output
+  if (h->enc_fn_w) LAUNCH_OK(h, launch_layernorm_rows(in, in, h->enc_fn_w, h->enc_fn_b, d.layer_norm_eps, M, s));
+  *memory = in;
+  return B200VQA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder: greedy decode of `steps` positions against `memory`
+// ---------------------------------------------------------------------------------------------
+struct DecodeIO {
+  int start_token = 0;
+  const int64_t* start_tokens = nullptr;  // per-question start (teacher-forced forward)
+  int start_ld = 0;
+  int steps = 0;
+  int64_t* tokens = nullptr;  // [B, tok_ld]
+  int tok_ld = 0;
+  int tok_col0 = 0;           // column of the first generated token (IQAP 0, FA 1)
+  bool write_start = false;   // FA: tokens[b,0] = start
+  int32_t* cache_out = nullptr;
+  long long cache_ld = 0;
+  int cache_store_forced = 0;
+  const int32_t* n_steps = nullptr;
+  int step = 0;
+  float* logits = nullptr;    // [B, logits_T, V]
+  int logits_T = 0;
+  const int64_t* forced = nullptr;
+  int forced_ld = 0;
+};
+
+int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                const DecodeIO& io, cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  const int M = B * kLP;
+  // cross-attention K|V of the memory: once per question (the reference recomputes it every step)
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    const MhaPacked& ca = h->dec[l].cross_attn;
+    RC_OK(gemm_bias(h, false, memory, M, kD, ca.w_in + size_t(kD) * kD, 2 * kD, ca.b_in + kD, w.ckv[l], s));
+  }
+  {
+    DecEmbedParams ep;
+    ep.B = B;
+    ep.emb = h->dec_emb;
+    ep.vocab = d.dec_vocab;
+    ep.pe = h->pe_dec;
+    ep.start_token = std::min(std::max(io.start_token, 0), d.dec_vocab - 1);
+    ep.start_tokens = io.start_tokens;
+    ep.start_ld = io.start_ld;
+    ep.x = w.dx;
+    ep.tokens = io.write_start ? io.tokens : nullptr;
+    ep.tok_ld = io.tok_ld;
+    ep.cache_out = io.cache_out;
+    ep.cache_ld = io.cache_ld;
+    ep.n_steps = io.n_steps;
+    ep.step = io.step;
+    LAUNCH_OK(h, launch_dec_embed_start(ep, s));
+  }
+  for (int t = 0; t < io.steps; ++t) {
+    const __nv_bfloat16* in = w.dx;
+    for (int l = 0; l < d.n_dec_layers; ++l) {
+      const LayerPacked& L = h->dec[l];
+      const bool last = l == d.n_dec_layers - 1;
+      __nv_bfloat16* out = w.dxo[l & 1];
+      RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.dqkv, s));
+      DecSelfAttnParams sp;
+      sp.B = B;
+      sp.nhead = d.nhead;
+      sp.t = t;
+      sp.t_max = w.t_max;
+      sp.qkv = w.dqkv;
+      sp.k_cache = w.kc[l];
+      sp.v_cache = w.vc[l];
+      sp.out = w.dattn;
+      LAUNCH_OK(h, launch_dec_self_attn(sp, s));
+      RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.dx1, nullptr, s));
+      RC_OK(gemm_bias(h, false, w.dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, w.dq, s));
+      DecCrossAttnParams cp;
+      cp.B = B;
+      cp.nhead = d.nhead;
+      cp.q = w.dq;
+      cp.kv = w.ckv[l];
+      cp.ld_kv = 2 * kD;
+      cp.k_col = 0;
+      cp.v_col = kD;
+      cp.lens = lens;
+      cp.const_len = const_len;
+      cp.out = w.dattn;
+      LAUNCH_OK(h, launch_dec_cross_attn(cp, s));
+      RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, w.dx1, L.n2w, L.n2b, w.dx2, nullptr,
+                        s));
+      RC_OK(gemm_bias(h, true, w.dx2, B, kD, L.w1, d.dim_ff, L.b1, w.dhid, s));
+      RC_OK(gemm_res_ln(h, w.dhid, B, d.dim_ff, L.w2, L.b2, w.dx2, L.n3w, L.n3b, out, last ? w.dout : nullptr, s));
+      in = out;
+    }
+    DecHeadParams hp;
+    hp.B = B;
+    hp.V = d.dec_vocab;
+    hp.t = t;
+    hp.x_f32 = w.dout;
+    hp.fn_gamma = h->dec_fn_w;
+    hp.fn_beta = h->dec_fn_b;
+    hp.eps = d.layer_norm_eps;
+    hp.w_t = h->head_wt;
+    hp.bias = h->head_b;
+    hp.tokens = io.tokens;
+    hp.tok_ld = io.tok_ld;
+    hp.tok_col = io.tok_col0 + t;
+    hp.logits = io.logits;
+    hp.logits_T = io.logits_T;
+    hp.forced = io.forced;
+    hp.forced_ld = io.forced_ld;
+    hp.emb = h->dec_emb;
+    hp.vocab = d.dec_vocab;
+    hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
+    hp.x_next = w.dx;
+    hp.cache_out = io.cache_out;
+    hp.cache_ld = io.cache_ld;
+    hp.cache_store_forced = io.cache_store_forced;
+    hp.n_steps = io.n_steps;
+    hp.step = io.step;
+    LAUNCH_OK(h, launch_dec_head(hp, s));
+  }
+  return B200VQA_OK;
+}
+
+int check_decode_len(const b200vqa_handle* h, int steps) {
+  if (steps < 1 || steps > kMaxDecodeLen || steps > h->d.pe_dec_len) {
+    set_error("decode length %d out of range (1..%d, positional table %d)", steps, kMaxDecodeLen, h->d.pe_dec_len);
+    return B200VQA_ERR_BAD_ARGUMENT;
+  }
+  return B200VQA_OK;
+}
+
+int set_device(const b200vqa_handle* h) {
+  B200VQA_CUDA_OK(cudaSetDevice(h->device));
+  return B200VQA_OK;
+}
+
+int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int T, float* answer, int64_t* programs,
+               float* step_logits, const int64_t* forced, float* opt_memory, int B_total, int b0, cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  const int S = 1 + d.n_img_tokens + d.max_q_len;
+  LAUNCH_OK(h, launch_iqap_embed(q, B, d.max_q_len, h->cls, h->enc_emb, d.enc_vocab, h->pe_enc, d.n_img_tokens, w.x, s));
+  {
+    // image_proj straight from the caller's fp32 features (tf32 tensor-core math), +bias +PE, written into
+    // rows 1..196 of each question's block (this is the reference's torch.cat, IQAP:164)
+    GemmParams p;
+    p.bias = h->img_b;
+    p.out = w.x;
+    p.ldc = kD;
+    p.rows_in = d.n_img_tokens;
+    p.rows_out = kLP;
+    p.row_off = 1;
+    p.pe = h->pe_enc;
+    p.pe_off = 1;
+    RC_OK(gemm(h, kEpiBiasPeRemap, true, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD, p,
+               s));
+  }
+  __nv_bfloat16* memory = nullptr;
+  RC_OK(run_encoder(h, B, nullptr, S, &memory, s));
+  if (opt_memory) {
+    // seq-first [S, B_total, d]: this chunk fills columns b0..b0+B
+    LAUNCH_OK(h, launch_memory_export(memory, S, B, B_total, opt_memory + size_t(b0) * kD, s));
+  }
+  LAUNCH_OK(h, launch_answer_head(memory, B, h->ans_w0t, h->ans_b0, d.answer_hidden, h->ans_w1, h->ans_b1,
+                                  d.num_classes, answer, s));
+  DecodeIO io;
+  io.start_token = 1;  // Config.SPECIAL_TOKEN_ID (IQAP:24,205)
+  io.steps = T;
+  io.tokens = programs;
+  io.tok_ld = T;
+  io.tok_col0 = 0;
+  io.logits = step_logits;
+  io.logits_T = T;
+  io.forced = forced;
+  io.forced_ld = T;
+  return run_decoder(h, B, memory, nullptr, S, io, s);
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported symbols
+// =================================================================================================
+extern "C" {
+
+B200VQA_API const char* b200vqa_last_error(void) { return get_error(); }
+B200VQA_API const char* b200vqa_version(void) { return "b200vqa 0.1 (sm_100a)"; }
+
+B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200vqa_handle** out) {
+  B200VQA_REQUIRE(out != nullptr, "out handle pointer is NULL");
+  *out = nullptr;
+  RC_OK(validate_desc(desc));
+  int num_sms = 0;
+  RC_OK(require_sm100(device, &num_sms));
+  B200VQA_CUDA_OK(cudaSetDevice(device));
+  b200vqa_handle* h = new (std::nothrow) b200vqa_handle();
+  if (!h) {
+    set_error("out of host memory");
+    return B200VQA_ERR_OUT_OF_MEMORY;
+  }
+  h->device = device;
+  h->num_sms = num_sms;
+  h->d = *desc;
+  h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
+  h->dec_src.assign(desc->dec_layers, desc->dec_layers + desc->n_dec_layers);
+  h->d.enc_layers = nullptr;
+  h->d.dec_layers = nullptr;
+  Arena measure;
+  layout_weights(h, measure);
+  h->wbytes = measure.off + 256;
+  cudaError_t e = cudaMalloc(&h->wbase, h->wbytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) for packed weights failed: %s", h->wbytes, cudaGetErrorString(e));
+    delete h;
+    return B200VQA_ERR_OUT_OF_MEMORY;
+  }
+  Arena a;
+  a.base = h->wbase;
+  layout_weights(h, a);
+  e = pack_weights(h, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) {
+    set_error("weight packing failed: %s", cudaGetErrorString(e));
+    cudaFree(h->wbase);
+    delete h;
+    return B200VQA_ERR_CUDA;
+  }
+  *out = h;
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_refresh_weights(b200vqa_handle* h, const b200vqa_model_desc* desc) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  RC_OK(validate_desc(desc));
+  const auto& o = h->d;
+  B200VQA_REQUIRE(desc->kind == o.kind && desc->nhead == o.nhead && desc->n_enc_layers == o.n_enc_layers &&
+                      desc->n_dec_layers == o.n_dec_layers && desc->dim_ff == o.dim_ff &&
+                      desc->enc_vocab == o.enc_vocab && desc->dec_vocab == o.dec_vocab &&
+                      desc->pe_enc_len == o.pe_enc_len && desc->pe_dec_len == o.pe_dec_len &&
+                      desc->answer_hidden == o.answer_hidden && desc->num_classes == o.num_classes &&
+                      desc->img_feat_dim == o.img_feat_dim,
+                  "refresh_weights: the new descriptor has different dimensions; create a new handle");
+  RC_OK(set_device(h));
+  h->d = *desc;
+  h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
+  h->dec_src.assign(desc->dec_layers, desc->dec_layers + desc->n_dec_layers);
+  h->d.enc_layers = nullptr;
+  h->d.dec_layers = nullptr;
+  B200VQA_CUDA_OK(cudaDeviceSynchronize());
+  B200VQA_CUDA_OK(pack_weights(h, nullptr));
+  B200VQA_CUDA_OK(cudaStreamSynchronize(nullptr));
+  return B200VQA_OK;
+}
+
+B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->ws.base) cudaFree(h->ws.base);
+  if (h->wbase) cudaFree(h->wbase);
+  if (h->stage) cudaFree(h->stage);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B) {
+  if (!h || B <= 0) return 0;
+  Arena measure;
+  Workspace tmp;
+  layout_workspace(h, tmp, measure, std::min(B, default_cap(h)), 32);
+  return measure.off + 256;
+}
+
+B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ IQAP
+B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_features, const int64_t* questions, int B,
+                         int program_len, float* answer, int64_t* programs, float* opt_step_logits,
+                         const int64_t* opt_forced_tokens, float* opt_memory, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(image_features && questions && answer && programs, "a required buffer is NULL");
+  RC_OK(check_decode_len(h, program_len));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, program_len));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  const int cap = h->ws.cap;
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    RC_OK(iqap_chunk(h, image_features + size_t(b0) * d.n_img_tokens * d.img_feat_dim,
+                     questions + size_t(b0) * d.max_q_len, nb, program_len, answer + size_t(b0) * d.num_classes,
+                     programs + size_t(b0) * program_len,
+                     opt_step_logits ? opt_step_logits + size_t(b0) * program_len * d.dec_vocab : nullptr,
+                     opt_forced_tokens ? opt_forced_tokens + size_t(b0) * program_len : nullptr, opt_memory, B, b0,
+                     s));
+  }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int S, int B, int program_len, int64_t* programs,
+                        float* opt_step_logits, const int64_t* opt_forced_tokens, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0 && S >= 1 && S <= kLP, "memory shape out of range (S %d, B %d)", S, B);
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(memory && programs, "a required buffer is NULL");
+  RC_OK(check_decode_len(h, program_len));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, program_len));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cap = h->ws.cap;
+  const int V = h->d.dec_vocab;
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    // seq-first memory interleaves questions: a chunk is the column range [b0, b0+nb) of every row
+    LAUNCH_OK(h, launch_memory_import(memory + size_t(b0) * kD, S, nb, B, h->ws.mem, s));
+    DecodeIO io;
+    io.start_token = 1;
+    io.steps = program_len;
+    io.tokens = programs + size_t(b0) * program_len;
+    io.tok_ld = program_len;
+    io.logits = opt_step_logits ? opt_step_logits + size_t(b0) * program_len * V : nullptr;
+    io.logits_T = program_len;
+    io.forced = opt_forced_tokens ? opt_forced_tokens + size_t(b0) * program_len : nullptr;
+    io.forced_ld = program_len;
+    RC_OK(run_decoder(h, nb, h->ws.mem, nullptr, S, io, s));
+  }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
+                              float* h_answer, int64_t* h_programs, int chunk, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(h_img && h_q && h_answer && h_programs, "a required buffer is NULL");
+  RC_OK(check_decode_len(h, program_len));
+  RC_OK(set_device(h));
+  const auto& d = h->d;
+  if (chunk <= 0) chunk = 128;
+  chunk = std::min({chunk, B, default_cap(h)});
+  RC_OK(ensure_workspace(h, chunk, program_len));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->copy_stream) {
+    B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  // staging: 2 x (features + questions) for the double-buffered upload, + results for the whole batch
+  const size_t img_b = size_t(chunk) * d.n_img_tokens * d.img_feat_dim * sizeof(float);
+  const size_t q_b = (size_t(chunk) * d.max_q_len * sizeof(int64_t) + 255) & ~size_t(255);
+  const size_t ans_b = (size_t(B) * d.num_classes * sizeof(float) + 255) & ~size_t(255);
+  const size_t prog_b = (size_t(B) * program_len * sizeof(int64_t) + 255) & ~size_t(255);
+  const size_t need = 2 * (img_b + q_b) + ans_b + prog_b;
+  if (h->stage_bytes < need) {
+    if (h->stage) {
+      B200VQA_CUDA_OK(cudaDeviceSynchronize());
+      B200VQA_CUDA_OK(cudaFree(h->stage));
+      h->stage = nullptr;
+      h->stage_bytes = 0;
+      h->tmaps.clear();
+    }
+    B200VQA_CUDA_OK(cudaMalloc(&h->stage, need));
+    h->stage_bytes = need;
+  }
+  uint8_t* p = h->stage;
+  float* d_img[2];
+  int64_t* d_q[2];
+  for (int i = 0; i < 2; ++i) {
+    d_img[i] = reinterpret_cast<float*>(p); p += img_b;
+    d_q[i] = reinterpret_cast<int64_t*>(p); p += q_b;
+  }
+  float* d_ans = reinterpret_cast<float*>(p); p += ans_b;
+  int64_t* d_prog = reinterpret_cast<int64_t*>(p);
+
+  int it = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++it) {
+    const int nb = std::min(chunk, B - b0);
+    const int slot = it & 1;
+    if (it >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot], h_img + size_t(b0) * d.n_img_tokens * d.img_feat_dim,
+                                    size_t(nb) * d.n_img_tokens * d.img_feat_dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, h->copy_stream));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_q[slot], h_q + size_t(b0) * d.max_q_len,
+                                    size_t(nb) * d.max_q_len * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                    h->copy_stream));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[slot], h->copy_stream));
+    B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[slot], 0));
+    RC_OK(iqap_chunk(h, d_img[slot], d_q[slot], nb, program_len, d_ans + size_t(b0) * d.num_classes,
+                     d_prog + size_t(b0) * program_len, nullptr, nullptr, nullptr, B, b0, s));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[slot], s));
+  }
+  B200VQA_CUDA_OK(cudaMemcpyAsync(h_answer, d_ans, size_t(B) * d.num_classes * sizeof(float), cudaMemcpyDeviceToHost, s));
+  B200VQA_CUDA_OK(cudaMemcpyAsync(h_programs, d_prog, size_t(B) * program_len * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, s));
+  B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  return B200VQA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ FA
+B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_features, int B, void* img_tokens_bf16,
+                              void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
+  B200VQA_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(image_features && img_tokens_bf16, "a required buffer is NULL");
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, 20));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  const int cap = h->ws.cap;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(img_tokens_bf16);
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    // channel-major fp32 [nb,1024,196] -> token-major bf16 [nb*196,1024] (the reference's view+permute, FA:47,130)
+    LAUNCH_OK(h, launch_transpose_cast(image_features + size_t(b0) * d.img_feat_dim * d.n_img_tokens, h->ws.img_t, nb,
+                                       d.img_feat_dim, d.n_img_tokens, s));
+    GemmParams p;
+    p.bias = h->img_b;
+    p.out = out + size_t(b0) * d.n_img_tokens * kD;
+    p.ldc = kD;
+    p.rows_in = d.n_img_tokens;
+    p.rows_out = d.n_img_tokens;
+    p.row_off = 0;
+    p.pe = h->pe_enc;
+    p.pe_off = 0;
+    RC_OK(gemm(h, kEpiBiasPeRemap, false, h->ws.img_t, nb * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim,
+               h->img_w_bf16, kD, p, s));
+  }
+  return B200VQA_OK;
+}
+
+static int fa_one_step(b200vqa_handle* h, const __nv_bfloat16* img_tokens, FaBuildSrcParams bp, int B, DecodeIO io,
+                       cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  bp.B = B;
+  bp.img_tokens = img_tokens;
+  bp.emb = h->enc_emb;
+  bp.vocab = d.enc_vocab;
+  bp.pe = h->pe_enc;
+  bp.pe_len = d.pe_enc_len;
+  bp.n_img = d.n_img_tokens;
+  bp.x = w.x;
+  bp.lens = w.lens;
+  LAUNCH_OK(h, launch_fa_build_src(bp, s));
+  __nv_bfloat16* memory = nullptr;
+  RC_OK(run_encoder(h, B, w.lens, 0, &memory, s));
+  return run_decoder(h, B, memory, w.lens, 0, io, s);
+}
+
+B200VQA_API int b200vqa_fa_step(b200vqa_handle* h, const void* img_tokens_bf16, const int64_t* src, const int32_t* src_len,
+                    int src_ld, int B, int start_token, int max_len, int64_t* out_tokens, float* opt_logits,
+                    const int64_t* opt_forced, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
+  B200VQA_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(img_tokens_bf16 && src && out_tokens, "a required buffer is NULL");
+  B200VQA_REQUIRE(src_ld >= 0 && src_ld <= 60 && h->d.n_img_tokens + src_ld <= h->d.pe_enc_len,
+                  "src length %d exceeds the encoder positional table (%d rows, %d image tokens) or 60 tokens",
+                  src_ld, h->d.pe_enc_len, h->d.n_img_tokens);
+  B200VQA_REQUIRE(max_len >= 2, "max_len must be at least 2");
+  RC_OK(check_decode_len(h, max_len - 1));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, max_len - 1));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  const int cap = h->ws.cap;
+  const int T = max_len - 1;
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    FaBuildSrcParams bp;
+    bp.src_direct = src + size_t(b0) * src_ld;
+    bp.src_len_in = src_len ? src_len + b0 : nullptr;
+    bp.src_ld = src_ld;
+    DecodeIO io;
+    io.start_token = start_token;
+    io.steps = T;
+    io.tokens = out_tokens + size_t(b0) * max_len;
+    io.tok_ld = max_len;
+    io.tok_col0 = 1;
+    io.write_start = true;
+    io.logits = opt_logits ? opt_logits + size_t(b0) * T * d.dec_vocab : nullptr;
+    io.logits_T = T;
+    io.forced = opt_forced ? opt_forced + size_t(b0) * T : nullptr;
+    io.forced_ld = T;
+    RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp, nb,
+                      io, s));
+  }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_fa_forward(b200vqa_handle* h, const void* img_tokens_bf16, const int64_t* src,
+                                   const int32_t* src_len, int src_ld, int B, const int64_t* tgt, int T, float* logits,
+                                   void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
+  B200VQA_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(img_tokens_bf16 && src && tgt && logits, "a required buffer is NULL");
+  B200VQA_REQUIRE(src_ld >= 0 && src_ld <= 60 && h->d.n_img_tokens + src_ld <= h->d.pe_enc_len,
+                  "src length %d exceeds the encoder positional table (%d rows, %d image tokens) or 60 tokens",
+                  src_ld, h->d.pe_enc_len, h->d.n_img_tokens);
+  RC_OK(check_decode_len(h, T));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, T));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  const int cap = h->ws.cap;
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    FaBuildSrcParams bp;
+    bp.src_direct = src + size_t(b0) * src_ld;
+    bp.src_len_in = src_len ? src_len + b0 : nullptr;
+    bp.src_ld = src_ld;
+    DecodeIO io;
+    io.start_tokens = tgt + size_t(b0) * T;
+    io.start_ld = T;
+    io.steps = T;
+    io.logits = logits + size_t(b0) * T * d.dec_vocab;
+    io.logits_T = T;
+    io.forced = tgt + size_t(b0) * T + 1;  // position t+1 is fed tgt[b, t+1]; never read at t = T-1
+    io.forced_ld = T;
+    RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp, nb,
+                      io, s));
+  }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_bf16, const int32_t* func, const int32_t* deps,
+                         const int32_t* n_steps, int B, int S, int start_token, int max_len, int32_t* cache,
+                         const int32_t* h_active, float* opt_logits, const int64_t* opt_forced, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
+  B200VQA_REQUIRE(B >= 0 && S >= 0, "negative batch or step count");
+  if (B == 0 || S == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(img_tokens_bf16 && func && deps && n_steps && cache, "a required buffer is NULL");
+  B200VQA_REQUIRE(max_len >= 2 && 1 + 2 * max_len <= 60, "max_len %d out of range (2..29)", max_len);
+  B200VQA_REQUIRE(h->d.n_img_tokens + 1 + 2 * max_len <= std::min(h->d.pe_enc_len, kLP),
+                  "1 + 2*max_len source tokens exceed the encoder positional table (%d rows)", h->d.pe_enc_len);
+  RC_OK(check_decode_len(h, max_len - 1));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, max_len - 1));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  const int cap = h->ws.cap;
+  const int T = max_len - 1;
+  // questions are independent, steps of one question are sequential: chunk over questions, loop steps inside
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb_full = std::min(cap, B - b0);
+    for (int i = 0; i < S; ++i) {
+      int nb = nb_full;
+      if (h_active) nb = std::max(0, std::min(nb_full, h_active[i] - b0));
+      if (nb == 0) continue;
+      FaBuildSrcParams bp;
+      bp.step = i;
+      bp.S = S;
+      bp.T = max_len;
+      bp.func = func + size_t(b0) * S;
+      bp.deps = deps + size_t(b0) * S * 2;
+      bp.n_steps = n_steps + b0;
+      bp.cache = cache + size_t(b0) * S * max_len;
+      DecodeIO io;
+      io.start_token = start_token;
+      io.steps = T;
+      io.tok_col0 = 1;
+      io.cache_out = cache + (size_t(b0) * S + i) * max_len;
+      io.cache_ld = (long long)S * max_len;
+      io.cache_store_forced = opt_forced ? 1 : 0;
+      io.n_steps = n_steps + b0;
+      io.step = i;
+      io.logits = opt_logits ? opt_logits + (size_t(b0) * S + i) * T * d.dec_vocab : nullptr;
+      io.logits_T = S * T;  // row (b, i, t) = b*S*T + i*T + t
+      io.forced = opt_forced ? opt_forced + (size_t(b0) * S + i) * T : nullptr;
+      io.forced_ld = S * T;
+      RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp,
+                        nb, io, s));
+    }
+  }
+  return B200VQA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
+  B200VQA_REQUIRE(a != nullptr, "args is NULL");
+  int dev = 0, num_sms = 0;
+  B200VQA_CUDA_OK(cudaGetDevice(&dev));
+  RC_OK(require_sm100(dev, &num_sms));
+  const TmapType ty = a->tf32 ? TmapType::kF32 : TmapType::kBF16;
+  CUtensorMap ta, tw;
+  RC_OK(make_tmap_2d(&ta, a->A, ty, uint64_t(a->M), uint64_t(a->K), uint64_t(a->K), 128));
+  RC_OK(make_tmap_2d(&tw, a->W, ty, uint64_t(a->N), uint64_t(a->K), uint64_t(a->K), uint32_t(a->block_n)));
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.ldc = a->ldc;
+  p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  p.ldr = a->N;
+  p.gamma = a->gamma;
+  p.beta = a->beta;
+  p.out_f32 = a->out_f32;
+  p.rows_in = a->rows_in > 0 ? a->rows_in : 1;
+  p.rows_out = a->rows_out > 0 ? a->rows_out : 1;
+  p.row_off = a->row_off;
+  p.pe = a->pe;
+  p.pe_off = a->pe_off;
+  B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, p, num_sms, static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_dbg_gemm_check(int a_is_f32, const void* A, const void* W, const float* bias, float* out, int M, int N,
+                           int K, void* stream) {
+  B200VQA_CUDA_OK(launch_gemm_check(a_is_f32 != 0, A, W, bias, out, M, N, K, static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, int const_len, int B, int nhead, int v_mode,
+                              void* out, void* stream) {
+  B200VQA_REQUIRE(qkv && out && B > 0 && (nhead == 2 || nhead == 4), "bad arguments");
+  int dev = 0;
+  B200VQA_CUDA_OK(cudaGetDevice(&dev));
+  RC_OK(require_sm100(dev, nullptr));
+  CUtensorMap tq, tkv;
+  RC_OK(make_tmap_2d(&tq, qkv, TmapType::kBF16, uint64_t(B) * kLP, 3 * kD, 3 * kD, 128));
+  RC_OK(make_tmap_2d(&tkv, qkv, TmapType::kBF16, uint64_t(B) * kLP, 3 * kD, 3 * kD, 256));
+  EncAttnParams ap;
+  ap.B = B;
+  ap.nhead = nhead;
+  ap.lens = lens;
+  ap.const_len = const_len;
+  ap.out = static_cast<__nv_bfloat16*>(out);
+  ap.scale = 1.f / sqrtf(float(kD / nhead));
+  ap.v_mode = v_mode;
+  B200VQA_CUDA_OK(launch_enc_attention(tq, tkv, static_cast<const __nv_bfloat16*>(qkv), ap,
+                                       static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+#include "host_util.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace b200vqa {
+
+namespace {
+thread_local char g_err[1024] = "";
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn resolve_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* get_error() { return g_err; }
+
+int make_tmap_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows) {
+  EncodeTiledFn enc = resolve_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return B200VQA_ERR_CUDA;
+  }
+  const uint32_t esz = type == TmapType::kBF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * esz) & 15)) {
+    set_error("TMA operand must be 16-byte aligned (base %p, leading dimension %llu elements)", base,
+              (unsigned long long)ld);
+    return B200VQA_ERR_BAD_ARGUMENT;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {128 / esz, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, type == TmapType::kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu box_rows %u)", int(r),
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return B200VQA_ERR_CUDA;
+  }
+  return B200VQA_OK;
+}
+
+int require_sm100(int device, int* num_sms) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties(%d) failed: %s", device, cudaGetErrorString(e));
+    return B200VQA_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libb200vqa is built for sm_100a (B200) only and has no other path", device,
+              prop.major, prop.minor);
+    return B200VQA_ERR_UNSUPPORTED_ARCH;
+  }
+  if (num_sms) *num_sms = prop.multiProcessorCount;
+  return B200VQA_OK;
+}
+
+}  // namespace b200vqa

@@ -1,0 +1,192 @@
+// Internal (C++) launch interface between the C-ABI layer (api.cu) and the kernel translation units.
+// Nothing here crosses the shared-library boundary; the public surface is include/b200vqa.h.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace b200vqa {
+
+// Padded per-question row count of the encoder activations (sequence rows live at [b*kLP, b*kLP+len)).
+constexpr int kLP = 256;
+constexpr int kD = 256;  // d_model the kernels are specialised for (IQAP:15, FA:157)
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 GEMM:  out[M,N] = epilogue( A[M,K] . W[N,K]^T + bias )
+// ------------------------------------------------------------------------------------------
+enum GemmEpilogue : int {
+  kEpiBias = 0,       // bf16 out = acc + bias
+  kEpiBiasRelu = 1,   // bf16 out = relu(acc + bias)
+  kEpiBiasResLN = 2,  // bf16 out = LayerNorm(acc + bias + residual) * gamma + beta   (N == 256)
+  kEpiBiasPeRemap = 3 // bf16 out[row'] = acc + bias + pe[p]; row' = item*rows_out + off + p
+};
+
+struct GemmParams {
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;       // [N] fp32 (may be null)
+  __nv_bfloat16* out = nullptr;      // bf16 output
+  int ldc = 0;                       // output leading dimension (elements)
+  // kEpiBiasResLN
+  const __nv_bfloat16* residual = nullptr;
+  int ldr = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  float* out_f32 = nullptr;          // optional fp32 copy of the LN output, leading dim N
+  // kEpiBiasPeRemap
+  int rows_in = 1;                   // GEMM rows per item (196 image tokens)
+  int rows_out = 1;                  // output rows per item (kLP, or 196 for the FA image-token store)
+  int row_off = 0;                   // first output row inside the item
+  const float* pe = nullptr;         // [*, N] fp32 positional-encoding table
+  int pe_off = 0;                    // pe row = pe_off + p
+};
+
+// A/W tensor maps: 2D, 128-byte swizzle, box = {128 B of K, 128 rows (A) | BN rows (W)}.
+cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
+                        const GemmParams& p, int num_sms, cudaStream_t stream);
+
+// Plain CUDA-core GEMM used ONLY by the test suite to cross-check the tensor-core kernel on the GPU
+// at sizes where a host check is too slow. fp32 accumulate over the same bf16 (or fp32) inputs.
+cudaError_t launch_gemm_check(bool a_is_f32, const void* A, const void* W, const float* bias, float* out, int M,
+                              int N, int K, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// Encoder self-attention (tcgen05): one CTA per (question, head, 128-query tile).
+//   qkv  [B*kLP, 3*kD] bf16 (q | k | v), lens[b] = valid rows (keys >= len are masked), out [B*kLP, kD].
+// ------------------------------------------------------------------------------------------
+struct EncAttnParams {
+  int B = 0;
+  int nhead = 4;
+  const int32_t* lens = nullptr;  // [B] or null -> const_len
+  int const_len = 0;
+  __nv_bfloat16* out = nullptr;   // [B*kLP, kD]
+  float scale = 0.125f;           // 1/sqrt(dh)
+  int v_mode = 0;                 // 0: V as MN-major operand straight from TMA; 1: transposed in smem first
+};
+cudaError_t launch_enc_attention(const CUtensorMap& tm_qkv, const CUtensorMap& tm_v, const __nv_bfloat16* qkv,
+                                 const EncAttnParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// Small CUDA-core kernels (memory-bound or tiny)
+// ------------------------------------------------------------------------------------------
+// IQAP encoder-input rows that are not image tokens: CLS row 0 and question rows 197..242 (+PE), pad rows zero.
+cudaError_t launch_iqap_embed(const int64_t* questions, int B, int q_len, const float* cls, const float* emb,
+                              int vocab, const float* pe, int n_img, __nv_bfloat16* x, cudaStream_t stream);
+
+// FA: x[b] = [img_tokens[b] (PE already added) | emb(src)+PE | zero pad]; src gathered through the step cache.
+struct FaBuildSrcParams {
+  int B = 0;
+  int step = 0;                      // chain step index i
+  int S = 0;                         // steps dimension of func/deps/cache
+  int T = 20;                        // tokens per cached step output
+  const int32_t* func = nullptr;     // [B,S]
+  const int32_t* deps = nullptr;     // [B,S,2]  (-1 = none; >= step or unwritten -> contributes nothing)
+  const int32_t* n_steps = nullptr;  // [B]
+  const int32_t* cache = nullptr;    // [B,S,T]
+  const int64_t* src_direct = nullptr;  // alternative: explicit src tokens [B, src_ld] with src_len[b]
+  const int32_t* src_len_in = nullptr;
+  int src_ld = 0;
+  const __nv_bfloat16* img_tokens = nullptr;  // [B,196,kD]
+  const float* emb = nullptr;
+  int vocab = 0;
+  const float* pe = nullptr;
+  int pe_len = 0;
+  int n_img = 196;
+  __nv_bfloat16* x = nullptr;        // [B*kLP, kD]
+  int32_t* lens = nullptr;           // [B] out: 196 + src_len
+};
+cudaError_t launch_fa_build_src(const FaBuildSrcParams& p, cudaStream_t stream);
+
+// Row LayerNorm over kD columns, bf16 in/out (nn.Transformer's final encoder norm, FA:42).
+cudaError_t launch_layernorm_rows(const __nv_bfloat16* in, __nv_bfloat16* out, const float* gamma,
+                                  const float* beta, float eps, int rows, cudaStream_t stream);
+
+// fp32 [B, C, P] (channel-major, FA:47) -> bf16 [B*P, C]
+cudaError_t launch_transpose_cast(const float* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream);
+
+// seq-first fp32 memory [S,B,kD] -> padded bf16 rows [B*kLP, kD] (IQAP:190 entry with caller memory)
+// (ldb = batch size of the full seq-first tensor; `mem` already points at this chunk's first question)
+cudaError_t launch_memory_import(const float* mem, int S, int B, int ldb, __nv_bfloat16* x, cudaStream_t stream);
+// padded bf16 rows -> seq-first fp32 [S,B,kD]
+cudaError_t launch_memory_export(const __nv_bfloat16* x, int S, int B, int ldb, float* mem, cudaStream_t stream);
+
+// IQAP answer head on the CLS row: Linear(256,hidden)+ReLU+Linear(hidden,C), fp32 weights (IQAP:122-127,179).
+cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0, const float* b0, int hidden,
+                               const float* w1, const float* b1, int classes, float* out, cudaStream_t stream);
+
+// Decoder state initialisation: x0[b] = emb[start] + pe[0]; tokens[b,0] = start (FA keeps it, IQAP drops it).
+struct DecEmbedParams {
+  int B = 0;
+  const float* emb = nullptr;
+  int vocab = 0;
+  const float* pe = nullptr;
+  int start_token = 0;
+  const int64_t* start_tokens = nullptr;  // optional per-question start token: start_tokens[b*start_ld]
+  int start_ld = 0;
+  __nv_bfloat16* x = nullptr;       // [B,kD]
+  int64_t* tokens = nullptr;        // optional: tokens[b*tok_ld] = start (FA `ys` column 0)
+  int tok_ld = 0;
+  int32_t* cache_out = nullptr;     // optional FA step cache row base: cache_out[b*cache_ld] = start
+  long long cache_ld = 0;
+  const int32_t* n_steps = nullptr; // with cache_out: questions with n_steps[b] <= step are not written
+  int step = 0;
+};
+cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream);
+
+// Decoder self-attention for ONE new position t against the per-layer KV cache (exact form of the
+// reference's causal-mask recompute, IQAP:208-227 / FA:137-141).
+struct DecSelfAttnParams {
+  int B = 0, nhead = 4, t = 0, t_max = 0;
+  const __nv_bfloat16* qkv = nullptr;  // [B, 3*kD] this step's q|k|v
+  __nv_bfloat16* k_cache = nullptr;    // [B, t_max, kD]
+  __nv_bfloat16* v_cache = nullptr;    // [B, t_max, kD]
+  __nv_bfloat16* out = nullptr;        // [B, kD]
+};
+cudaError_t launch_dec_self_attn(const DecSelfAttnParams& p, cudaStream_t stream);
+
+// Decoder cross-attention of one query row per question over the encoder memory's projected K/V.
+struct DecCrossAttnParams {
+  int B = 0, nhead = 4;
+  const __nv_bfloat16* q = nullptr;   // [B, kD]
+  const __nv_bfloat16* kv = nullptr;  // [B*kLP, ld_kv]; K at col k_col, V at col v_col
+  int ld_kv = 0, k_col = 0, v_col = 0;
+  const int32_t* lens = nullptr;      // [B] or null
+  int const_len = 0;
+  __nv_bfloat16* out = nullptr;       // [B, kD]
+};
+cudaError_t launch_dec_cross_attn(const DecCrossAttnParams& p, cudaStream_t stream);
+
+// Output head for decode position t: (optional final LayerNorm) -> Linear(kD, V) fp32 -> argmax ->
+// tokens[b, t_out] ; next-step input x = emb[next] + pe[t+1] where next = forced token if given.
+struct DecHeadParams {
+  int B = 0, V = 0, t = 0;
+  const float* x_f32 = nullptr;       // [B,kD] fp32 output of the last decoder layer's norm3
+  const float* fn_gamma = nullptr;    // final decoder norm (FA) or null
+  const float* fn_beta = nullptr;
+  float eps = 1e-5f;
+  const float* w_t = nullptr;         // [kD, V] fp32 (transposed head weight)
+  const float* bias = nullptr;        // [V]
+  int64_t* tokens = nullptr;          // [B, tok_ld]
+  int tok_ld = 0, tok_col = 0;        // write argmax at tokens[b, tok_col]
+  float* logits = nullptr;            // optional [B, T, V]; row t
+  int logits_T = 0;
+  const int64_t* forced = nullptr;    // optional [B, forced_ld] teacher-forcing tokens; uses forced[b, t]
+  int forced_ld = 0;
+  const float* emb = nullptr;         // decoder embedding for the next input
+  int vocab = 0;
+  const float* pe_next = nullptr;     // pe row t+1 (null on the last step)
+  __nv_bfloat16* x_next = nullptr;    // [B,kD]
+  int32_t* cache_out = nullptr;       // optional FA step cache row base: cache_out[b*cache_ld + tok_col]
+  long long cache_ld = 0;
+  int cache_store_forced = 0;         // cache receives the forced token instead of the argmax (parity runs)
+  const int32_t* n_steps = nullptr;   // with cache_out: questions with n_steps[b] <= step are not written
+  int step = 0;
+};
+cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream);
+
+// Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.
+cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t stream);
+
+}  // namespace b200vqa

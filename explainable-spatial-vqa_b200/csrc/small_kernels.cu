@@ -1,0 +1,567 @@
+// CUDA-core kernels of the executor path: everything that is a gather, a per-row reduction or a
+// one-query attention. They are HBM- or latency-bound (no GEMM shape worth a tensor core), so the rules
+// that matter are coalesced 16-byte accesses, enough loads in flight, and no host round trips.
+#include <algorithm>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200vqa {
+namespace {
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void load_f32x8(const float* src, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IQAP: [CLS] row, question rows and padding of the encoder input (IQAP:156-170). One warp per row,
+// 8 columns per lane. Image rows 1..196 are written by the image_proj GEMM epilogue.
+// ------------------------------------------------------------------------------------------------
+__global__ void iqap_embed_kernel(const int64_t* __restrict__ questions, int B, int q_len,
+                                  const float* __restrict__ cls, const float* __restrict__ emb, int vocab,
+                                  const float* __restrict__ pe, int n_img, __nv_bfloat16* __restrict__ x) {
+  const int rows_per_q = kLP - n_img;  // CLS + question + pad
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * rows_per_q) return;
+  const int b = gw / rows_per_q;
+  const int i = gw % rows_per_q;
+  const int row = (i == 0) ? 0 : n_img + i;  // 0, 197, 198, ...
+  float v[8];
+  if (row == 0) {
+    float c[8], p8[8];
+    load_f32x8(cls + lane * 8, c);
+    load_f32x8(pe + lane * 8, p8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c[j] + p8[j];
+  } else if (row < 1 + n_img + q_len) {
+    long long tok = questions[size_t(b) * q_len + (row - 1 - n_img)];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    float e[8], p8[8];
+    load_f32x8(emb + size_t(tok) * kD + lane * 8, e);
+    load_f32x8(pe + size_t(row) * kD + lane * 8, p8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = e[j] + p8[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  store_bf16x8(x + (size_t(b) * kLP + row) * kD + lane * 8, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FA: encoder input of one chain step, gathered through the HBM-resident inference cache
+// (run_inference_chain, FA:96-118): src = [func] + cache[dep0] + cache[dep1]; x = [img | emb(src)] + PE.
+// One block per question.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fa_build_src_kernel(const FaBuildSrcParams p) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  __shared__ int s_tok[64];
+  __shared__ int s_len;
+
+  if (threadIdx.x == 0) {
+    int n = 0;
+    if (p.src_direct) {
+      n = p.src_len_in ? p.src_len_in[b] : p.src_ld;
+      n = n > 60 ? 60 : n;
+      for (int j = 0; j < n; ++j) s_tok[j] = int(p.src_direct[size_t(b) * p.src_ld + j]);
+    } else {
+      const size_t bs = size_t(b) * p.S + p.step;
+      s_tok[n++] = p.func[bs];
+      for (int d = 0; d < 2; ++d) {
+        const int dep = p.deps[bs * 2 + d];
+        // a pointer to a step without cached output contributes nothing (FA:110-115 `cache.get(idx, "")`)
+        if (dep >= 0 && dep < p.step && dep < p.n_steps[b]) {
+          const int32_t* c = p.cache + (size_t(b) * p.S + dep) * p.T;
+          for (int j = 0; j < p.T && n < 60; ++j) s_tok[n++] = c[j];
+        }
+      }
+    }
+    const int room = p.pe_len - p.n_img;  // positional table bounds the sequence (FA:40)
+    if (n > room) n = room;
+    if (n > kLP - p.n_img) n = kLP - p.n_img;
+    s_len = n;
+    p.lens[b] = p.n_img + n;
+  }
+  __syncthreads();
+  const int n = s_len;
+
+  // image tokens: straight 16-byte copy (PE rows 0..195 were folded in by fa_project_images)
+  const uint4* src = reinterpret_cast<const uint4*>(p.img_tokens + size_t(b) * p.n_img * kD);
+  uint4* dst = reinterpret_cast<uint4*>(p.x + size_t(b) * kLP * kD);
+  const int n16 = p.n_img * kD / 8;
+  for (int i = threadIdx.x; i < n16; i += 256) dst[i] = src[i];
+
+  // text rows + zero padding, one warp per row
+  for (int row = p.n_img + warp; row < kLP; row += 8) {
+    float v[8];
+    const int j = row - p.n_img;
+    if (j < n) {
+      int tok = s_tok[j];
+      tok = tok < 0 ? 0 : (tok >= p.vocab ? p.vocab - 1 : tok);
+      float e[8], pe8[8];
+      load_f32x8(p.emb + size_t(tok) * kD + lane * 8, e);
+      load_f32x8(p.pe + size_t(row) * kD + lane * 8, pe8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = e[k] + pe8[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    store_bf16x8(p.x + (size_t(b) * kLP + row) * kD + lane * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm (nn.Transformer's final encoder norm, FA:42). One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[8];
+  load_bf16x8(in + size_t(row) * kD + lane * 8, v);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  const float mean = warp_sum(s) * (1.f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / kD) + eps);
+  float g[8], bt[8];
+  load_f32x8(gamma + lane * 8, g);
+  load_f32x8(beta + lane * 8, bt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bt[j];
+  store_bf16x8(out + size_t(row) * kD + lane * 8, v);
+}
+
+// fp32 [B, C, P] -> bf16 [B*P, C] through a padded 32x32 shared tile.
+__global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int P) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, pp = p0 + tx;
+    tile[i][tx] = (c < C && pp < P) ? in[(size_t(b) * C + c) * P + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int pp = p0 + i, c = c0 + tx;
+    if (pp < P && c < C) out[(size_t(b) * P + pp) * C + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+__global__ void memory_import_kernel(const float* __restrict__ mem, int S, int B, int ldb,
+                                     __nv_bfloat16* __restrict__ x) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * kLP) return;
+  const int b = gw / kLP, s = gw % kLP;
+  float v[8];
+  if (s < S) load_f32x8(mem + (size_t(s) * ldb + b) * kD + lane * 8, v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  store_bf16x8(x + size_t(gw) * kD + lane * 8, v);
+}
+
+__global__ void memory_export_kernel(const __nv_bfloat16* __restrict__ x, int S, int B, int ldb,
+                                     float* __restrict__ mem) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * S) return;
+  const int s = gw / B, b = gw % B;
+  float v[8];
+  load_bf16x8(x + (size_t(b) * kLP + s) * kD + lane * 8, v);
+  float4* dst = reinterpret_cast<float4*>(mem + (size_t(s) * ldb + b) * kD + lane * 8);
+  dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+  dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IQAP answer head (IQAP:122-127,176-179) on the CLS row; fp32 weights, one block per question.
+// w0_t is answer_classifier.0.weight transposed to [d, hidden] so thread j reads coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) answer_head_kernel(const __nv_bfloat16* __restrict__ memory,
+                                                          const float* __restrict__ w0_t,
+                                                          const float* __restrict__ b0, int hidden,
+                                                          const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, int classes,
+                                                          float* __restrict__ out) {
+  __shared__ float xs[kD];
+  __shared__ float hs[1024];
+  const int b = blockIdx.x;
+  xs[threadIdx.x] = __bfloat162float(memory[size_t(b) * kLP * kD + threadIdx.x]);
+  __syncthreads();
+  for (int j = threadIdx.x; j < hidden; j += 256) {
+    float acc = b0[j];
+    for (int k = 0; k < kD; ++k) acc = fmaf(xs[k], __ldg(w0_t + size_t(k) * hidden + j), acc);
+    hs[j] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < classes; c += 8) {
+    float acc = 0.f;
+    for (int j = lane; j < hidden; j += 32) acc = fmaf(hs[j], __ldg(w1 + size_t(c) * hidden + j), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[size_t(b) * classes + c] = acc + b1[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_embed_start_kernel(const DecEmbedParams p) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  float e[8], pe8[8], v[8];
+  long long st = p.start_tokens ? p.start_tokens[size_t(b) * p.start_ld] : (long long)p.start_token;
+  st = st < 0 ? 0 : (st >= p.vocab ? p.vocab - 1 : st);
+  load_f32x8(p.emb + size_t(st) * kD + lane * 8, e);
+  load_f32x8(p.pe + lane * 8, pe8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = e[j] + pe8[j];
+  store_bf16x8(p.x + size_t(b) * kD + lane * 8, v);
+  if (lane == 0) {
+    if (p.tokens) p.tokens[size_t(b) * p.tok_ld] = st;
+    if (p.cache_out && !(p.n_steps && p.step >= p.n_steps[b])) p.cache_out[size_t(b) * p.cache_ld] = int(st);
+  }
+}
+
+// One warp per (question, head); lane owns DH/32 contiguous channels. Online softmax over the cached
+// positions 0..t (the reference recomputes the full causal prefix every step; position t's row of that
+// computation is exactly this).
+template <int DH>
+__global__ void dec_self_attn_kernel(const DecSelfAttnParams p) {
+  constexpr int E = DH / 32;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= p.B * p.nhead) return;
+  const int b = gw / p.nhead, h = gw % p.nhead;
+  const int col = h * DH + lane * E;
+  const float scale = rsqrtf(float(DH));
+
+  float q[E], kc[E], vc[E];
+  const __nv_bfloat16* qkv = p.qkv + size_t(b) * 3 * kD;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    q[e] = __bfloat162float(qkv[col + e]) * scale;
+    kc[e] = __bfloat162float(qkv[kD + col + e]);
+    vc[e] = __bfloat162float(qkv[2 * kD + col + e]);
+  }
+  __nv_bfloat16* kdst = p.k_cache + (size_t(b) * p.t_max + p.t) * kD + col;
+  __nv_bfloat16* vdst = p.v_cache + (size_t(b) * p.t_max + p.t) * kD + col;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    kdst[e] = qkv[kD + col + e];
+    vdst[e] = qkv[2 * kD + col + e];
+  }
+
+  float m = -INFINITY, l = 0.f, acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  for (int j = 0; j <= p.t; ++j) {
+    float kj[E], vj[E];
+    if (j < p.t) {
+      const __nv_bfloat16* kr = p.k_cache + (size_t(b) * p.t_max + j) * kD + col;
+      const __nv_bfloat16* vr = p.v_cache + (size_t(b) * p.t_max + j) * kD + col;
+#pragma unroll
+      for (int e = 0; e < E; ++e) { kj[e] = __bfloat162float(kr[e]); vj[e] = __bfloat162float(vr[e]); }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { kj[e] = kc[e]; vj[e] = vc[e]; }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s = fmaf(q[e], kj[e], s);
+    s = warp_sum(s);
+    const float mn = fmaxf(m, s);
+    const float corr = __expf(m - mn);
+    const float pj = __expf(s - mn);
+    l = l * corr + pj;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = acc[e] * corr + pj * vj[e];
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  __nv_bfloat16* o = p.out + size_t(b) * kD + col;
+#pragma unroll
+  for (int e = 0; e < E; ++e) o[e] = __float2bfloat16(acc[e] * inv);
+}
+
+// One warp per (question, head). LPK = DH/8 lanes cooperate on one key row (16 B each), 32/LPK keys per
+// warp-wide load, so every load instruction touches whole 128-byte lines of K (then V). Scores live in
+// shared memory between the two passes; K and V are each read exactly once per step.
+template <int DH>
+__global__ void __launch_bounds__(128) dec_cross_attn_kernel(const DecCrossAttnParams p) {
+  constexpr int LPK = DH / 8;
+  constexpr int KPI = 32 / LPK;
+  __shared__ float s_sc[4][kLP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 4 + warp;
+  if (gw >= p.B * p.nhead) return;
+  const int b = gw / p.nhead, h = gw % p.nhead;
+  const int len = p.lens ? p.lens[b] : p.const_len;
+  const int sub = lane % LPK;  // which 16-byte chunk of the head's row
+  const int grp = lane / LPK;  // which key of the KPI handled per iteration
+  float* sc = s_sc[warp];
+
+  float q[8];
+  load_bf16x8(p.q + size_t(b) * kD + h * DH + sub * 8, q);
+  const float sl2 = rsqrtf(float(DH)) * 1.4426950408889634f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] *= sl2;
+
+  const __nv_bfloat16* kbase = p.kv + size_t(b) * kLP * p.ld_kv + p.k_col + h * DH + sub * 8;
+  const __nv_bfloat16* vbase = p.kv + size_t(b) * kLP * p.ld_kv + p.v_col + h * DH + sub * 8;
+
+  float mx = -INFINITY;
+#pragma unroll 4
+  for (int j0 = 0; j0 < len; j0 += KPI) {
+    const int j = j0 + grp;
+    float s = 0.f;
+    if (j < len) {
+      float kx[8];
+      load_bf16x8(kbase + size_t(j) * p.ld_kv, kx);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q[e], kx[e], s);
+    }
+#pragma unroll
+    for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (j < len) {
+      if (sub == 0) sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < len; j += 32) {
+    const float e = exp2f(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (int j0 = 0; j0 < len; j0 += KPI) {
+    const int j = j0 + grp;
+    if (j < len) {
+      float vx[8];
+      load_bf16x8(vbase + size_t(j) * p.ld_kv, vx);
+      const float pj = sc[j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
+    }
+  }
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  }
+  if (grp == 0) {
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    store_bf16x8(p.out + size_t(b) * kD + h * DH + sub * 8, acc);
+  }
+}
+
+// One warp per question: optional final LayerNorm, fp32 vocabulary head, argmax (lowest index wins
+// ties, like torch.max / torch.argmax on CPU), token store, next-step embedding.
+__global__ void __launch_bounds__(128) dec_head_kernel(const DecHeadParams p) {
+  __shared__ float s_x[4][kD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= p.B) return;
+  float* xs = s_x[warp];
+
+  float v[8];
+  load_f32x8(p.x_f32 + size_t(b) * kD + lane * 8, v);
+  if (p.fn_gamma) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.f / kD);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / kD) + p.eps);
+    float g[8], bt[8];
+    load_f32x8(p.fn_gamma + lane * 8, g);
+    load_f32x8(p.fn_beta + lane * 8, bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bt[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xs[lane * 8 + j] = v[j];
+  __syncwarp();
+
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int v0 = 0; v0 < p.V; v0 += 32) {
+    const int vi = v0 + lane;
+    float acc = 0.f;
+    if (vi < p.V) {
+      acc = p.bias[vi];
+#pragma unroll 8
+      for (int k = 0; k < kD; ++k) acc = fmaf(xs[k], __ldg(p.w_t + size_t(k) * p.V + vi), acc);
+      if (p.logits) p.logits[(size_t(b) * p.logits_T + p.t) * p.V + vi] = acc;
+      if (acc > best) { best = acc; besti = vi; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (besti >= p.V) besti = 0;  // all-NaN row: keep the index in range
+  const bool use_forced = p.forced && (p.pe_next || p.cache_store_forced);
+  long long nxt = use_forced ? p.forced[size_t(b) * p.forced_ld + p.t] : (long long)besti;
+  nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
+  if (lane == 0) {
+    if (p.tokens) p.tokens[size_t(b) * p.tok_ld + p.tok_col] = besti;
+    if (p.cache_out && !(p.n_steps && p.step >= p.n_steps[b]))
+      p.cache_out[size_t(b) * p.cache_ld + p.tok_col] = p.cache_store_forced ? int(nxt) : besti;
+  }
+  if (p.pe_next) {
+    float e[8], pe8[8], o[8];
+    load_f32x8(p.emb + size_t(nxt) * kD + lane * 8, e);
+    load_f32x8(p.pe_next + lane * 8, pe8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = e[j] + pe8[j];
+    store_bf16x8(p.x_next + size_t(b) * kD + lane * 8, o);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[size_t(r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) out[size_t(c) * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
+
+}  // namespace
+
+cudaError_t launch_iqap_embed(const int64_t* questions, int B, int q_len, const float* cls, const float* emb,
+                              int vocab, const float* pe, int n_img, __nv_bfloat16* x, cudaStream_t stream) {
+  const long long warps = (long long)B * (kLP - n_img);
+  iqap_embed_kernel<<<ceil_div(warps * 32, 256), 256, 0, stream>>>(questions, B, q_len, cls, emb, vocab, pe, n_img, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fa_build_src(const FaBuildSrcParams& p, cudaStream_t stream) {
+  fa_build_src_kernel<<<p.B, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm_rows(const __nv_bfloat16* in, __nv_bfloat16* out, const float* gamma,
+                                  const float* beta, float eps, int rows, cudaStream_t stream) {
+  layernorm_rows_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(in, out, gamma, beta, eps, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_cast(const float* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream) {
+  dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, stream>>>(in, out, C, P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_memory_import(const float* mem, int S, int B, int ldb, __nv_bfloat16* x, cudaStream_t stream) {
+  memory_import_kernel<<<ceil_div((long long)B * kLP * 32, 256), 256, 0, stream>>>(mem, S, B, ldb, x);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_memory_export(const __nv_bfloat16* x, int S, int B, int ldb, float* mem, cudaStream_t stream) {
+  memory_export_kernel<<<ceil_div((long long)B * S * 32, 256), 256, 0, stream>>>(x, S, B, ldb, mem);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0_t, const float* b0, int hidden,
+                               const float* w1, const float* b1, int classes, float* out, cudaStream_t stream) {
+  if (hidden > 1024) return cudaErrorInvalidValue;
+  answer_head_kernel<<<B, 256, 0, stream>>>(memory, w0_t, b0, hidden, w1, b1, classes, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream) {
+  dec_embed_start_kernel<<<ceil_div((long long)p.B * 32, 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dec_self_attn(const DecSelfAttnParams& p, cudaStream_t stream) {
+  const int grid = ceil_div((long long)p.B * p.nhead * 32, 128);
+  const int dh = kD / p.nhead;
+  if (dh == 64) dec_self_attn_kernel<64><<<grid, 128, 0, stream>>>(p);
+  else if (dh == 128) dec_self_attn_kernel<128><<<grid, 128, 0, stream>>>(p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dec_cross_attn(const DecCrossAttnParams& p, cudaStream_t stream) {
+  const int grid = ceil_div((long long)p.B * p.nhead, 4);
+  const int dh = kD / p.nhead;
+  if (dh == 64) dec_cross_attn_kernel<64><<<grid, 128, 0, stream>>>(p);
+  else if (dh == 128) dec_cross_attn_kernel<128><<<grid, 128, 0, stream>>>(p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream) {
+  dec_head_kernel<<<ceil_div(p.B, 4), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int grid = int(std::min<size_t>((n + 255) / 256, 4096));
+  cast_bf16_kernel<<<grid, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t stream) {
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+  transpose_f32_kernel<<<grid, block, 0, stream>>>(in, out, R, C);
+  return cudaGetLastError();
+}
+
+}  // namespace b200vqa

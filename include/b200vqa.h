@@ -1,0 +1,241 @@
+/*
+ * b200vqa.h - C ABI of libb200vqa.so, the sm_100a (B200) implementation of the batched Program Executor
+ * inference path of guoyu-zhang/explainable-spatial-vqa.
+ *
+ * The reference has no FFI: its "operator interface" for this path is two Python files,
+ *   code/inference_transformer_iqap.py                    ("IQAP")
+ *   code/inference_transformer_full_annotation_new.py     ("FA")
+ * Each entry point below names the reference function (file:line) whose arithmetic it replaces.
+ * The Python modules of the same names in explainable-spatial-vqa_b200/ bind these symbols with ctypes
+ *  and keep the reference's class / function signatures.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a raw DEVICE pointer unless the name starts with h_ (host).
+ *   - the caller owns all input/output buffers; the library owns packed weights and its workspace.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and performs no host sync,
+ *     except the *_host entry points, which return after their results are in the host buffers.
+ *   - return value 0 = ok, negative = b200vqa_status; the message is in b200vqa_last_error() (thread local).
+ *   - there is no CPU fallback: a device that is not compute capability 10.x is an error.
+ */
+#ifndef B200VQA_H_
+#define B200VQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200VQA_API __attribute__((visibility("default")))
+#else
+#define B200VQA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200vqa_handle b200vqa_handle;
+
+typedef enum b200vqa_status {
+  B200VQA_OK = 0,
+  B200VQA_ERR_BAD_ARGUMENT = -1,
+  B200VQA_ERR_UNSUPPORTED_ARCH = -2,
+  B200VQA_ERR_OUT_OF_MEMORY = -3,
+  B200VQA_ERR_CUDA = -4,
+  B200VQA_ERR_UNSUPPORTED_SHAPE = -5
+} b200vqa_status;
+
+typedef enum b200vqa_model_kind {
+  B200VQA_MODEL_IQAP = 0, /* VQAModel, IQAP:95-241 */
+  B200VQA_MODEL_FA = 1    /* MultiModalTransformer, FA:32-58 */
+} b200vqa_model_kind;
+
+/* torch.nn.MultiheadAttention parameters, fp32, state-dict layout (in_proj packed q|k|v on dim 0). */
+typedef struct b200vqa_mha_weights {
+  const float* in_proj_weight;  /* [3d, d] */
+  const float* in_proj_bias;    /* [3d]    */
+  const float* out_proj_weight; /* [d, d]  */
+  const float* out_proj_bias;   /* [d]     */
+} b200vqa_mha_weights;
+
+/* torch.nn.TransformerEncoderLayer (post-norm, ReLU), IQAP:118 / FA:42 */
+typedef struct b200vqa_encoder_layer_weights {
+  b200vqa_mha_weights self_attn;
+  const float* linear1_weight; /* [ff, d] */
+  const float* linear1_bias;   /* [ff]    */
+  const float* linear2_weight; /* [d, ff] */
+  const float* linear2_bias;   /* [d]     */
+  const float* norm1_weight;
+  const float* norm1_bias;
+  const float* norm2_weight;
+  const float* norm2_bias;
+} b200vqa_encoder_layer_weights;
+
+/* torch.nn.TransformerDecoderLayer (post-norm, ReLU), IQAP:132 / FA:42 */
+typedef struct b200vqa_decoder_layer_weights {
+  b200vqa_mha_weights self_attn;
+  b200vqa_mha_weights multihead_attn;
+  const float* linear1_weight;
+  const float* linear1_bias;
+  const float* linear2_weight;
+  const float* linear2_bias;
+  const float* norm1_weight;
+  const float* norm1_bias;
+  const float* norm2_weight;
+  const float* norm2_bias;
+  const float* norm3_weight;
+  const float* norm3_bias;
+} b200vqa_decoder_layer_weights;
+
+/* Everything b200vqa_create needs: dimensions + fp32 device pointers exactly as in the module's state_dict. */
+typedef struct b200vqa_model_desc {
+  int32_t kind;          /* b200vqa_model_kind */
+  int32_t d_model;       /* 256 (IQAP:15, FA:157); the kernels are specialised for 256 */
+  int32_t img_feat_dim;  /* 1024 (IQAP:17, FA:38) */
+  int32_t n_img_tokens;  /* 196 */
+  int32_t nhead;         /* IQAP 4 (IQAP:118,132); FA ctor argument (FA:158 uses 2) */
+  int32_t n_enc_layers;
+  int32_t n_dec_layers;
+  int32_t dim_ff;        /* IQAP 2048 (torch default); FA ctor argument (512) */
+  int32_t enc_vocab;     /* IQAP question vocab / FA vocab */
+  int32_t dec_vocab;     /* IQAP program vocab / FA vocab (= head output size) */
+  int32_t max_q_len;     /* IQAP 46 (Config.MAX_QUESTION_LEN); FA: max_text_len */
+  int32_t pe_enc_len;    /* rows of pos_encoder.pe */
+  int32_t pe_dec_len;    /* rows of pos_decoder.pe */
+  int32_t answer_hidden; /* IQAP hidden_dim (256) */
+  int32_t num_classes;   /* IQAP answer classes */
+  float layer_norm_eps;  /* 1e-5 */
+
+  const float* image_proj_weight; /* [d, 1024] */
+  const float* image_proj_bias;   /* [d] */
+  const float* cls_token;         /* IQAP [d]; FA NULL */
+  const float* enc_embedding;     /* IQAP embedding.weight / FA text_embedding.weight  [enc_vocab, d] */
+  const float* dec_embedding;     /* IQAP program_decoder_embedding.weight / FA text_embedding.weight */
+  const float* pe_enc;            /* [pe_enc_len, d] */
+  const float* pe_dec;            /* [pe_dec_len, d] */
+  const b200vqa_encoder_layer_weights* enc_layers; /* HOST array of n_enc_layers structs */
+  const b200vqa_decoder_layer_weights* dec_layers; /* HOST array of n_dec_layers structs */
+  const float* enc_final_norm_weight; /* FA transformer.encoder.norm, else NULL */
+  const float* enc_final_norm_bias;
+  const float* dec_final_norm_weight; /* FA transformer.decoder.norm, else NULL */
+  const float* dec_final_norm_bias;
+  const float* head_weight;       /* IQAP program_output.weight / FA output_linear.weight [dec_vocab, d] */
+  const float* head_bias;
+  const float* answer_w0;         /* IQAP answer_classifier.0 [hidden, d] */
+  const float* answer_b0;
+  const float* answer_w1;         /* IQAP answer_classifier.3 [classes, hidden] */
+  const float* answer_b1;
+} b200vqa_model_desc;
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Lifetime                                                                                               */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* Replaces: VQAModel.__init__ + load_state_dict (IQAP:96-134, 255-276) / MultiModalTransformer.__init__
+ * (FA:33-44, 175-180): packs the fp32 state-dict tensors into the bf16 / tf32 layouts the kernels read. */
+B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200vqa_handle** out);
+B200VQA_API void b200vqa_destroy(b200vqa_handle* h);
+/* Re-pack after the caller changed parameter values in place (load_state_dict on a live module). */
+B200VQA_API int b200vqa_refresh_weights(b200vqa_handle* h, const b200vqa_model_desc* desc);
+/* Device bytes of activations the library will hold for a batch of B questions. */
+B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B);
+B200VQA_API const char* b200vqa_last_error(void);
+B200VQA_API const char* b200vqa_version(void);
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* IQAP                                                                                                   */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* Replaces VQAModel.forward (IQAP:136-188) incl. autoregressive_program_generation (IQAP:190-241).
+ *   image_features [B,196,1024] f32, questions [B,46] i64  ->  answer [B,classes] f32, programs [B,T] i64
+ *   opt_step_logits  : NULL or [B,T,dec_vocab] f32, the program_output logits of every decode position
+ *   opt_forced_tokens: NULL or [B,T] i64; when given, position t+1 is fed forced[b,t] instead of the argmax
+ *                      (teacher forcing, used by the parity tests; `programs` still receives the argmax)
+ *   opt_memory       : NULL or [243,B,256] f32, the encoder output in the reference's seq-first layout */
+B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_features, const int64_t* questions, int B,
+                         int program_len, float* answer, int64_t* programs, float* opt_step_logits,
+                         const int64_t* opt_forced_tokens, float* opt_memory, void* stream);
+
+/* Replaces VQAModel.autoregressive_program_generation (IQAP:190-241) for a caller-supplied memory
+ * [S,B,256] f32 (seq-first, S <= 256). */
+B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int S, int B, int program_len, int64_t* programs,
+                        float* opt_step_logits, const int64_t* opt_forced_tokens, void* stream);
+
+/* Same as b200vqa_iqap_forward with HOST buffers (pinned or pageable): the host->device copy of the
+ * inputs and the device->host copy of the results happen inside the call, chunked and overlapped with
+ * compute. Returns once h_answer / h_programs are valid. This is the call bench.py times for "e2e". */
+B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_image_features, const int64_t* h_questions, int B,
+                              int program_len, float* h_answer, int64_t* h_programs, int chunk, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* FA (step-wise executor with the inference cache)                                                       */
+/* ---------------------------------------------------------------------------------------------------- */
+
+/* Replaces the image half of greedy_decode (FA:129-131): view(B,1024,196).permute(0,2,1) -> image_proj.
+ * Output: img_tokens [B,196,256] bf16 with the positional encoding of rows 0..195 already added; reused by
+ * every program step of the question (the reference recomputes it per step). */
+B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_features /*[B,1024,196]*/, int B,
+                              void* img_tokens_bf16, void* stream);
+
+/* Replaces greedy_decode (FA:126-146), batched: src [B,src_ld] i64 with src_len[b] valid tokens each
+ * (the reference is batch 1 and never pads; here keys beyond 196+src_len[b] are masked).
+ *   out_tokens [B,max_len] i64 (column 0 = start_token, like `ys`)
+ *   opt_logits NULL or [B,max_len-1,vocab] f32; opt_forced NULL or [B,max_len-1] i64 (teacher forcing:
+ *   this is also MultiModalTransformer.forward(image, src, tgt), FA:45-58, with tgt = [start | forced]) */
+B200VQA_API int b200vqa_fa_step(b200vqa_handle* h, const void* img_tokens_bf16, const int64_t* src, const int32_t* src_len,
+                    int src_ld, int B, int start_token, int max_len, int64_t* out_tokens, float* opt_logits,
+                    const int64_t* opt_forced, void* stream);
+
+/* Replaces MultiModalTransformer.forward (FA:45-58), the teacher-forced path: logits [B,T,vocab] f32 for
+ * tgt [B,T] i64 (position t attends to tgt[:, :t+1]); src as in b200vqa_fa_step. */
+B200VQA_API int b200vqa_fa_forward(b200vqa_handle* h, const void* img_tokens_bf16, const int64_t* src,
+                                   const int32_t* src_len, int src_ld, int B, const int64_t* tgt, int T, float* logits,
+                                   void* stream);
+
+/* Replaces run_inference_chain (FA:83-124) for B questions at once with the cache resident in HBM.
+ *   func [B,S] i32      function token of step i
+ *   deps [B,S,2] i32    dependency pointers (step indices < i), -1 = none; a pointer to a step that has not
+ *                       produced output contributes no tokens (the reference's `cache.get(idx, "")`, FA:110-115)
+ *   n_steps [B] i32     steps of question b (<= S)
+ *   cache [B,S,max_len] i32  OUT: all max_len tokens of every executed step incl. the start token (FA:120-121)
+ *   h_active NULL or HOST int32[S]: h_active[i] = number of leading questions with n_steps > i (callers that
+ *                       sort questions by n_steps descending let the library skip finished questions)
+ *   opt_logits NULL or [B,S,max_len-1,vocab] f32; opt_forced NULL or [B,S,max_len-1] i64. With opt_forced the
+ *   cache receives the FORCED tokens (later steps then consume exactly the tokens the caller dictated) and the
+ *   model's own decisions are read from opt_logits - the parity tests feed the oracle's tokens this way. */
+B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_bf16, const int32_t* func, const int32_t* deps,
+                         const int32_t* n_steps, int B, int S, int start_token, int max_len, int32_t* cache,
+                         const int32_t* h_active, float* opt_logits, const int64_t* opt_forced, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* Kernel-level entry points used by the test-suite only (not part of the drop-in surface)               */
+/* ---------------------------------------------------------------------------------------------------- */
+typedef struct b200vqa_dbg_gemm_args {
+  int32_t epilogue; /* 0 bias, 1 bias+relu, 2 bias+residual+layernorm, 3 bias+pe+row remap */
+  int32_t tf32;     /* A/W are fp32 (tf32 math) instead of bf16 */
+  int32_t block_n;  /* 128 or 256 */
+  int32_t M, N, K;
+  const void* A;    /* [M,K] */
+  const void* W;    /* [N,K] */
+  const float* bias;
+  void* out;        /* bf16 */
+  int32_t ldc;
+  const void* residual; /* bf16 [M,N] */
+  const float* gamma;
+  const float* beta;
+  float* out_f32;
+  int32_t rows_in, rows_out, row_off, pe_off;
+  const float* pe;
+} b200vqa_dbg_gemm_args;
+B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* args, void* stream);
+B200VQA_API int b200vqa_dbg_gemm_check(int a_is_f32, const void* A, const void* W, const float* bias, float* out, int M, int N,
+                           int K, void* stream);
+/* qkv [B*256, 768] bf16 -> out [B*256, 256] bf16; lens NULL -> const_len */
+B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, int const_len, int B, int nhead, int v_mode,
+                              void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VQA_H_ */

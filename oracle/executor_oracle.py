@@ -1,0 +1,354 @@
+"""CPU restatement (plain fp32 torch ops on the host) of the reference's Program Executor inference path.
+
+TEST INFRASTRUCTURE - see oracle/__init__.py for who may import this.
+
+The arithmetic of the reference lives in PyTorch (third-party, unpinned in code/requirements.txt; torch
+2.11.0 in this image): nn.TransformerEncoderLayer / DecoderLayer / nn.Transformer (post-norm, ReLU,
+eps 1e-5), nn.MultiheadAttention (packed in_proj q|k|v), nn.Linear, nn.Embedding.  Every function below
+restates one reference function from a *state-dict* (the reference's own parameter names) with
+F.linear / softmax / layer_norm only and cites the lines it follows:
+
+  IQAP = /root/reference/code/inference_transformer_iqap.py
+  FA   = /root/reference/code/inference_transformer_full_annotation_new.py
+
+Parity pin: the reference ships no tests, checkpoints or golden vectors for this path, so the
+pins are outputs of the reference ITSELF, generated in the build container by oracle/make_golden.py
+(imports the reference's modules) and committed under tests/golden/; tests/test_oracle_golden.py checks
+this restatement against them.
+
+`recompute=True` follows the reference's execution literally (whole decoder prefix re-run every step, cross
+K/V re-projected every step: IQAP:208-236, FA:137-145) and is the mode bench.py times as the CPU
+baseline; `recompute=False` is the algebraically identical KV-cached form the CUDA path implements.
+"""
+from __future__ import annotations
+
+import math
+import re
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks (torch/nn/functional.py multi_head_attention_forward; nn/modules/transformer.py)
+# ------------------------------------------------------------------------------------------------
+def mha(sd, prefix, x_q, x_kv, nhead, attn_mask=None, key_len=None):
+    """nn.MultiheadAttention forward, batch-first tensors (B, Lq, d) / (B, Lk, d).
+    attn_mask: additive (Lq, Lk) or None; key_len: (B,) valid key counts (keys beyond are masked) or None."""
+    w, b = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
+    d = x_q.shape[-1]
+    dh = d // nhead
+    q = F.linear(x_q, w[:d], b[:d])
+    k = F.linear(x_kv, w[d:2 * d], b[d:2 * d])
+    v = F.linear(x_kv, w[2 * d:], b[2 * d:])
+    B, Lq, Lk = x_q.shape[0], x_q.shape[1], x_kv.shape[1]
+    q = q.view(B, Lq, nhead, dh).transpose(1, 2) * (1.0 / math.sqrt(dh))
+    k = k.view(B, Lk, nhead, dh).transpose(1, 2)
+    v = v.view(B, Lk, nhead, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if attn_mask is not None:
+        s = s + attn_mask
+    if key_len is not None:
+        dead = torch.arange(Lk)[None, :] >= key_len[:, None]
+        s = s.masked_fill(dead[:, None, None, :], float("-inf"))
+    o = torch.softmax(s, dim=-1) @ v
+    o = o.transpose(1, 2).reshape(B, Lq, d)
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+
+
+def layer_norm(sd, prefix, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], EPS)
+
+
+def ffn(sd, prefix, x):
+    return F.linear(torch.relu(F.linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])),
+                    sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
+
+
+def encoder_layer(sd, prefix, x, nhead, key_len=None):
+    """Post-norm TransformerEncoderLayer: x = LN1(x + SA(x)); x = LN2(x + FFN(x))."""
+    x = layer_norm(sd, prefix + "norm1.", x + mha(sd, prefix + "self_attn.", x, x, nhead, key_len=key_len))
+    return layer_norm(sd, prefix + "norm2.", x + ffn(sd, prefix, x))
+
+
+def causal_mask(n):
+    return torch.full((n, n), float("-inf")).triu(1)
+
+
+def decoder_layer(sd, prefix, x, memory, nhead, mem_len=None):
+    """Post-norm TransformerDecoderLayer over the whole prefix x (B, t, d) with a causal mask."""
+    x = layer_norm(sd, prefix + "norm1.", x + mha(sd, prefix + "self_attn.", x, x, nhead, causal_mask(x.shape[1])))
+    x = layer_norm(sd, prefix + "norm2.", x + mha(sd, prefix + "multihead_attn.", x, memory, nhead, key_len=mem_len))
+    return layer_norm(sd, prefix + "norm3.", x + ffn(sd, prefix, x))
+
+
+def count_layers(sd, prefix):
+    n = 0
+    while f"{prefix}{n}.norm1.weight" in sd:
+        n += 1
+    return n
+
+
+class _CachedDecoder:
+    """KV-cached greedy decoder: identical arithmetic to re-running the causal prefix (each position only
+    ever attends to earlier ones), with the cross-attention K/V of `memory` projected once."""
+
+    def __init__(self, sd, layer_prefix, memory, nhead, mem_len=None):
+        self.sd, self.pre, self.nhead, self.mem_len = sd, layer_prefix, nhead, mem_len
+        self.n = count_layers(sd, layer_prefix)
+        d = memory.shape[-1]
+        self.d, self.dh = d, d // nhead
+        B, L = memory.shape[0], memory.shape[1]
+        self.ck, self.cv, self.sk, self.sv = [], [], [], []
+        for l in range(self.n):
+            w, b = sd[f"{self.pre}{l}.multihead_attn.in_proj_weight"], sd[f"{self.pre}{l}.multihead_attn.in_proj_bias"]
+            self.ck.append(F.linear(memory, w[d:2 * d], b[d:2 * d]).view(B, L, nhead, self.dh).transpose(1, 2))
+            self.cv.append(F.linear(memory, w[2 * d:], b[2 * d:]).view(B, L, nhead, self.dh).transpose(1, 2))
+            self.sk.append(None)
+            self.sv.append(None)
+
+    def _attend(self, q, k, v, key_len=None):
+        B = q.shape[0]
+        qh = q.view(B, 1, self.nhead, self.dh).transpose(1, 2) * (1.0 / math.sqrt(self.dh))
+        s = qh @ k.transpose(-1, -2)
+        if key_len is not None:
+            dead = torch.arange(k.shape[2])[None, :] >= key_len[:, None]
+            s = s.masked_fill(dead[:, None, None, :], float("-inf"))
+        return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, 1, self.d)
+
+    def step(self, x):
+        """x (B, 1, d): embedding + positional row of the newest position -> decoder output (B, 1, d)."""
+        sd, d, B = self.sd, self.d, x.shape[0]
+        for l in range(self.n):
+            p = f"{self.pre}{l}."
+            w, b = sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"]
+            qkv = F.linear(x, w, b)
+            q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+            k = k.view(B, 1, self.nhead, self.dh).transpose(1, 2)
+            v = v.view(B, 1, self.nhead, self.dh).transpose(1, 2)
+            self.sk[l] = k if self.sk[l] is None else torch.cat([self.sk[l], k], dim=2)
+            self.sv[l] = v if self.sv[l] is None else torch.cat([self.sv[l], v], dim=2)
+            a = self._attend(q, self.sk[l], self.sv[l])
+            x = layer_norm(sd, p + "norm1.", x + F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"]))
+            w, b = sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"]
+            q = F.linear(x, w[:d], b[:d])
+            a = self._attend(q, self.ck[l], self.cv[l], self.mem_len)
+            x = layer_norm(sd, p + "norm2.", x + F.linear(a, sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"]))
+            x = layer_norm(sd, p + "norm3.", x + ffn(sd, p, x))
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# IQAP: VQAModel.forward (IQAP:136-188) + autoregressive_program_generation (IQAP:190-241)
+# ------------------------------------------------------------------------------------------------
+def iqap_encode(sd, image_features, questions, nhead=4):
+    """-> memory (B, S, d) batch-first (the reference holds it seq-first; attention does not care)."""
+    B = image_features.shape[0]
+    img = F.linear(image_features, sd["image_proj.weight"], sd["image_proj.bias"])          # IQAP:152
+    qe = F.embedding(questions, sd["embedding.weight"])                                      # IQAP:156 (row 0 is zero)
+    cls = sd["cls_token"].expand(B, -1, -1)                                                  # IQAP:160
+    x = torch.cat([cls, img, qe], dim=1)                                                     # IQAP:164
+    x = x + sd["pos_encoder.pe"][: x.shape[1], 0][None]                                      # IQAP:170
+    for l in range(count_layers(sd, "transformer_encoder.layers.")):                          # IQAP:173, no mask, no final norm
+        x = encoder_layer(sd, f"transformer_encoder.layers.{l}.", x, nhead)
+    return x
+
+
+def iqap_answer(sd, memory):
+    cls = memory[:, 0]                                                                       # IQAP:176
+    h = torch.relu(F.linear(cls, sd["answer_classifier.0.weight"], sd["answer_classifier.0.bias"]))
+    return F.linear(h, sd["answer_classifier.3.weight"], sd["answer_classifier.3.bias"])     # IQAP:179
+
+
+def iqap_decode(sd, memory, T=27, start_token=1, nhead=4, forced=None, recompute=False):
+    """Greedy program decode.  Returns (tokens (B,T) i64, logits (B,T,Vp)).  `forced` (B,T): position t+1 is
+    fed forced[:, t] instead of the argmax (teacher forcing); tokens still hold the argmax."""
+    B = memory.shape[0]
+    emb, pe = sd["program_decoder_embedding.weight"], sd["pos_decoder.pe"][:, 0]
+    prefix = torch.full((B, 1), start_token, dtype=torch.long)                               # IQAP:205
+    dec = None if recompute else _CachedDecoder(sd, "transformer_decoder.layers.", memory, nhead)
+    n_layers = count_layers(sd, "transformer_decoder.layers.")
+    toks, logits = [], []
+    for t in range(T):
+        if recompute:
+            x = F.embedding(prefix, emb) + pe[: prefix.shape[1]][None]                       # IQAP:210-216
+            for l in range(n_layers):
+                x = decoder_layer(sd, f"transformer_decoder.layers.{l}.", x, memory, nhead)  # IQAP:223-227
+            last = x[:, -1]
+        else:
+            last = dec.step(F.embedding(prefix[:, -1:], emb) + pe[t][None, None])[:, 0]
+        lg = F.linear(last, sd["program_output.weight"], sd["program_output.bias"])          # IQAP:230
+        nxt = torch.max(lg, dim=1)[1]                                                        # IQAP:233
+        toks.append(nxt)
+        logits.append(lg)
+        feed = forced[:, t] if forced is not None else nxt
+        prefix = torch.cat([prefix, feed[:, None]], dim=1)                                   # IQAP:236
+    return torch.stack(toks, dim=1), torch.stack(logits, dim=1)
+
+
+@torch.no_grad()
+def iqap_forward(sd, image_features, questions, T=27, forced=None, recompute=False):
+    """-> dict(answer (B,C), programs (B,T), logits (B,T,Vp), memory (S,B,d) seq-first like the reference)."""
+    memory = iqap_encode(sd, image_features.float(), questions.long())
+    answer = iqap_answer(sd, memory)
+    programs, logits = iqap_decode(sd, memory, T, 1, 4, forced, recompute)
+    return {"answer": answer, "programs": programs, "logits": logits, "memory": memory.transpose(0, 1).contiguous()}
+
+
+# ------------------------------------------------------------------------------------------------
+# FA: MultiModalTransformer.forward (FA:45-58), greedy_decode (FA:126-146), run_inference_chain (FA:83-124)
+# ------------------------------------------------------------------------------------------------
+def fa_nhead(sd, nhead):
+    return nhead
+
+
+def fa_encode(sd, image_features, src_text, nhead, src_len=None):
+    """image_features (B,1024,14,14) or (B,1024,196); src_text (B,S) -> (memory (B,196+S,d), key_len or None)."""
+    B = image_features.shape[0]
+    img = image_features.reshape(B, 1024, -1).permute(0, 2, 1)                               # FA:47 / FA:130
+    x = torch.cat([F.linear(img, sd["image_proj.weight"], sd["image_proj.bias"]),            # FA:48
+                   F.embedding(src_text, sd["text_embedding.weight"])], dim=1)               # FA:49-50
+    x = x + sd["pos_encoder.pe"][:, : x.shape[1]]                                            # FA:51
+    key_len = None if src_len is None else img.shape[1] + src_len
+    for l in range(count_layers(sd, "transformer.encoder.layers.")):
+        x = encoder_layer(sd, f"transformer.encoder.layers.{l}.", x, nhead, key_len)
+    if "transformer.encoder.norm.weight" in sd:                                              # nn.Transformer adds it
+        x = layer_norm(sd, "transformer.encoder.norm.", x)
+    return x, key_len
+
+
+def fa_decode_logits(sd, memory, tgt, nhead, mem_len=None):
+    """Teacher-forced decoder + head over tgt (B,T): logits (B,T,V)   (FA:53-57)."""
+    x = F.embedding(tgt, sd["text_embedding.weight"]) + sd["pos_decoder.pe"][:, : tgt.shape[1]]
+    for l in range(count_layers(sd, "transformer.decoder.layers.")):
+        x = decoder_layer(sd, f"transformer.decoder.layers.{l}.", x, memory, nhead, mem_len)
+    if "transformer.decoder.norm.weight" in sd:
+        x = layer_norm(sd, "transformer.decoder.norm.", x)
+    return F.linear(x, sd["output_linear.weight"], sd["output_linear.bias"])
+
+
+@torch.no_grad()
+def fa_forward(sd, image_features, src_text, tgt_text, nhead, src_len=None):
+    memory, key_len = fa_encode(sd, image_features.float(), src_text.long(), nhead, src_len)
+    return fa_decode_logits(sd, memory, tgt_text.long(), nhead, key_len)
+
+
+@torch.no_grad()
+def fa_greedy_decode(sd, image_features, src_text, start_token, max_len, nhead, src_len=None, forced=None,
+                     recompute=False):
+    """-> (ys (B,max_len) i64 with column 0 = start_token, logits (B,max_len-1,V)).  Batched with optional
+    per-question src_len (the reference is batch-1 and never pads, FA:136)."""
+    memory, key_len = fa_encode(sd, image_features.float(), src_text.long(), nhead, src_len)
+    B = memory.shape[0]
+    ys = torch.full((B, 1), start_token, dtype=torch.long)                                   # FA:136
+    fed = ys.clone()
+    emb, pe = sd["text_embedding.weight"], sd["pos_decoder.pe"][0]
+    dec = None if recompute else _CachedDecoder(sd, "transformer.decoder.layers.", memory, nhead, key_len)
+    logits = []
+    for t in range(max_len - 1):                                                             # FA:137
+        if recompute:
+            lg = fa_decode_logits(sd, memory, fed, nhead, key_len)[:, -1]                    # FA:138-143
+        else:
+            x = dec.step(F.embedding(fed[:, -1:], emb) + pe[t][None, None])
+            if "transformer.decoder.norm.weight" in sd:
+                x = layer_norm(sd, "transformer.decoder.norm.", x)
+            lg = F.linear(x[:, 0], sd["output_linear.weight"], sd["output_linear.bias"])
+        nxt = torch.argmax(lg, dim=1)                                                        # FA:144
+        logits.append(lg)
+        ys = torch.cat([ys, nxt[:, None]], dim=1)                                            # FA:145
+        fed = torch.cat([fed, (forced[:, t] if forced is not None else nxt)[:, None]], dim=1)
+    return ys, torch.stack(logits, dim=1)
+
+
+def parse_chain(final_chain, rev_vocab):
+    """run_inference_chain's parsing (FA:96-108): -> list of (func_token:int, [dependency step indices])."""
+    steps = []
+    for elem in final_chain:
+        parts = elem.strip().split()
+        deps = []
+        for tok in parts[1:]:
+            original = rev_vocab.get(int(tok), None)
+            if original is not None and original.isdigit():
+                deps.append(int(original))
+        steps.append((int(parts[0]), deps))
+    return steps
+
+
+@torch.no_grad()
+def fa_run_chain(sd, image_features, final_chain, rev_vocab, start_token, max_infer_len, nhead, forced=None,
+                 recompute=False):
+    """run_inference_chain (FA:83-124) for ONE question, cache kept as {step: [token ids]} (the reference keeps
+    the same tokens space-joined in a string).  Returns (cache, logits {step: (max_len-1, V)}).
+    `forced` {step: (max_len-1,) tokens}: teacher-forces the decode AND is what gets cached for that step."""
+    cache, all_logits = {}, {}
+    for i, (func, deps) in enumerate(parse_chain(final_chain, rev_vocab)):
+        src = [func]
+        for idx in deps:
+            src += cache.get(idx, [])                                                        # FA:109-116, missing -> ""
+        src_t = torch.tensor([src], dtype=torch.long)
+        fz = None if forced is None else torch.as_tensor(forced[i], dtype=torch.long)[None]
+        ys, lg = fa_greedy_decode(sd, image_features, src_t, start_token, max_infer_len, nhead, forced=fz,
+                                  recompute=recompute)
+        toks = ys[0].tolist()
+        if fz is not None:
+            toks = [start_token] + fz[0].tolist()
+        cache[i] = toks                                                                      # FA:120-121 (all tokens)
+        all_logits[i] = lg[0]
+    return cache, all_logits
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic CLEVR-shaped workloads shared by the tests and bench.py
+# ------------------------------------------------------------------------------------------------
+def iqap_inputs(B, seed=1234, relu=True):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, 196, 1024, generator=g)
+    if relu:
+        img.relu_()  # conv4 features are post-ReLU
+    q = torch.zeros(B, 46, dtype=torch.long)
+    for b in range(B):
+        n = int(torch.randint(8, 47, (1,), generator=g))
+        q[b, 0] = 1
+        q[b, 1:n - 1] = torch.randint(4, 85, (n - 2,), generator=g)
+        q[b, n - 1] = 2
+    return img, q
+
+
+def fa_vocab(V=170):
+    """ids 0..26 are the digit strings "0".."26" (dependency pointers), the rest are opaque tokens."""
+    return {i: (str(i) if i < 27 else f"tok{i}") for i in range(V)}
+
+
+def fa_programs(B, seed=4321, max_steps=25, V=170):
+    """CLEVR-shaped DAGs: n_steps~U[2,25]; step 0 is a root; later steps: 15 % new root, 75 % unary on the
+    previous step, 10 % binary on two distinct earlier steps.  -> func (B,S) i32, deps (B,S,2) i32, n_steps (B,)"""
+    g = torch.Generator().manual_seed(seed)
+    func = torch.zeros(B, max_steps, dtype=torch.int32)
+    deps = torch.full((B, max_steps, 2), -1, dtype=torch.int32)
+    n_steps = torch.randint(2, max_steps + 1, (B,), generator=g, dtype=torch.int32)
+    for b in range(B):
+        for i in range(int(n_steps[b])):
+            func[b, i] = int(torch.randint(27, min(67, V), (1,), generator=g))
+            if i == 0:
+                continue
+            r = float(torch.rand(1, generator=g))
+            if r < 0.15:
+                continue
+            if r < 0.90 or i < 2:
+                deps[b, i, 0] = i - 1
+            else:
+                a = int(torch.randint(0, i - 1, (1,), generator=g))
+                deps[b, i, 0] = a
+                deps[b, i, 1] = i - 1
+    return func, deps, n_steps
+
+
+def chain_strings(func_row, deps_row, n):
+    """arrays -> the reference's `final_chain_of_thought` strings (dependency k is written as vocab id k)."""
+    out = []
+    for i in range(int(n)):
+        toks = [str(int(func_row[i]))] + [str(int(d)) for d in deps_row[i] if int(d) >= 0]
+        out.append(" ".join(toks))
+    return out
