@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the batched Program Executor inference path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload iqap|fa]
+
+A "step" is one pass of the hot path over one batch of synthetic input on every GPU:
+  iqap (default, BASELINE configs[1]): VQAModel.forward on 1024 questions per GPU = encoder + answer head +
+       27 greedy program positions; 1 question = 27 program-steps.
+  fa   (configs[2]): run_inference_chain_batched on 4096 questions per GPU with CLEVR-shaped ragged programs;
+       1 chain element = 1 program-step.
+`value` is whole-job program-steps/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the
+same metric through the public host-buffer call (pinned host inputs uploaded and results downloaded inside
+the timed region).  N > 1: one process per GPU under torchrun, questions sharded, no per-step collective in
+the data path; the per-step result gather (answers + programs) over NCCL is inside the timed region.
+
+`--impl reference` times the reference's own CPU algorithm (oracle/executor_oracle.py in `recompute` mode: the
+decoder prefix and the cross K/V are recomputed every step exactly as the reference's PyTorch modules do) on
+the host cores, on a bounded sample of the same workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import warnings
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+warnings.filterwarnings("ignore", message="enable_nested_tensor")
+
+T_PROG = 27
+S_IQAP = 243
+D = 256
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# algorithmic work per kernel class and per question (S=243 valid rows, d=256, ff=2048, T=27)
+# ----------------------------------------------------------------------------------------------------------
+def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
+    d = D
+    w = {
+        "image_proj_gemm": ("tensor", 2 * 196 * 1024 * d),
+        "enc_qkv_gemm": ("tensor", 2 * S * d * 3 * d),
+        "enc_attention": ("tensor", 4 * S * S * d),
+        "enc_outproj_ln_gemm": ("tensor", 2 * S * d * d),
+        "enc_ffn1_gemm": ("tensor", 2 * S * d * ff),
+        "enc_ffn2_ln_gemm": ("tensor", 2 * S * d * ff),
+        "dec_cross_kv_gemm": ("tensor", n_dec * 2 * S * d * 2 * d),
+        "dec_step_gemms": ("tensor", n_dec * T * (2 * d * 3 * d + 3 * 2 * d * d + 4 * d * ff)),
+        # HBM-bound: every step re-reads the projected K and V of the memory (bf16), SURVEY H2
+        "dec_cross_attention": ("hbm", n_dec * T * S * 2 * d * 2),
+        "dec_self_attention": ("hbm", n_dec * sum((t + 1) * 2 * d * 2 for t in range(T))),
+        "dec_head_argmax": ("hbm", T * (d * 4 + 8)),
+        "answer_head": ("hbm", d * 2 + C * 4),
+        "embed_gather": ("hbm", (256 - 196) * d * 2),
+    }
+    return w
+
+
+IQAP_FLOPS_PER_QUESTION = 1.0983e9
+
+
+class ClockSampler:
+    """nvidia-smi style clock / throttle sampling DURING the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), threading.Event()
+        self.max_mhz = None
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover - NVML missing
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU legs (oracle; rank 0 only)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_iqap(sample_b, repeats, recompute=True):
+    """program-steps/s of the oracle on `sample_b` questions of the workload, best of `repeats`."""
+    from oracle import executor_oracle as orc
+    from explainable_spatial_vqa_b200 import inference_transformer_iqap as iqap
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = iqap.VQAModel(85, 256, 256, 32, 44, T_PROG, 196).eval().state_dict()
+    img, q = orc.iqap_inputs(sample_b, seed=1234)
+    orc.iqap_forward(sd, img[:4], q[:4], recompute=recompute)  # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.iqap_forward(sd, img, q, recompute=recompute)
+        best = min(best, time.perf_counter() - t0)
+    return sample_b * T_PROG / best, best
+
+
+def cpu_fa(n_questions, recompute=True):
+    """program-steps/s of the oracle chain (batch-1 loop, the reference's only mode)."""
+    from oracle import executor_oracle as orc
+    from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = fa.MultiModalTransformer(170, 256, 2, 1, 1, 512, 0.1, 50, 196).eval().state_dict()
+    func, deps, n_steps = orc.fa_programs(n_questions, seed=4321)
+    g = torch.Generator().manual_seed(4321)
+    img = torch.randn(n_questions, 1024, 14, 14, generator=g).relu_()
+    rev = orc.fa_vocab(170)
+    orc.fa_run_chain(sd, img[:1], orc.chain_strings(func[0], deps[0], 2), rev, 0, 20, 2, recompute=recompute)
+    t0 = time.perf_counter()
+    for b in range(n_questions):
+        orc.fa_run_chain(sd, img[b:b + 1], orc.chain_strings(func[b], deps[b], n_steps[b]), rev, 0, 20, 2,
+                         recompute=recompute)
+    dt = time.perf_counter() - t0
+    return float(n_steps.sum()) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_sample or (64 if args.workload == "iqap" else 2)
+    cores = os.cpu_count() or 1
+    times = []
+    units = 0.0
+    for i in range(args.warmup + args.steps):
+        if args.workload == "iqap":
+            v, dt = cpu_iqap(sample, 1)
+            u = sample * T_PROG
+        else:
+            v, dt = cpu_fa(sample)
+            u = v * dt
+        if i >= args.warmup:
+            times.append(dt)
+            units += u
+    total = sum(times)
+    value = units / total
+    line = {
+        "impl": "reference", "metric": "program_steps_per_s", "value": value, "unit": "program-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "program-steps/s", "cores": cores, "kind": "port",
+                         "cpu": cpu_model_name(),
+                         "sample": f"{sample} questions of the workload per step, oracle in the reference's "
+                                   "recompute-every-step form (torch CPU fp32, all host threads)"},
+        "e2e": {"value": value, "unit": "program-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    if args.workload == "iqap":
+        return {"workload": f"IQAP executor (VQAModel 85/256/256/32/44, 1 enc + 2 dec layers, ff 2048), batch {args.batch} "
+                            "questions per GPU, 27 program positions each, seq 243",
+                "batch_per_gpu": args.batch, "program_len": T_PROG,
+                "l2": "inputs are 822 MB of fp32 features per step (> 126 MB L2), activations 2.4 GB",
+                "gather": "per step: all_gather of answers + programs (NCCL) when n_gpus > 1"}
+    return {"workload": f"FA executor (MultiModalTransformer V=170 nhead 2, 1+1 layers, ff 512), batch {args.batch} "
+                        "questions per GPU, CLEVR-shaped ragged programs of 2..25 steps, 20 tokens per step",
+            "batch_per_gpu": args.batch,
+            "l2": "per-step activations exceed L2 (4096 questions x 128 KB encoder rows)",
+            "gather": "per step: all_gather of the final-step tokens (NCCL) when n_gpus > 1"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from explainable_spatial_vqa_b200 import sharding
+    from oracle import executor_oracle as orc
+
+    rank, local, world = sharding.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    B = args.batch
+
+    if args.workload == "iqap":
+        from explainable_spatial_vqa_b200 import inference_transformer_iqap as iqap
+        torch.manual_seed(0)
+        model = iqap.VQAModel(85, 256, 256, 32, 44, T_PROG, 196).eval().to(dev)
+        # synthetic conv4-like features (post-ReLU) generated on the device; questions from the CPU generator
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        img = torch.randn(B, 196, 1024, device=dev, generator=g).relu_()
+        _, q_cpu = orc.iqap_inputs(B, seed=1234 + rank, relu=False) if B <= 4096 else (None, None)
+        q = q_cpu.to(dev)
+        units_per_step = B * T_PROG
+        counts = [B] * world
+
+        def step():
+            ans, prog = model(img, q)
+            if world > 1:
+                both = torch.cat([ans.argmax(1, keepdim=True), prog], dim=1)
+                sharding.gather_varlen(both, counts)
+            return ans, prog
+
+        img_host = torch.empty(B, 196, 1024, dtype=torch.float32).pin_memory()
+        img_host.copy_(img)
+        q_host = q_cpu.pin_memory()
+
+        def step_e2e():
+            return model.forward_host(img_host, q_host, chunk=args.e2e_chunk)
+
+        h2d = img_host.numel() * 4 + q_host.numel() * 8
+        d2h = B * 32 * 4 + B * T_PROG * 8
+    else:
+        from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
+        torch.manual_seed(0)
+        model = fa.MultiModalTransformer(170, 256, 2, 1, 1, 512, 0.1, 50, 196).eval().to(dev)
+        g = torch.Generator(device=dev).manual_seed(4321 + rank)
+        img = torch.randn(B, 1024, 14, 14, device=dev, generator=g).relu_()
+        func, deps, n_steps = orc.fa_programs(B, seed=4321 + rank)
+        func, deps, n_steps = func.to(dev), deps.to(dev), n_steps.to(dev)
+        units_per_step = int(n_steps.sum())
+        counts = [B] * world
+
+        def step():
+            cache = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+            if world > 1:
+                last = cache[torch.arange(B, device=dev), (n_steps - 1).long()]
+                sharding.gather_varlen(last, counts)
+            return cache
+
+        img_host = torch.empty(B, 1024, 14, 14, dtype=torch.float32).pin_memory()
+        img_host.copy_(img)
+        f_h, d_h, n_h = func.cpu().pin_memory(), deps.cpu().pin_memory(), n_steps.cpu().pin_memory()
+
+        def step_e2e():
+            cache = fa.run_inference_chain_batched(model, img_host.to(dev, non_blocking=True), f_h.to(dev, non_blocking=True),
+                                                   d_h.to(dev, non_blocking=True), n_h.to(dev, non_blocking=True), 0, 20)
+            return cache.cpu()
+
+        h2d = img_host.numel() * 4 + f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4
+        d2h = B * func.shape[1] * 20 * 4
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        launches0 = model.native_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        return ms, model.native_launch_count() - launches0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    value = world * units_per_step * args.steps / (ms * 1e-3)
+
+    # end-to-end: host buffers, H2D + D2H inside the timed region (wall clock around a synchronous call ==
+    # device time here; still reported from CUDA events for consistency)
+    ms_e2e, _ = timed(step_e2e, max(1, args.steps // 2), 1)
+    e2e_value = world * units_per_step * max(1, args.steps // 2) / (ms_e2e * 1e-3)
+
+    # live per-kernel-class timing (CUDA events on the launch stream) over a few extra steps -> roofline
+    roofline, kernels = None, None
+    if rank == 0 or world == 1:
+        h = model._native()
+        prof_steps = 3
+        torch.cuda.synchronize()
+        h.profile_begin()
+        for _ in range(prof_steps):
+            step()
+        prof = h.profile_end()
+        total = sum(v[0] for v in prof.values())
+        kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps,
+                       "share": v[0] / total} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        if args.workload == "iqap":
+            work = iqap_work_per_question()
+            top = next(k for k in kernels if k in work)
+            kind, per_q = work[top]
+            per_launch = per_q * B / kernels[top]["launches_per_step"]
+            dur = kernels[top]["ms_per_step"] / kernels[top]["launches_per_step"] * 1e-3
+            if kind == "tensor":
+                ach = per_launch / dur / 1e12
+                roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                            "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+            else:
+                ach = per_launch / dur / 1e9
+                roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy)"}
+            roofline["algorithmic_per_launch"] = per_launch
+            roofline["avg_launch_ms"] = dur * 1e3
+            # whole-step tensor-core utilisation: algorithmic FLOPs of the model / step time / peak
+            roofline["model_flops_frac_of_bf16_peak"] = (IQAP_FLOPS_PER_QUESTION * B / (ms / args.steps * 1e-3)) / (
+                peaks["bf16_tflops_sustained"] * 1e12)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.workload == "iqap":
+            sample = args.cpu_sample or 64
+            v, dt = cpu_iqap(sample, 2)
+            what = f"{sample} of the {B} questions, best of 2 ({dt:.1f} s each)"
+        else:
+            sample = args.cpu_sample or 4
+            v, dt = cpu_fa(sample)
+            what = f"{sample} of the {B} questions as a batch-1 loop ({dt:.1f} s)"
+        cpu_baseline = {"value": v, "unit": "program-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "cpu": cpu_model_name(),
+                        "sample": what + "; oracle in the reference's recompute-every-step form, torch CPU fp32"}
+
+    if rank == 0:
+        line = {
+            "metric": "program_steps_per_s", "value": value, "unit": "program-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args),
+            "questions_per_s": value / T_PROG if args.workload == "iqap" else world * B * args.steps / (ms * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "program-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / max(1, args.steps // 2)},
+            "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="iqap", choices=["iqap", "fa"])
+    ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
+    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--cpu-sample", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 1024 if args.workload == "iqap" else 4096
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

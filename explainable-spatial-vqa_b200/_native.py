@@ -75,6 +75,10 @@ SIGNATURES = {
     "b200vqa_last_error": (C.c_char_p, []),
     "b200vqa_version": (C.c_char_p, []),
     "b200vqa_launch_count": (C.c_uint64, [_vp]),
+    "b200vqa_profile_num_tags": (C.c_int, []),
+    "b200vqa_profile_tag_name": (C.c_char_p, [C.c_int]),
+    "b200vqa_profile_begin": (C.c_int, [_vp]),
+    "b200vqa_profile_end": (C.c_int, [_vp, _vp, _vp]),
     "b200vqa_iqap_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
@@ -172,6 +176,17 @@ class Handle:
 
     def workspace_bytes(self, B: int) -> int:
         return int(self._lib.b200vqa_workspace_bytes(self._h, int(B)))
+
+    def profile_begin(self):
+        check(self._lib.b200vqa_profile_begin(self._h), "b200vqa_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{kernel class: (total ms, launches)} since profile_begin (synchronises the device)."""
+        n = self._lib.b200vqa_profile_num_tags()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        check(self._lib.b200vqa_profile_end(self._h, ms, cnt), "b200vqa_profile_end")
+        return {self._lib.b200vqa_profile_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
     def close(self):
         if self._h:

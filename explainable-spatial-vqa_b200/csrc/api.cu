@@ -73,6 +73,21 @@ struct Workspace {
 
 using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t>;
 
+// kernel classes for the built-in profiler (b200vqa_profile_*)
+enum Tag : int {
+  kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFinalLn,
+  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
+};
+const char* const kTagNames[kNumTags] = {
+    "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
+    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_step_gemms", "dec_self_attention",
+    "dec_cross_attention", "dec_head_argmax", "misc"};
+
+struct ProfRec {
+  int tag;
+  cudaEvent_t a, b;
+};
+
 }  // namespace
 
 struct b200vqa_handle {
@@ -95,6 +110,9 @@ struct b200vqa_handle {
   Workspace ws;
   std::map<TmapKey, CUtensorMap> tmaps;
   uint64_t launches = 0;
+  int cur_tag = kTagMisc;
+  bool profiling = false;
+  std::vector<ProfRec> prof;
 
   // host-buffer entry point
   cudaStream_t copy_stream = nullptr;
@@ -362,10 +380,20 @@ int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, 
 
 #define LAUNCH_OK(h, expr)                                                                        \
   do {                                                                                            \
+    ProfRec pr__{(h)->cur_tag, nullptr, nullptr};                                                 \
+    if ((h)->profiling) {                                                                         \
+      cudaEventCreate(&pr__.a);                                                                   \
+      cudaEventCreate(&pr__.b);                                                                   \
+      cudaEventRecord(pr__.a, s);                                                                 \
+    }                                                                                             \
     cudaError_t e__ = (expr);                                                                     \
     if (e__ != cudaSuccess) {                                                                     \
       set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);     \
       return B200VQA_ERR_CUDA;                                                                    \
+    }                                                                                             \
+    if ((h)->profiling) {                                                                         \
+      cudaEventRecord(pr__.b, s);                                                                 \
+      (h)->prof.push_back(pr__);                                                                  \
     }                                                                                             \
     ++(h)->launches;                                                                              \
   } while (0)
@@ -424,8 +452,10 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
   __nv_bfloat16* out = w.mem;
   for (int l = 0; l < d.n_enc_layers; ++l) {
     const LayerPacked& L = h->enc[l];
+    h->cur_tag = kTagEncQkv;
     RC_OK(gemm_bias(h, false, in, M, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.qkv, s));
     {
+      h->cur_tag = kTagEncAttn;
       const CUtensorMap *tq, *tkv;
       RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 128, &tq));
       RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 256, &tkv));
@@ -438,12 +468,16 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
       ap.scale = 1.f / sqrtf(float(kD / d.nhead));
       LAUNCH_OK(h, launch_enc_attention(*tq, *tkv, w.qkv, ap, s));
     }
+    h->cur_tag = kTagEncOutLn;
     RC_OK(gemm_res_ln(h, w.attn, M, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.x1, nullptr, s));
+    h->cur_tag = kTagEncFfn1;
     RC_OK(gemm_bias(h, true, w.x1, M, kD, L.w1, d.dim_ff, L.b1, w.hid, s));
+    h->cur_tag = kTagEncFfn2Ln;
     RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s));
     std::swap(in, out);
   }
   // `in` now holds the last layer's output
+  h->cur_tag = kTagEncFinalLn;
   if (h->enc_fn_w) LAUNCH_OK(h, launch_layernorm_rows(in, in, h->enc_fn_w, h->enc_fn_b, d.layer_norm_eps, M, s));
   *memory = in;
   return B200VQA_OK;
@@ -478,6 +512,7 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
   const auto& d = h->d;
   const int M = B * kLP;
   // cross-attention K|V of the memory: once per question (the reference recomputes it every step)
+  h->cur_tag = kTagDecCrossKv;
   for (int l = 0; l < d.n_dec_layers; ++l) {
     const MhaPacked& ca = h->dec[l].cross_attn;
     RC_OK(gemm_bias(h, false, memory, M, kD, ca.w_in + size_t(kD) * kD, 2 * kD, ca.b_in + kD, w.ckv[l], s));
@@ -498,6 +533,7 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     ep.cache_ld = io.cache_ld;
     ep.n_steps = io.n_steps;
     ep.step = io.step;
+    h->cur_tag = kTagEmbed;
     LAUNCH_OK(h, launch_dec_embed_start(ep, s));
   }
   for (int t = 0; t < io.steps; ++t) {
@@ -506,6 +542,7 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
       const LayerPacked& L = h->dec[l];
       const bool last = l == d.n_dec_layers - 1;
       __nv_bfloat16* out = w.dxo[l & 1];
+      h->cur_tag = kTagDecGemm;
       RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.dqkv, s));
       DecSelfAttnParams sp;
       sp.B = B;
@@ -516,7 +553,9 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
       sp.k_cache = w.kc[l];
       sp.v_cache = w.vc[l];
       sp.out = w.dattn;
+      h->cur_tag = kTagDecSelfAttn;
       LAUNCH_OK(h, launch_dec_self_attn(sp, s));
+      h->cur_tag = kTagDecGemm;
       RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.dx1, nullptr, s));
       RC_OK(gemm_bias(h, false, w.dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, w.dq, s));
       DecCrossAttnParams cp;
@@ -530,7 +569,9 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
       cp.lens = lens;
       cp.const_len = const_len;
       cp.out = w.dattn;
+      h->cur_tag = kTagDecCrossAttn;
       LAUNCH_OK(h, launch_dec_cross_attn(cp, s));
+      h->cur_tag = kTagDecGemm;
       RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, w.dx1, L.n2w, L.n2b, w.dx2, nullptr,
                         s));
       RC_OK(gemm_bias(h, true, w.dx2, B, kD, L.w1, d.dim_ff, L.b1, w.dhid, s));
@@ -563,6 +604,7 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     hp.cache_store_forced = io.cache_store_forced;
     hp.n_steps = io.n_steps;
     hp.step = io.step;
+    h->cur_tag = kTagDecHead;
     LAUNCH_OK(h, launch_dec_head(hp, s));
   }
   return B200VQA_OK;
@@ -586,10 +628,12 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
   Workspace& w = h->ws;
   const auto& d = h->d;
   const int S = 1 + d.n_img_tokens + d.max_q_len;
+  h->cur_tag = kTagEmbed;
   LAUNCH_OK(h, launch_iqap_embed(q, B, d.max_q_len, h->cls, h->enc_emb, d.enc_vocab, h->pe_enc, d.n_img_tokens, w.x, s));
   {
     // image_proj straight from the caller's fp32 features (tf32 tensor-core math), +bias +PE, written into
     // rows 1..196 of each question's block (this is the reference's torch.cat, IQAP:164)
+    h->cur_tag = kTagImgProj;
     GemmParams p;
     p.bias = h->img_b;
     p.out = w.x;
@@ -606,8 +650,10 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
   RC_OK(run_encoder(h, B, nullptr, S, &memory, s));
   if (opt_memory) {
     // seq-first [S, B_total, d]: this chunk fills columns b0..b0+B
+    h->cur_tag = kTagMisc;
     LAUNCH_OK(h, launch_memory_export(memory, S, B, B_total, opt_memory + size_t(b0) * kD, s));
   }
+  h->cur_tag = kTagAnswer;
   LAUNCH_OK(h, launch_answer_head(memory, B, h->ans_w0t, h->ans_b0, d.answer_hidden, h->ans_w1, h->ans_b1,
                                   d.num_classes, answer, s));
   DecodeIO io;
@@ -724,6 +770,42 @@ B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B) {
 
 B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h) { return h ? h->launches : 0; }
 
+// ------------------------------------------------------------------------------------------------ profiler
+B200VQA_API int b200vqa_profile_num_tags(void) { return kNumTags; }
+B200VQA_API const char* b200vqa_profile_tag_name(int tag) { return (tag >= 0 && tag < kNumTags) ? kTagNames[tag] : ""; }
+
+B200VQA_API int b200vqa_profile_begin(b200vqa_handle* h) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  h->profiling = true;
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_profile_end(b200vqa_handle* h, float* ms_per_tag, int32_t* launches_per_tag) {
+  B200VQA_REQUIRE(h != nullptr && ms_per_tag && launches_per_tag, "NULL argument");
+  RC_OK(set_device(h));
+  h->profiling = false;
+  B200VQA_CUDA_OK(cudaDeviceSynchronize());
+  for (int t = 0; t < kNumTags; ++t) {
+    ms_per_tag[t] = 0.f;
+    launches_per_tag[t] = 0;
+  }
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    B200VQA_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_tag[r.tag] += ms;
+    launches_per_tag[r.tag] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  return B200VQA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ IQAP
 B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_features, const int64_t* questions, int B,
                          int program_len, float* answer, int64_t* programs, float* opt_step_logits,
@@ -767,6 +849,7 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
   for (int b0 = 0; b0 < B; b0 += cap) {
     const int nb = std::min(cap, B - b0);
     // seq-first memory interleaves questions: a chunk is the column range [b0, b0+nb) of every row
+    h->cur_tag = kTagMisc;
     LAUNCH_OK(h, launch_memory_import(memory + size_t(b0) * kD, S, nb, B, h->ws.mem, s));
     DecodeIO io;
     io.start_token = 1;
@@ -871,8 +954,10 @@ B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_
   for (int b0 = 0; b0 < B; b0 += cap) {
     const int nb = std::min(cap, B - b0);
     // channel-major fp32 [nb,1024,196] -> token-major bf16 [nb*196,1024] (the reference's view+permute, FA:47,130)
+    h->cur_tag = kTagMisc;
     LAUNCH_OK(h, launch_transpose_cast(image_features + size_t(b0) * d.img_feat_dim * d.n_img_tokens, h->ws.img_t, nb,
                                        d.img_feat_dim, d.n_img_tokens, s));
+    h->cur_tag = kTagImgProj;
     GemmParams p;
     p.bias = h->img_b;
     p.out = out + size_t(b0) * d.n_img_tokens * kD;
@@ -901,6 +986,7 @@ static int fa_one_step(b200vqa_handle* h, const __nv_bfloat16* img_tokens, FaBui
   bp.n_img = d.n_img_tokens;
   bp.x = w.x;
   bp.lens = w.lens;
+  h->cur_tag = kTagEmbed;
   LAUNCH_OK(h, launch_fa_build_src(bp, s));
   __nv_bfloat16* memory = nullptr;
   RC_OK(run_encoder(h, B, w.lens, 0, &memory, s));

@@ -143,6 +143,14 @@ B200VQA_API const char* b200vqa_version(void);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h);
 
+/* Built-in per-kernel-class timer (CUDA events on the caller's stream around every launch). bench.py uses it
+ * for the live roofline numbers; it serialises nothing but adds two event records per launch, so it is
+ * only enabled for a few untimed steps.  ms_per_tag / launches_per_tag have b200vqa_profile_num_tags() slots. */
+B200VQA_API int b200vqa_profile_num_tags(void);
+B200VQA_API const char* b200vqa_profile_tag_name(int tag);
+B200VQA_API int b200vqa_profile_begin(b200vqa_handle* h);
+B200VQA_API int b200vqa_profile_end(b200vqa_handle* h, float* ms_per_tag, int32_t* launches_per_tag);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* IQAP                                                                                                   */
 /* ---------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,161 @@
+"""CPU: host-side logic of the drop-in surface - state-dict compatibility, vocabulary / chain parsing, the
+sharding helpers, and the world_size-2 gather over gloo."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
+from explainable_spatial_vqa_b200 import inference_transformer_iqap as iqap
+from explainable_spatial_vqa_b200 import sharding
+from oracle import executor_oracle as orc
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_iqap_state_dict_layout():
+    """names/shapes of the reference's VQAModel(85,256,256,32,44,27,196)."""
+    sd = common.seeded_iqap().state_dict()
+    assert len(sd) == 61 and sum(p.numel() for p in common.seeded_iqap().parameters()) == 4853580
+    want = {"cls_token": (1, 1, 256), "image_proj.weight": (256, 1024), "embedding.weight": (85, 256),
+            "pos_encoder.pe": (243, 1, 256), "pos_decoder.pe": (28, 1, 256),
+            "transformer_encoder.layers.0.self_attn.in_proj_weight": (768, 256),
+            "transformer_encoder.layers.0.linear1.weight": (2048, 256),
+            "transformer_decoder.layers.1.multihead_attn.out_proj.weight": (256, 256),
+            "transformer_decoder.layers.0.norm3.bias": (256,),
+            "answer_classifier.0.weight": (256, 256), "answer_classifier.3.weight": (32, 256),
+            "program_decoder_embedding.weight": (44, 256), "program_output.weight": (44, 256)}
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert float(sd["embedding.weight"][0].abs().sum()) == 0.0  # padding_idx row
+    g = common.load_golden("iqap_b4.npz")
+    assert sorted(sd) == [str(k) for k in g["sd_keys"]]  # the reference's own key set
+
+
+def test_fa_state_dict_layout():
+    m = common.seeded_fa()
+    sd = m.state_dict()
+    assert len(sd) == 41 and sum(p.numel() for p in m.parameters()) == 1668522
+    for k, shape in {"pos_encoder.pe": (1, 246, 256), "pos_decoder.pe": (1, 50, 256),
+                     "transformer.encoder.norm.weight": (256,), "transformer.decoder.norm.bias": (256,),
+                     "transformer.decoder.layers.0.linear1.weight": (512, 256), "output_linear.weight": (170, 256),
+                     "text_embedding.weight": (170, 256)}.items():
+        assert tuple(sd[k].shape) == shape, k
+    g = common.load_golden("fa_nhead2.npz")
+    assert sorted(sd) == [str(k) for k in g["sd_keys"]]
+
+
+def test_positional_encoding_and_mask():
+    pe = iqap.PositionalEncoding(256, max_len=30).pe
+    assert pe.shape == (30, 1, 256)
+    p, i = 7, 5
+    w = np.exp(-(2 * i) * np.log(10000.0) / 256)
+    assert abs(float(pe[p, 0, 2 * i]) - np.sin(p * w)) < 1e-6 and abs(float(pe[p, 0, 2 * i + 1]) - np.cos(p * w)) < 1e-6
+    assert torch.allclose(fa.PositionalEncoding(256, max_len=30).pe[0], pe[:, 0], atol=1e-6)
+    m = iqap.generate_square_subsequent_mask(4)
+    assert m[2, 3] == float("-inf") and m[3, 2] == 0 and m[1, 1] == 0
+    x = torch.zeros(5, 2, 256)
+    assert torch.equal(iqap.PositionalEncoding(256, max_len=30).eval()(x)[:, 0], pe[:5, 0])
+
+
+def test_vocab_helpers(tmp_path):
+    vocab = {"<PAD>": 0, "<UNK>": 1, "0": 2, "1": 3, "[": 4, "]": 5, "scene": 6}
+    p = tmp_path / "vocab.json"
+    p.write_text(json.dumps(vocab))
+    v, rev = fa.load_vocab(str(p))
+    assert v == vocab and rev[6] == "scene" and rev[2] == "0"
+    assert fa.decode_tokens([6, 4, 99], rev) == "scene [ <unk>"
+    assert fa.tokenize_field("filter_color", "function") == ["filter_color"]
+    assert fa.tokenize_field("", "function") == []
+    assert fa.tokenize_field("[0.3 0.1] red [ 0.5]", "output") == ["[", "0.3", "0.1", "]", "red", "[", "0.5", "]"]
+
+
+def test_chain_parsing_follows_reference_rules(caplog):
+    rev = {2: "0", 3: "1", 4: "2", 50: "scene", 51: "filter", 60: "red"}
+    chain = ["50", "51 2", "51 3 60", "52 2 4"]
+    func, deps = fa.chain_to_arrays(chain, rev)
+    assert func.tolist() == [50, 51, 51, 52]
+    assert deps.tolist() == [[-1, -1], [0, -1], [1, -1], [0, 2]]  # non-digit token 60 skipped with a warning
+    assert any("not recognized as a digit" in r.message for r in caplog.records)
+    with pytest.raises(ValueError):
+        fa.chain_to_arrays(["50 2 3 4"], rev)
+    # same rule set as the oracle's parser
+    assert [d for _, d in orc.parse_chain(chain, rev)] == [[], [0], [1], [0, 2]]
+
+
+def test_synthetic_programs_are_clevr_shaped():
+    func, deps, n = orc.fa_programs(64, seed=4321)
+    assert func.shape == (64, 25) and deps.shape == (64, 25, 2)
+    assert int(n.min()) >= 2 and int(n.max()) <= 25
+    for b in range(64):
+        assert deps[b, 0].tolist() == [-1, -1]
+        for i in range(int(n[b])):
+            assert all(int(d) < i for d in deps[b, i])
+            assert 27 <= int(func[b, i]) < 67
+    strings = orc.chain_strings(func[0], deps[0], n[0])
+    f2, d2 = fa.chain_to_arrays(strings, orc.fa_vocab(170))
+    assert f2.tolist() == func[0, : int(n[0])].tolist() and d2.tolist() == deps[0, : int(n[0])].tolist()
+
+
+def test_shard_ranges_partition_the_batch():
+    for n in (0, 1, 7, 1024, 150000):
+        for w in (1, 2, 4, 8):
+            parts = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+    costs = [int(c) for c in orc.fa_programs(200, seed=1)[2]]
+    parts = sharding.balanced_ranges(costs, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 200 and all(parts[i][1] == parts[i + 1][0] for i in range(7))
+    loads = [sum(costs[lo:hi]) for lo, hi in parts]
+    assert max(loads) <= 1.25 * (sum(costs) / 8) + 25
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 4, 4)
+
+
+GLOO_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {repo!r})
+import torch.distributed as dist
+from explainable_spatial_vqa_b200 import sharding
+rank, local, world = sharding.init_from_env("gloo")
+N = 11
+lo, hi = sharding.shard_range(N, rank, world)
+full = torch.arange(N * 3, dtype=torch.int64).view(N, 3)
+mine = full[lo:hi].clone()                       # this rank's "programs"
+counts = [sharding.shard_range(N, r, world)[1] - sharding.shard_range(N, r, world)[0] for r in range(world)]
+got = sharding.gather_varlen(mine, counts)
+assert torch.equal(got, full), (rank, got)
+assert sharding.max_over_ranks(float(rank + 1)) == float(world)
+assert sharding.sum_over_ranks(1.0) == float(world)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_gather_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(repo=REPO))
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "program-steps/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

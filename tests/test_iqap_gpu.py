@@ -1,0 +1,131 @@
+"""GPU parity of the IQAP path (VQAModel.forward through the C ABI) against the CPU oracle and the golden
+outputs of the reference."""
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import executor_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    return common.seeded_iqap().cuda()
+
+
+def cpu_sd(model):
+    return {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+
+def test_teacher_forced_logits_and_answer_match_oracle(model):
+    img, q = orc.iqap_inputs(8, seed=1234)
+    ref = orc.iqap_forward(cpu_sd(model), img, q)
+    ans, prog, logits, memory = model.forward_detailed(img.cuda(), q.cuda(), forced_programs=ref["programs"].cuda(),
+                                                       want_logits=True, want_memory=True)
+    torch.cuda.synchronize()
+    assert common.rel_err(memory, ref["memory"]) < common.LOGIT_REL_TOL
+    assert common.rel_err(ans, ref["answer"]) < common.LOGIT_REL_TOL
+    assert common.rel_err(logits, ref["logits"]) < common.LOGIT_REL_TOL
+    frac, err = common.check_tokens_where_decisive(prog, ref["programs"], ref["logits"], logits, "iqap programs")
+    print(f"decisive fraction {frac:.3f}, max logit error {err:.3e}")
+    # the answer argmax: exact where decisive
+    am = common.margins(ref["answer"])
+    aerr = float((ans.cpu() - ref["answer"]).abs().max())
+    dec = am > 4 * aerr
+    assert torch.equal(ans.cpu().argmax(1)[dec], ref["answer"].argmax(1)[dec])
+
+
+def test_matches_reference_golden(model):
+    g = common.load_golden("iqap_b4.npz")
+    if not common.weights_match_golden(cpu_sd(model), g):
+        pytest.skip("seeded init differs from the golden run")
+    img, q = orc.iqap_inputs(4, seed=1234)
+    ans, prog, logits, _ = model.forward_detailed(img.cuda(), q.cuda(), forced_programs=torch.from_numpy(g["programs"]).cuda(),
+                                                  want_logits=True)
+    assert common.rel_err(ans, g["answer"]) < common.LOGIT_REL_TOL
+    assert common.rel_err(logits, g["logits"]) < common.LOGIT_REL_TOL
+    common.check_tokens_where_decisive(prog, g["programs"], g["logits"], logits, "iqap golden")
+
+
+def test_free_running_equals_forward_surface(model):
+    """The two-value reference surface, free-running decode; deterministic and chunk-invariant."""
+    img, q = orc.iqap_inputs(6, seed=99)
+    a1, p1 = model(img.cuda(), q.cuda())
+    a2, p2 = model(img.cuda(), q.cuda())
+    assert a1.shape == (6, 32) and p1.shape == (6, 27) and p1.dtype == torch.int64
+    assert torch.equal(a1, a2) and torch.equal(p1, p2)
+    a3, p3 = model(img[:3].cuda(), q[:3].cuda())
+    assert torch.equal(a3, a1[:3]) and torch.equal(p3, p1[:3])  # no cross-sample arithmetic
+    assert int(p1.min()) >= 0 and int(p1.max()) < 44
+
+
+def test_decisive_weights_free_running_exact_match():
+    """With the program head sharpened (x8) greedy decisions are decisive and the free-running token
+    sequences match the oracle exactly on every decisive prefix."""
+    m = common.seeded_iqap()
+    with torch.no_grad():
+        m.program_output.weight.mul_(8.0)
+    m = m.cuda()
+    img, q = orc.iqap_inputs(8, seed=7)
+    ref = orc.iqap_forward(cpu_sd(m), img, q)
+    _, prog = m(img.cuda(), q.cuda())
+    prog = prog.cpu()
+    mg = common.margins(ref["logits"])
+    ok_rows = 0
+    for b in range(8):
+        # compare up to the first non-decisive decision (after a legit near-tie flip the sequences may diverge)
+        t_end = 27
+        for t in range(27):
+            if mg[b, t] < 0.05:
+                t_end = t
+                break
+        assert torch.equal(prog[b, :t_end], ref["programs"][b, :t_end]), (b, t_end)
+        ok_rows += t_end == 27
+    assert ok_rows >= 2
+
+
+def test_autoregressive_program_generation_from_memory(model):
+    img, q = orc.iqap_inputs(5, seed=3)
+    sd = cpu_sd(model)
+    memory = orc.iqap_encode(sd, img, q)          # (B,S,d) oracle memory
+    ref_tok, ref_logits = orc.iqap_decode(sd, memory, 27)
+    got = model.autoregressive_program_generation(memory.transpose(0, 1).contiguous().cuda(), 27).cpu()
+    mg = common.margins(ref_logits)
+    for b in range(5):
+        t_end = next((t for t in range(27) if mg[b, t] < 0.02), 27)
+        assert torch.equal(got[b, :t_end], ref_tok[b, :t_end])
+
+
+def test_chunked_batch_and_host_entry(model):
+    """B larger than the workspace chunk (512) and the host-buffer entry point give the same results."""
+    img, q = orc.iqap_inputs(600, seed=11)
+    a_dev, p_dev = model(img.cuda(), q.cuda())
+    a_host, p_host = model.forward_host(img.pin_memory(), q.pin_memory(), chunk=128)
+    assert torch.equal(a_dev.cpu(), a_host) and torch.equal(p_dev.cpu(), p_host)
+    a_small, p_small = model(img[520:530].cuda(), q[520:530].cuda())
+    assert torch.equal(a_small, a_dev[520:530]) and torch.equal(p_small, p_dev[520:530])
+
+
+def test_state_dict_roundtrip_and_refresh(model):
+    m2 = common.seeded_iqap(seed=5).cuda()
+    img, q = orc.iqap_inputs(2, seed=1)
+    a_before, _ = m2(img.cuda(), q.cuda())
+    m2.load_state_dict(model.state_dict())       # in-place parameter update -> packed weights must refresh
+    a_after, p_after = m2(img.cuda(), q.cuda())
+    a_ref, p_ref = model(img.cuda(), q.cuda())
+    assert not torch.equal(a_before, a_after)
+    assert torch.equal(a_after, a_ref) and torch.equal(p_after, p_ref)
+
+
+def test_cpu_tensors_raise(model):
+    from explainable_spatial_vqa_b200 import _native as nat
+    img, q = orc.iqap_inputs(1)
+    with pytest.raises(nat.NativeError):
+        model(img, q.cuda())
+
+
+def test_empty_batch(model):
+    a, p = model(torch.zeros(0, 196, 1024, device="cuda"), torch.zeros(0, 46, dtype=torch.long, device="cuda"))
+    assert a.shape == (0, 32) and p.shape == (0, 27)
