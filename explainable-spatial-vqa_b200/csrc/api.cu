@@ -71,7 +71,7 @@ struct Workspace {
   __nv_bfloat16* img_t = nullptr;  // FA: transposed + cast image features [cap*196, 1024]
 };
 
-using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t>;
+using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>;
 
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
@@ -357,14 +357,16 @@ int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
 // ---------------------------------------------------------------------------------------------
 // GEMM helpers
 // ---------------------------------------------------------------------------------------------
+// box_cols == 0: 128-byte swizzled operand box; otherwise the un-swizzled {box_cols, box_rows} store box
 int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
-             uint32_t box_rows, const CUtensorMap** out) {
-  TmapKey key{base, int(type), rows, cols, ld, box_rows};
+             uint32_t box_rows, const CUtensorMap** out, uint32_t box_cols = 0) {
+  TmapKey key{base, int(type), rows, cols, ld, box_rows, box_cols};
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
     if (h->tmaps.size() > 4096) h->tmaps.clear();
     CUtensorMap m;
-    int rc = make_tmap_2d(&m, base, type, rows, cols, ld, box_rows);
+    int rc = box_cols ? make_tmap_2d_store(&m, base, type, rows, cols, ld, box_cols, box_rows)
+                      : make_tmap_2d(&m, base, type, rows, cols, ld, box_rows);
     if (rc != B200VQA_OK) return rc;
     it = h->tmaps.emplace(key, m).first;
   }
@@ -403,15 +405,23 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
          GemmParams p, cudaStream_t s) {
   if (M <= 0) return B200VQA_OK;
   const TmapType ty = tf32 ? TmapType::kF32 : TmapType::kBF16;
-  const int bn = 256;
-  const CUtensorMap *ta, *tw;
+  // narrower tiles when there are too few 128-row tiles to occupy the SMs (the decode GEMMs, M = batch)
+  int bn = 256;
+  if (epi == kEpiBias || epi == kEpiBiasRelu) {
+    const int tiles_m = (M + 127) / 128;
+    if (tiles_m * (N / 256) < h->num_sms / 2 && N % 128 == 0) bn = 128;
+    if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0) bn = 64;
+  }
+  const CUtensorMap *ta, *tw, *to;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(K), uint64_t(lda), 128, &ta));
   RC_OK(get_tmap(h, W, ty, uint64_t(N), uint64_t(K), uint64_t(K), bn, &tw));
+  if (epi == kEpiBiasPeRemap) to = ta;  // unused by that epilogue
+  else RC_OK(get_tmap(h, p.out, TmapType::kBF16, uint64_t(M), uint64_t(N), uint64_t(p.ldc), 32, &to, 32));
   p.M = M;
   p.N = N;
   p.K = K;
-  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, p, h->num_sms, s));
+  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, *to, p, h->num_sms, s));
   return B200VQA_OK;
 }
 
@@ -1132,9 +1142,11 @@ B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   B200VQA_CUDA_OK(cudaGetDevice(&dev));
   RC_OK(require_sm100(dev, &num_sms));
   const TmapType ty = a->tf32 ? TmapType::kF32 : TmapType::kBF16;
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, to;
   RC_OK(make_tmap_2d(&ta, a->A, ty, uint64_t(a->M), uint64_t(a->K), uint64_t(a->K), 128));
   RC_OK(make_tmap_2d(&tw, a->W, ty, uint64_t(a->N), uint64_t(a->K), uint64_t(a->K), uint32_t(a->block_n)));
+  if (a->epilogue == kEpiBiasPeRemap) to = ta;
+  else RC_OK(make_tmap_2d_store(&to, a->out, TmapType::kBF16, uint64_t(a->M), uint64_t(a->N), uint64_t(a->ldc), 32, 32));
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.bias = a->bias;
@@ -1150,7 +1162,8 @@ B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   p.row_off = a->row_off;
   p.pe = a->pe;
   p.pe_off = a->pe_off;
-  B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, p, num_sms, static_cast<cudaStream_t>(stream)));
+  B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, to, p, num_sms,
+                              static_cast<cudaStream_t>(stream)));
   return B200VQA_OK;
 }
 

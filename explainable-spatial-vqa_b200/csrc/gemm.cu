@@ -9,13 +9,21 @@
 //   linear1 + ReLU                  (transformer.py _ff_block) ReLU epilogue
 //   linear2 + residual + norm       LN epilogue
 //
-// Structure (one CTA per SM, 192 threads):
-//   warp 0      : TMA producer   - A tile [128 x 128B] and W tile [BN x 128B] per k-block into a smem ring
-//   warp 1      : MMA issuer     - tcgen05.mma (M=128, N=BN, K=32B) accumulating into TMEM; owns TMEM alloc
-//   warps 2..5  : epilogue       - tcgen05.ld the 128 x BN fp32 accumulator (one row per thread), fused
-//                                  bias / ReLU / residual+LayerNorm / positional-encoding, bf16 stores
-// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
-// mainloop of tile i+1. Tiles are walked n-fastest so CTAs running concurrently share A rows in L2.
+// Structure (one CTA per SM, 320 threads):
+//   warp 0      : TMA producer   - operand tiles into shared memory (128-byte swizzle)
+//   warp 1      : MMA issuer     - tcgen05.mma (M=128, N=BN, K=32 B) accumulating into TMEM; owns the TMEM allocation
+//   warps 2..9  : epilogue       - two warps per TMEM lane quarter, each taking every other 32-column chunk:
+//                                  tcgen05.ld -> fused bias / ReLU / residual+LayerNorm -> bf16 tile staged in
+//                                  shared memory -> TMA store (coalesced; rows >= M are clipped by the tensor map)
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop
+// of tile i+1.
+//
+// Operand staging has two modes, chosen per launch:
+//   W-stationary (K <= 4 k-blocks, i.e. every K=256 layer): the CTA walks a contiguous range of tiles in
+//     n-major order, keeps its W[n-tile] (BN x K) resident in shared memory and streams only A through a
+//     4-stage ring.  With K=256 a 128x256 tile is just 2048 tensor-core cycles; re-fetching W per tile would
+//     need ~180 GB/s per SM from L2, three times what the L2 can give all 148 SMs at once.
+//   streaming (K > 256: linear2 with K = ff, image_proj with K = 1024): A and W k-blocks share a 4-stage ring.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -26,59 +34,81 @@ namespace {
 constexpr int kBM = 128;          // rows per tile = UMMA M
 constexpr int kKBytes = 128;      // bytes of K per k-block = one 128B swizzle row
 constexpr int kUmmaKBytes = 32;   // bytes of K per tcgen05.mma (16 bf16 / 8 tf32)
-constexpr int kGemmThreads = 192;
-constexpr int kEpiWarp0 = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 constexpr int kAccStages = 2;
+constexpr int kStages = 4;
+constexpr int kWstatMaxKb = 4;    // W-stationary when the whole K fits in 4 k-blocks
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStageA = kBM * kKBytes;  // 16 KB
-  static constexpr int kStageB = BN * kKBytes;   // 16 / 32 KB
-  static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kBytes = kBarOff + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
+  static constexpr int kStageA = kBM * kKBytes;             // 16 KB
+  static constexpr int kStageB = BN * kKBytes;              // 8 / 16 / 32 KB
+  static constexpr int kRing = kStages * (kStageA + kStageB);  // streaming ring == W (4 blocks) + A ring
+  static constexpr int kStgPerWarp = 2 * 2048;              // two 32-row x 64-byte staging tiles per epilogue warp
+  static constexpr int kOffStg = kRing;
+  static constexpr int kOffXch = kOffStg + kEpiWarps * kStgPerWarp;  // LayerNorm pair exchange
+  static constexpr int kOffBar = kOffXch + kEpiWarps * 32 * 8;
+  static constexpr int kBytes = kOffBar + 128 /*barriers + tmem ptr*/;
 };
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 template <int BN, int EPI, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   using L = GemmSmem<BN>;
-  constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = kAccStages * BN;
-  static_assert(kTmemCols <= 512, "TMEM budget");
+  static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
   static_assert(EPI != kEpiBiasResLN || BN == 256, "LN epilogue needs the whole row in one tile");
+  constexpr int kChunks = BN / 32;            // 32-column chunks per tile
+  constexpr int kMyChunks = kChunks / 2;      // per epilogue warp
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  // 128-byte swizzled operand tiles need 1024-byte alignment; the whole 227 KB budget is in use, so there is no
+  // slack to round up - the alignment attribute is relied upon and checked
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_full = empty_bar + kStages;
   uint64_t* acc_empty = acc_full + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  uint64_t* w_full = acc_empty + kAccStages;
+  uint64_t* w_empty = w_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int elem_bytes = TF32 ? 4 : 2;
-  const int bk = kKBytes / elem_bytes;               // elements of K per k-block
+  constexpr int elem_bytes = TF32 ? 4 : 2;
+  constexpr int bk = kKBytes / elem_bytes;           // elements of K per k-block
   const int num_kb = (p.K + bk - 1) / bk;
   const int tiles_m = (p.M + kBM - 1) / kBM;
   const int tiles_n = p.N / BN;
   const int num_tiles = tiles_m * tiles_n;
+  const bool wstat = num_kb <= kWstatMaxKb;
+  // contiguous, balanced tile range of this CTA in n-major order (tile L -> n = L / tiles_m, m = L % tiles_m)
+  const int t_begin = int((long long)num_tiles * blockIdx.x / gridDim.x);
+  const int t_end = int((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
+
+  // W-stationary layout: [W block 0..3 | A ring]; streaming layout: stage s = [A | W]
+  uint8_t* sW = smem;
+  uint8_t* sAring = smem + kWstatMaxKb * L::kStageB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
+    if (EPI != kEpiBiasPeRemap) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], kEpiWarps);  // one arrive per epilogue warp
     }
+    mbar_init(w_full, 1);
+    mbar_init(w_empty, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -92,16 +122,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * kBM;
-        const int n0 = (tile % tiles_n) * BN;
+      int cur_n = -1;
+      uint32_t wphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int nt = tile / tiles_m;
+        const int m0 = (tile - nt * tiles_m) * kBM;
+        const int n0 = nt * BN;
+        if (wstat && nt != cur_n) {
+          mbar_wait(w_empty, wphase ^ 1);  // every MMA that read the previous W has retired
+          mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
+          for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, n0);
+          cur_n = nt;
+          wphase ^= 1;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStage;
-          uint8_t* sb = sa + L::kStageA;
-          mbar_expect_tx(&full_bar[stage], L::kStage);
-          tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk, m0);
-          tma_load_2d(&tm_w, &full_bar[stage], sb, kb * bk, n0);
+          if (wstat) {
+            mbar_expect_tx(&full_bar[stage], L::kStageA);
+            tma_load_2d(&tm_a, &full_bar[stage], sAring + stage * L::kStageA, kb * bk, m0);
+          } else {
+            uint8_t* sa = smem + stage * (L::kStageA + L::kStageB);
+            mbar_expect_tx(&full_bar[stage], L::kStageA + L::kStageB);
+            tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk, m0);
+            tma_load_2d(&tm_w, &full_bar[stage], sa + L::kStageA, kb * bk, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -114,15 +158,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cur_n = -1;
+      uint32_t wphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int nt = tile / tiles_m;
+        if (wstat && nt != cur_n) {
+          mbar_wait(w_full, wphase);
+          wphase ^= 1;
+          cur_n = nt;
+        }
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * L::kStage);
-          const uint32_t sb = sa + L::kStageA;
+          uint32_t sa, sb;
+          if (wstat) {
+            sa = smem_u32(sAring + stage * L::kStageA);
+            sb = smem_u32(sW + kb * L::kStageB);
+          } else {
+            sa = smem_u32(smem + stage * (L::kStageA + L::kStageB));
+            sb = sa + L::kStageA;
+          }
 #pragma unroll
           for (int k = 0; k < kKBytes / kUmmaKBytes; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaKBytes, 16, 1024);
@@ -134,18 +192,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[as]);        // accumulator ready for the epilogue
+        if (wstat) {
+          const bool last_with_w = (tile + 1 == t_end) || ((tile + 1) / tiles_m != nt);
+          if (last_with_w) umma_commit(w_empty);
+        }
         if (++as == kAccStages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, row per thread)
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const int half = ew >> 2;      // which of the two warps of this quarter: takes chunks half, half+2, ...
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* stg = smem + L::kOffStg + ew * L::kStgPerWarp;
+    float2* xch = reinterpret_cast<float2*>(smem + L::kOffXch);  // [kEpiWarps][32]
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * kBM;
-      const int n0 = (tile % tiles_n) * BN;
+    uint32_t nstore = 0;  // TMA stores issued by this warp's lane 0 (staging buffer = nstore & 1)
+
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int nt = tile / tiles_m;
+      const int m0 = (tile - nt * tiles_m) * kBM;
+      const int n0 = nt * BN;
       const int row = m0 + row_in_tile;
       const bool valid = row < p.M;
       mbar_wait(&acc_full[as], aphase);
@@ -154,51 +223,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * BN);
 
       if constexpr (EPI == kEpiBias || EPI == kEpiBiasRelu) {
-        __nv_bfloat16* orow = p.out + size_t(valid ? row : 0) * p.ldc + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (i == kMyChunks - 1) {  // all TMEM reads of this stage are done -> hand it back to the MMA warp
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
           uint32_t o[16];
+          const float* bptr = p.bias + n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]);
-            float v1 = __uint_as_float(r[j + 1]);
-            if (p.bias) {
-              v0 += __ldg(p.bias + n0 + c * 32 + j);
-              v1 += __ldg(p.bias + n0 + c * 32 + j + 1);
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = p.bias ? ldg4(bptr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+            float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+            if (EPI == kEpiBiasRelu) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
             }
-            if (EPI == kEpiBiasRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             o[j >> 1] = pack_bf16x2(v0, v1);
+            o[(j >> 1) + 1] = pack_bf16x2(v2, v3);
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+          uint8_t* buf = stg + (nstore & 1) * 2048;
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          __syncwarp();
+          uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, buf, n0 + c * 32, m0 + quarter * 32);
+            tma_store_commit();
           }
+          ++nstore;
         }
       } else if constexpr (EPI == kEpiBiasPeRemap) {
         const int item = row / p.rows_in;
         const int pos = row - item * p.rows_in;
-        __nv_bfloat16* orow = p.out + (size_t(valid ? item : 0) * p.rows_out + p.row_off + (valid ? pos : 0)) * p.ldc + n0;
+        __nv_bfloat16* orow =
+            p.out + (size_t(valid ? item : 0) * p.rows_out + p.row_off + (valid ? pos : 0)) * p.ldc + n0;
         const float* perow = p.pe + size_t(p.pe_off + (valid ? pos : 0)) * p.N + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (i == kMyChunks - 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 pe4 = __ldg(reinterpret_cast<const float4*>(perow + c * 32 + j));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
-            const float v0 = __uint_as_float(r[j]) + b4.x + pe4.x;
-            const float v1 = __uint_as_float(r[j + 1]) + b4.y + pe4.y;
-            const float v2 = __uint_as_float(r[j + 2]) + b4.z + pe4.z;
-            const float v3 = __uint_as_float(r[j + 3]) + b4.w + pe4.w;
-            o[j >> 1] = pack_bf16x2(v0, v1);
-            o[(j >> 1) + 1] = pack_bf16x2(v2, v3);
+            const float4 pe4 = ldg4(perow + c * 32 + j);
+            const float4 b4 = ldg4(p.bias + n0 + c * 32 + j);
+            o[j >> 1] = pack_bf16x2(__uint_as_float(r[j]) + b4.x + pe4.x, __uint_as_float(r[j + 1]) + b4.y + pe4.y);
+            o[(j >> 1) + 1] =
+                pack_bf16x2(__uint_as_float(r[j + 2]) + b4.z + pe4.z, __uint_as_float(r[j + 3]) + b4.w + pe4.w);
           }
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
@@ -206,80 +293,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
           }
         }
-      } else {  // kEpiBiasResLN : whole 256-wide row belongs to this thread
-        const __nv_bfloat16* rrow = p.residual + size_t(valid ? row : 0) * p.ldr;
-        float sum = 0.f, sumsq = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+      } else {  // kEpiBiasResLN : this warp holds 32 rows x (BN/2) columns of v = acc + bias + residual in registers
+        float v[kMyChunks][32];
+        // the previous tile's stores may still read the staging buffers that now receive the residual
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
+          // residual chunk (32 rows x 64 B): coalesced 16-byte loads (8 rows per instruction), transposed through smem
+          uint8_t* buf = stg + (i & 1) * 2048;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int rr = (lane >> 2) + 8 * k;
+            const int grow = m0 + quarter * 32 + rr;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (grow < p.M)
+              val = *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + c * 32 + (lane & 3) * 8);
+            *reinterpret_cast<uint4*>(buf + rr * 64 + (lane & 3) * 16) = val;
+          }
+          __syncwarp();
           tmem_ld_wait();
-          const uint4* rs = reinterpret_cast<const uint4*>(rrow + c * 32);
+          const float* bptr = p.bias + n0 + c * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 rv = rs[q];
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint4 rv = *reinterpret_cast<const uint4*>(buf + lane * 64 + q * 16);
+            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+            const float4 b0 = ldg4(bptr + q * 8), b1 = ldg4(bptr + q * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              const float2 res = unpack_bf16x2(w4[e]);
               const int j = q * 8 + e * 2;
-              const float2 res = unpack_bf16x2(w[e]);
-              const float v0 = __uint_as_float(r[j]) + __ldg(p.bias + c * 32 + j) + res.x;
-              const float v1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + c * 32 + j + 1) + res.y;
-              sum += v0 + v1;
-              sumsq += v0 * v0 + v1 * v1;
+              v[i][j] = __uint_as_float(r[j]) + bb[e * 2] + res.x;
+              v[i][j + 1] = __uint_as_float(r[j + 1]) + bb[e * 2 + 1] + res.y;
             }
           }
+          __syncwarp();  // buffer (i & 1) is rewritten two chunks later
         }
-        const float mean = sum * (1.f / BN);
-        const float var = fmaxf(sumsq * (1.f / BN) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.eps);
-        __nv_bfloat16* orow = p.out + size_t(valid ? row : 0) * p.ldc;
-        float* frow = p.out_f32 ? p.out_f32 + size_t(valid ? row : 0) * BN : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-          const uint4* rs = reinterpret_cast<const uint4*>(rrow + c * 32);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+
+        // row statistics over all BN columns: exchange partial sums with the partner warp of this quarter
+        const int partner = ew ^ 4;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMyChunks; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += v[i][j];
+        xch[ew * 32 + lane].x = s;
+        named_bar_sync(1 + quarter, 64);
+        const float mean = (s + xch[partner * 32 + lane].x) * (1.f / BN);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMyChunks; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = v[i][j] - mean;
+            sq = fmaf(d, d, sq);
+          }
+        xch[ew * 32 + lane].y = sq;
+        named_bar_sync(1 + quarter, 64);
+        const float rstd = rsqrtf((sq + xch[partner * 32 + lane].y) * (1.f / BN) + p.eps);
+        // (xch is rewritten only after the next tile's first barrier of this pair, which orders the reads above)
+
+        float* frow = (p.out_f32 && valid) ? p.out_f32 + size_t(row) * BN : nullptr;
+#pragma unroll
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
+          const float* gptr = p.gamma + c * 32;
+          const float* btptr = p.beta + c * 32;
           uint32_t o[16];
-          float yv[32];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 rv = rs[q];
-            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = q * 8 + e * 2;
-              const float2 res = unpack_bf16x2(w[e]);
-              const float v0 = __uint_as_float(r[j]) + __ldg(p.bias + c * 32 + j) + res.x;
-              const float v1 = __uint_as_float(r[j + 1]) + __ldg(p.bias + c * 32 + j + 1) + res.y;
-              const float y0 = (v0 - mean) * rstd * __ldg(p.gamma + c * 32 + j) + __ldg(p.beta + c * 32 + j);
-              const float y1 =
-                  (v1 - mean) * rstd * __ldg(p.gamma + c * 32 + j + 1) + __ldg(p.beta + c * 32 + j + 1);
-              yv[j] = y0;
-              yv[j + 1] = y1;
-              o[j >> 1] = pack_bf16x2(y0, y1);
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 g4 = ldg4(gptr + j), t4 = ldg4(btptr + j);
+            const float y0 = (v[i][j] - mean) * rstd * g4.x + t4.x;
+            const float y1 = (v[i][j + 1] - mean) * rstd * g4.y + t4.y;
+            const float y2 = (v[i][j + 2] - mean) * rstd * g4.z + t4.z;
+            const float y3 = (v[i][j + 3] - mean) * rstd * g4.w + t4.w;
+            o[j >> 1] = pack_bf16x2(y0, y1);
+            o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
+            if (frow) *reinterpret_cast<float4*>(frow + c * 32 + j) = make_float4(y0, y1, y2, y3);
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+          uint8_t* buf = stg + (nstore & 1) * 2048;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            if (frow) {
-              float4* fdst = reinterpret_cast<float4*>(frow + c * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) fdst[q] = make_float4(yv[4 * q], yv[4 * q + 1], yv[4 * q + 2], yv[4 * q + 3]);
-            }
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, buf, n0 + c * 32, m0 + quarter * 32);
+            tma_store_commit();
           }
+          ++nstore;
         }
       }
-
-      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (++as == kAccStages) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the bulk stores reading it
   }
 
   tc_fence_before_sync();
@@ -292,8 +408,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 template <int BN, int EPI, bool TF32>
-cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p, int num_sms,
-                       cudaStream_t stream) {
+cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
+                       const GemmParams& p, int num_sms, cudaStream_t stream) {
   using L = GemmSmem<BN>;
   auto kfn = gemm_tc_kernel<BN, EPI, TF32>;
   static bool attr_done = false;
@@ -305,7 +421,7 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const G
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kfn<<<grid, kGemmThreads, L::kBytes, stream>>>(tm_a, tm_w, p);
+  kfn<<<grid, kGemmThreads, L::kBytes, stream>>>(tm_a, tm_w, tm_out, p);
   return cudaGetLastError();
 }
 
@@ -326,20 +442,21 @@ __global__ void gemm_check_kernel(const TA* __restrict__ A, const TA* __restrict
 }  // namespace
 
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
-                        const GemmParams& p, int num_sms, cudaStream_t stream) {
+                        const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.N % block_n != 0) return cudaErrorInvalidValue;
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \
-    return launch_one<BN_, EPI_, TF_>(tm_a, tm_w, p, num_sms, stream);
+    return launch_one<BN_, EPI_, TF_>(tm_a, tm_w, tm_out, p, num_sms, stream);
   B200VQA_GEMM_CASE(256, kEpiBias, false)
   B200VQA_GEMM_CASE(128, kEpiBias, false)
+  B200VQA_GEMM_CASE(64, kEpiBias, false)
   B200VQA_GEMM_CASE(256, kEpiBiasRelu, false)
   B200VQA_GEMM_CASE(128, kEpiBiasRelu, false)
+  B200VQA_GEMM_CASE(64, kEpiBiasRelu, false)
   B200VQA_GEMM_CASE(256, kEpiBiasResLN, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, true)
-  B200VQA_GEMM_CASE(256, kEpiBias, true)
 #undef B200VQA_GEMM_CASE
   return cudaErrorInvalidValue;
 }

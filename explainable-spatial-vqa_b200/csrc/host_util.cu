@@ -35,8 +35,22 @@ void set_error(const char* fmt, ...) {
 
 const char* get_error() { return g_err; }
 
+static int encode_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle);
+
 int make_tmap_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows) {
+  const uint32_t esz = type == TmapType::kBF16 ? 2 : 4;
+  return encode_2d(out, base, type, rows, cols, ld, 128 / esz, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_2d_store(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_cols, uint32_t box_rows) {
+  return encode_2d(out, base, type, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+static int encode_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = resolve_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -50,11 +64,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t row
   }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * esz};
-  cuuint32_t box[2] = {128 / esz, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, type == TmapType::kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu box_rows %u)", int(r),
