@@ -14,6 +14,7 @@
 //   d*                 bf16 [cap, *]         one decode position per question
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -28,6 +29,7 @@ using namespace b200vqa;
 namespace {
 
 constexpr int kMaxDecodeLen = 64;
+constexpr int kTokLd = kMaxDecodeLen + 1;
 
 struct MhaPacked {
   __nv_bfloat16* w_in = nullptr;   // [3d, d]
@@ -68,6 +70,7 @@ struct Workspace {
   __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dx1 = nullptr, *dq = nullptr, *dx2 = nullptr,
                 *dhid = nullptr, *dxo[2] = {nullptr, nullptr};
   float* dout = nullptr;
+  int64_t* tok = nullptr;          // [cap, kTokLd] greedy tokens of the running decode (column 0 = start token)
   __nv_bfloat16* img_t = nullptr;  // FA: transposed + cast image features [cap*196, 1024]
 };
 
@@ -86,6 +89,12 @@ const char* const kTagNames[kNumTags] = {
 struct ProfRec {
   int tag;
   cudaEvent_t a, b;
+};
+
+using GraphKey = std::tuple<int, int, int, int, const void*, const void*>;
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches = 0;  // kernel nodes in the graph (for b200vqa_launch_count)
 };
 
 }  // namespace
@@ -111,6 +120,9 @@ struct b200vqa_handle {
   std::map<TmapKey, CUtensorMap> tmaps;
   uint64_t launches = 0;
   int cur_tag = kTagMisc;
+  bool use_graphs = true;
+  std::map<GraphKey, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   bool profiling = false;
   std::vector<ProfRec> prof;
 
@@ -123,7 +135,9 @@ struct b200vqa_handle {
 
 namespace {
 
-int default_cap(const b200vqa_handle* h) { return h->d.kind == B200VQA_MODEL_IQAP ? 512 : 1024; }
+// questions processed per pass of the kernel sequence (bounds the activation workspace: ~2.4 MB per IQAP
+// question with ff = 2048, ~1.5 MB per FA question with ff = 512)
+int default_cap(const b200vqa_handle* h) { return h->d.kind == B200VQA_MODEL_IQAP ? 2048 : 4096; }
 
 // ---------------------------------------------------------------------------------------------
 // weights
@@ -325,6 +339,7 @@ void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, 
   w.dxo[0] = a.take<__nv_bfloat16>(drows * kD);
   w.dxo[1] = a.take<__nv_bfloat16>(drows * kD);
   w.dout = a.take<float>(drows * kD);
+  w.tok = a.take<int64_t>(size_t(cap) * kTokLd);
   if (d.kind == B200VQA_MODEL_FA) w.img_t = a.take<__nv_bfloat16>(size_t(cap) * d.n_img_tokens * d.img_feat_dim);
 }
 
@@ -338,6 +353,8 @@ int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
     B200VQA_CUDA_OK(cudaFree(h->ws.base));
     h->ws = Workspace{};
     h->tmaps.clear();
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
   }
   Arena measure;
   Workspace tmp;
@@ -501,23 +518,17 @@ struct DecodeIO {
   const int64_t* start_tokens = nullptr;  // per-question start (teacher-forced forward)
   int start_ld = 0;
   int steps = 0;
-  int64_t* tokens = nullptr;  // [B, tok_ld]
-  int tok_ld = 0;
-  int tok_col0 = 0;           // column of the first generated token (IQAP 0, FA 1)
-  bool write_start = false;   // FA: tokens[b,0] = start
-  int32_t* cache_out = nullptr;
-  long long cache_ld = 0;
-  int cache_store_forced = 0;
-  const int32_t* n_steps = nullptr;
-  int step = 0;
   float* logits = nullptr;    // [B, logits_T, V]
   int logits_T = 0;
   const int64_t* forced = nullptr;
   int forced_ld = 0;
 };
 
-int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
-                const DecodeIO& io, cudaStream_t s) {
+// The launch sequence of one greedy decode: cross K|V projection of the memory, start embedding, then `steps`
+// positions x layers.  Every argument is a library-owned buffer or a value in the graph key, so the same
+// sequence can be captured once and replayed (run_decoder).
+int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                    const DecodeIO& io, cudaStream_t s) {
   Workspace& w = h->ws;
   const auto& d = h->d;
   const int M = B * kLP;
@@ -537,12 +548,8 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     ep.start_tokens = io.start_tokens;
     ep.start_ld = io.start_ld;
     ep.x = w.dx;
-    ep.tokens = io.write_start ? io.tokens : nullptr;
-    ep.tok_ld = io.tok_ld;
-    ep.cache_out = io.cache_out;
-    ep.cache_ld = io.cache_ld;
-    ep.n_steps = io.n_steps;
-    ep.step = io.step;
+    ep.tok = w.tok;
+    ep.tok_ld = kTokLd;
     h->cur_tag = kTagEmbed;
     LAUNCH_OK(h, launch_dec_embed_start(ep, s));
   }
@@ -554,33 +561,42 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
       __nv_bfloat16* out = w.dxo[l & 1];
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.dqkv, s));
-      DecSelfAttnParams sp;
+      RowAttnParams sp;
       sp.B = B;
       sp.nhead = d.nhead;
-      sp.t = t;
-      sp.t_max = w.t_max;
-      sp.qkv = w.dqkv;
-      sp.k_cache = w.kc[l];
-      sp.v_cache = w.vc[l];
+      sp.q = w.dqkv;
+      sp.ldq = 3 * kD;
+      sp.k = w.kc[l];
+      sp.v = w.vc[l];
+      sp.rows_per_q = w.t_max;
+      sp.ld = kD;
+      sp.const_len = t + 1;
+      sp.new_k = w.dqkv + kD;
+      sp.new_v = w.dqkv + 2 * kD;
+      sp.ld_new = 3 * kD;
+      sp.append_pos = t;
+      sp.k_app = w.kc[l];
+      sp.v_app = w.vc[l];
       sp.out = w.dattn;
       h->cur_tag = kTagDecSelfAttn;
-      LAUNCH_OK(h, launch_dec_self_attn(sp, s));
+      LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.dx1, nullptr, s));
       RC_OK(gemm_bias(h, false, w.dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, w.dq, s));
-      DecCrossAttnParams cp;
+      RowAttnParams cp;
       cp.B = B;
       cp.nhead = d.nhead;
       cp.q = w.dq;
-      cp.kv = w.ckv[l];
-      cp.ld_kv = 2 * kD;
-      cp.k_col = 0;
-      cp.v_col = kD;
+      cp.ldq = kD;
+      cp.k = w.ckv[l];
+      cp.v = w.ckv[l] + kD;
+      cp.rows_per_q = kLP;
+      cp.ld = 2 * kD;
       cp.lens = lens;
       cp.const_len = const_len;
       cp.out = w.dattn;
       h->cur_tag = kTagDecCrossAttn;
-      LAUNCH_OK(h, launch_dec_cross_attn(cp, s));
+      LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, w.dx1, L.n2w, L.n2b, w.dx2, nullptr,
                         s));
@@ -598,9 +614,8 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     hp.eps = d.layer_norm_eps;
     hp.w_t = h->head_wt;
     hp.bias = h->head_b;
-    hp.tokens = io.tokens;
-    hp.tok_ld = io.tok_ld;
-    hp.tok_col = io.tok_col0 + t;
+    hp.tok = w.tok;
+    hp.tok_ld = kTokLd;
     hp.logits = io.logits;
     hp.logits_T = io.logits_T;
     hp.forced = io.forced;
@@ -609,14 +624,77 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     hp.vocab = d.dec_vocab;
     hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
     hp.x_next = w.dx;
-    hp.cache_out = io.cache_out;
-    hp.cache_ld = io.cache_ld;
-    hp.cache_store_forced = io.cache_store_forced;
-    hp.n_steps = io.n_steps;
-    hp.step = io.step;
     h->cur_tag = kTagDecHead;
     LAUNCH_OK(h, launch_dec_head(hp, s));
   }
+  return B200VQA_OK;
+}
+
+// Greedy decode into ws.tok.  The plain (no logits / no teacher forcing) sequence depends only on
+// (B, steps, start token, memory buffer, length source) and library-owned buffers, so it is captured into a
+// CUDA graph on first use and replayed afterwards: ~20 launches per position collapse into one graph launch.
+int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                const DecodeIO& io, cudaStream_t s) {
+  const bool plain = !io.logits && !io.forced && !io.start_tokens;
+  if (!plain || h->profiling || !h->use_graphs) return enqueue_decoder(h, B, memory, lens, const_len, io, s);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  B200VQA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
+  if (cs != cudaStreamCaptureStatusNone) return enqueue_decoder(h, B, memory, lens, const_len, io, s);
+  GraphKey key{B, io.steps, io.start_token, const_len, static_cast<const void*>(memory), static_cast<const void*>(lens)};
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    // warm the tensor-map cache and the kernels' one-time attribute calls outside capture
+    const uint64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    if (!h->cap_stream) B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    B200VQA_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_decoder(h, B, memory, lens, const_len, io, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc != B200VQA_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+      return B200VQA_ERR_CUDA;
+    }
+    GraphEntry ge;
+    ge.launches = h->launches - before;
+    h->launches = before;
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      return B200VQA_ERR_CUDA;
+    }
+    if (h->graphs.size() >= 64) {
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+      h->graphs.clear();
+    }
+    it = h->graphs.emplace(key, ge).first;
+  }
+  B200VQA_CUDA_OK(cudaGraphLaunch(it->second.exec, s));
+  h->launches += it->second.launches;
+  return B200VQA_OK;
+}
+
+int publish(b200vqa_handle* h, int B, int n_cols, int src_col0, int64_t* out_i64, int32_t* out_i32, long long out_ld,
+            const int64_t* forced, int forced_ld, const int32_t* n_steps, int step, cudaStream_t s) {
+  PublishParams pp;
+  pp.B = B;
+  pp.n_cols = n_cols;
+  pp.src_col0 = src_col0;
+  pp.tok = h->ws.tok;
+  pp.tok_ld = kTokLd;
+  pp.out_i64 = out_i64;
+  pp.out_i32 = out_i32;
+  pp.out_ld = out_ld;
+  pp.forced = forced;
+  pp.forced_ld = forced_ld;
+  pp.n_steps = n_steps;
+  pp.step = step;
+  h->cur_tag = kTagMisc;
+  LAUNCH_OK(h, launch_publish_tokens(pp, s));
   return B200VQA_OK;
 }
 
@@ -669,14 +747,12 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
   DecodeIO io;
   io.start_token = 1;  // Config.SPECIAL_TOKEN_ID (IQAP:24,205)
   io.steps = T;
-  io.tokens = programs;
-  io.tok_ld = T;
-  io.tok_col0 = 0;
   io.logits = step_logits;
   io.logits_T = T;
   io.forced = forced;
   io.forced_ld = T;
-  return run_decoder(h, B, memory, nullptr, S, io, s);
+  RC_OK(run_decoder(h, B, memory, nullptr, S, io, s));
+  return publish(h, B, T, 1, programs, nullptr, T, nullptr, 0, nullptr, 0, s);  // drop the <START> column (IQAP:239)
 }
 
 }  // namespace
@@ -703,6 +779,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   }
   h->device = device;
   h->num_sms = num_sms;
+  if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
   h->dec_src.assign(desc->dec_layers, desc->dec_layers + desc->n_dec_layers);
@@ -759,6 +836,7 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->wbase) cudaFree(h->wbase);
   if (h->stage) cudaFree(h->stage);
@@ -767,6 +845,7 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -864,13 +943,13 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
     DecodeIO io;
     io.start_token = 1;
     io.steps = program_len;
-    io.tokens = programs + size_t(b0) * program_len;
-    io.tok_ld = program_len;
     io.logits = opt_step_logits ? opt_step_logits + size_t(b0) * program_len * V : nullptr;
     io.logits_T = program_len;
     io.forced = opt_forced_tokens ? opt_forced_tokens + size_t(b0) * program_len : nullptr;
     io.forced_ld = program_len;
     RC_OK(run_decoder(h, nb, h->ws.mem, nullptr, S, io, s));
+    RC_OK(publish(h, nb, program_len, 1, programs + size_t(b0) * program_len, nullptr, program_len, nullptr, 0, nullptr,
+                  0, s));
   }
   return B200VQA_OK;
 }
@@ -1031,16 +1110,13 @@ B200VQA_API int b200vqa_fa_step(b200vqa_handle* h, const void* img_tokens_bf16, 
     DecodeIO io;
     io.start_token = start_token;
     io.steps = T;
-    io.tokens = out_tokens + size_t(b0) * max_len;
-    io.tok_ld = max_len;
-    io.tok_col0 = 1;
-    io.write_start = true;
     io.logits = opt_logits ? opt_logits + size_t(b0) * T * d.dec_vocab : nullptr;
     io.logits_T = T;
     io.forced = opt_forced ? opt_forced + size_t(b0) * T : nullptr;
     io.forced_ld = T;
     RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp, nb,
                       io, s));
+    RC_OK(publish(h, nb, max_len, 0, out_tokens + size_t(b0) * max_len, nullptr, max_len, nullptr, 0, nullptr, 0, s));
   }
   return B200VQA_OK;
 }
@@ -1118,18 +1194,16 @@ B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_b
       DecodeIO io;
       io.start_token = start_token;
       io.steps = T;
-      io.tok_col0 = 1;
-      io.cache_out = cache + (size_t(b0) * S + i) * max_len;
-      io.cache_ld = (long long)S * max_len;
-      io.cache_store_forced = opt_forced ? 1 : 0;
-      io.n_steps = n_steps + b0;
-      io.step = i;
       io.logits = opt_logits ? opt_logits + (size_t(b0) * S + i) * T * d.dec_vocab : nullptr;
       io.logits_T = S * T;  // row (b, i, t) = b*S*T + i*T + t
       io.forced = opt_forced ? opt_forced + (size_t(b0) * S + i) * T : nullptr;
       io.forced_ld = S * T;
       RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp,
                         nb, io, s));
+      // step i's 20 tokens (start token included, FA:120-121) into the HBM cache; with teacher forcing the
+      // cache receives the forced tokens so that later steps consume exactly what the caller dictated
+      RC_OK(publish(h, nb, max_len, 0, nullptr, cache + (size_t(b0) * S + i) * max_len, (long long)S * max_len, io.forced,
+                    io.forced_ld, n_steps + b0, i, s));
     }
   }
   return B200VQA_OK;

@@ -117,7 +117,13 @@ cudaError_t launch_memory_export(const __nv_bfloat16* x, int S, int B, int ldb, 
 cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0, const float* b0, int hidden,
                                const float* w1, const float* b1, int classes, float* out, cudaStream_t stream);
 
-// Decoder state initialisation: x0[b] = emb[start] + pe[0]; tokens[b,0] = start (FA keeps it, IQAP drops it).
+// ------------------------------------------------------------------------------------------
+// Decoder (decode_kernels.cu).  All decode positions of a question are produced on the device; the greedy
+// tokens accumulate in a library-owned int64 buffer tok[B, tok_ld] (column 0 = start token) and are copied
+// to the caller's layout once at the end (launch_publish_tokens), so the decode loop itself has a fixed
+// launch sequence with fixed arguments and can be replayed as a CUDA graph.
+// ------------------------------------------------------------------------------------------
+// x0[b] = emb[start] + pe[0]; tok[b,0] = start.
 struct DecEmbedParams {
   int B = 0;
   const float* emb = nullptr;
@@ -126,41 +132,41 @@ struct DecEmbedParams {
   int start_token = 0;
   const int64_t* start_tokens = nullptr;  // optional per-question start token: start_tokens[b*start_ld]
   int start_ld = 0;
-  __nv_bfloat16* x = nullptr;       // [B,kD]
-  int64_t* tokens = nullptr;        // optional: tokens[b*tok_ld] = start (FA `ys` column 0)
+  __nv_bfloat16* x = nullptr;             // [B,kD]
+  int64_t* tok = nullptr;                 // [B, tok_ld]
   int tok_ld = 0;
-  int32_t* cache_out = nullptr;     // optional FA step cache row base: cache_out[b*cache_ld] = start
-  long long cache_ld = 0;
-  const int32_t* n_steps = nullptr; // with cache_out: questions with n_steps[b] <= step are not written
-  int step = 0;
 };
 cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream);
 
-// Decoder self-attention for ONE new position t against the per-layer KV cache (exact form of the
-// reference's causal-mask recompute, IQAP:208-227 / FA:137-141).
-struct DecSelfAttnParams {
-  int B = 0, nhead = 4, t = 0, t_max = 0;
-  const __nv_bfloat16* qkv = nullptr;  // [B, 3*kD] this step's q|k|v
-  __nv_bfloat16* k_cache = nullptr;    // [B, t_max, kD]
-  __nv_bfloat16* v_cache = nullptr;    // [B, t_max, kD]
-  __nv_bfloat16* out = nullptr;        // [B, kD]
-};
-cudaError_t launch_dec_self_attn(const DecSelfAttnParams& p, cudaStream_t stream);
-
-// Decoder cross-attention of one query row per question over the encoder memory's projected K/V.
-struct DecCrossAttnParams {
+// One query row per question against `len` key/value rows (all heads; one CTA per question).  Serves both
+// the decoder self-attention over its KV cache (exact form of the reference's causal-mask recompute,
+// IQAP:208-227 / FA:137-141; the new position's k/v are appended first) and the cross-attention over the
+// projected encoder memory.  Key row j of question b is at k + (b*rows_per_q + j)*ld: 256 contiguous bf16.
+struct RowAttnParams {
   int B = 0, nhead = 4;
-  const __nv_bfloat16* q = nullptr;   // [B, kD]
-  const __nv_bfloat16* kv = nullptr;  // [B*kLP, ld_kv]; K at col k_col, V at col v_col
-  int ld_kv = 0, k_col = 0, v_col = 0;
-  const int32_t* lens = nullptr;      // [B] or null
+  const __nv_bfloat16* q = nullptr;  // [B, ldq], columns 0..255
+  int ldq = 0;
+  const __nv_bfloat16* k = nullptr;
+  const __nv_bfloat16* v = nullptr;
+  long long rows_per_q = 0;
+  int ld = 0;
+  const int32_t* lens = nullptr;     // [B] or null -> const_len
   int const_len = 0;
-  __nv_bfloat16* out = nullptr;       // [B, kD]
+  // self-attention only: this position's key/value (row b of new_k / new_v, leading dim ld_new) is written to
+  // row append_pos of the caches (k_app / v_app alias k / v) before attending
+  const __nv_bfloat16* new_k = nullptr;
+  const __nv_bfloat16* new_v = nullptr;
+  int ld_new = 0;
+  int append_pos = 0;
+  __nv_bfloat16* k_app = nullptr;
+  __nv_bfloat16* v_app = nullptr;
+  __nv_bfloat16* out = nullptr;      // [B, kD]
 };
-cudaError_t launch_dec_cross_attn(const DecCrossAttnParams& p, cudaStream_t stream);
+cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream);
 
-// Output head for decode position t: (optional final LayerNorm) -> Linear(kD, V) fp32 -> argmax ->
-// tokens[b, t_out] ; next-step input x = emb[next] + pe[t+1] where next = forced token if given.
+// Output head for decode position t: (optional final LayerNorm) -> Linear(kD, V) fp32 -> argmax (lowest index
+// wins ties, like torch.max / torch.argmax) -> tok[b, t+1]; next-step input x = emb[next] + pe[t+1] where next =
+// forced token if given.
 struct DecHeadParams {
   int B = 0, V = 0, t = 0;
   const float* x_f32 = nullptr;       // [B,kD] fp32 output of the last decoder layer's norm3
@@ -169,23 +175,36 @@ struct DecHeadParams {
   float eps = 1e-5f;
   const float* w_t = nullptr;         // [kD, V] fp32 (transposed head weight)
   const float* bias = nullptr;        // [V]
-  int64_t* tokens = nullptr;          // [B, tok_ld]
-  int tok_ld = 0, tok_col = 0;        // write argmax at tokens[b, tok_col]
-  float* logits = nullptr;            // optional [B, T, V]; row t
+  int64_t* tok = nullptr;             // [B, tok_ld]; argmax written to column t+1
+  int tok_ld = 0;
+  float* logits = nullptr;            // optional [B, logits_T, V]; row t
   int logits_T = 0;
-  const int64_t* forced = nullptr;    // optional [B, forced_ld] teacher-forcing tokens; uses forced[b, t]
+  const int64_t* forced = nullptr;    // optional teacher-forcing tokens; position t+1 is fed forced[b*forced_ld + t]
   int forced_ld = 0;
   const float* emb = nullptr;         // decoder embedding for the next input
   int vocab = 0;
   const float* pe_next = nullptr;     // pe row t+1 (null on the last step)
   __nv_bfloat16* x_next = nullptr;    // [B,kD]
-  int32_t* cache_out = nullptr;       // optional FA step cache row base: cache_out[b*cache_ld + tok_col]
-  long long cache_ld = 0;
-  int cache_store_forced = 0;         // cache receives the forced token instead of the argmax (parity runs)
-  const int32_t* n_steps = nullptr;   // with cache_out: questions with n_steps[b] <= step are not written
-  int step = 0;
 };
 cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream);
+
+// tok[B, tok_ld] -> caller layout.
+//   out_i64 : out[b*out_ld + j] = tok[b, src_col0 + j], j < n_cols                       (IQAP programs, FA `ys`)
+//   out_i32 : FA step cache row: out[b*out_ld + j] = (j == 0 || !forced) ? tok[b, j] : forced[b*forced_ld + j-1],
+//             skipped for questions with n_steps[b] <= step (the reference never executes those steps)
+struct PublishParams {
+  int B = 0, n_cols = 0, src_col0 = 0;
+  const int64_t* tok = nullptr;
+  int tok_ld = 0;
+  int64_t* out_i64 = nullptr;
+  int32_t* out_i32 = nullptr;
+  long long out_ld = 0;
+  const int64_t* forced = nullptr;
+  int forced_ld = 0;
+  const int32_t* n_steps = nullptr;
+  int step = 0;
+};
+cudaError_t launch_publish_tokens(const PublishParams& p, cudaStream_t stream);
 
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);

@@ -227,238 +227,6 @@ __global__ void __launch_bounds__(256) answer_head_kernel(const __nv_bfloat16* _
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Decoder
-// ------------------------------------------------------------------------------------------------
-__global__ void dec_embed_start_kernel(const DecEmbedParams p) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= p.B) return;
-  float e[8], pe8[8], v[8];
-  long long st = p.start_tokens ? p.start_tokens[size_t(b) * p.start_ld] : (long long)p.start_token;
-  st = st < 0 ? 0 : (st >= p.vocab ? p.vocab - 1 : st);
-  load_f32x8(p.emb + size_t(st) * kD + lane * 8, e);
-  load_f32x8(p.pe + lane * 8, pe8);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = e[j] + pe8[j];
-  store_bf16x8(p.x + size_t(b) * kD + lane * 8, v);
-  if (lane == 0) {
-    if (p.tokens) p.tokens[size_t(b) * p.tok_ld] = st;
-    if (p.cache_out && !(p.n_steps && p.step >= p.n_steps[b])) p.cache_out[size_t(b) * p.cache_ld] = int(st);
-  }
-}
-
-// One warp per (question, head); lane owns DH/32 contiguous channels. Online softmax over the cached
-// positions 0..t (the reference recomputes the full causal prefix every step; position t's row of that
-// computation is exactly this).
-template <int DH>
-__global__ void dec_self_attn_kernel(const DecSelfAttnParams p) {
-  constexpr int E = DH / 32;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= p.B * p.nhead) return;
-  const int b = gw / p.nhead, h = gw % p.nhead;
-  const int col = h * DH + lane * E;
-  const float scale = rsqrtf(float(DH));
-
-  float q[E], kc[E], vc[E];
-  const __nv_bfloat16* qkv = p.qkv + size_t(b) * 3 * kD;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    q[e] = __bfloat162float(qkv[col + e]) * scale;
-    kc[e] = __bfloat162float(qkv[kD + col + e]);
-    vc[e] = __bfloat162float(qkv[2 * kD + col + e]);
-  }
-  __nv_bfloat16* kdst = p.k_cache + (size_t(b) * p.t_max + p.t) * kD + col;
-  __nv_bfloat16* vdst = p.v_cache + (size_t(b) * p.t_max + p.t) * kD + col;
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    kdst[e] = qkv[kD + col + e];
-    vdst[e] = qkv[2 * kD + col + e];
-  }
-
-  float m = -INFINITY, l = 0.f, acc[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) acc[e] = 0.f;
-  for (int j = 0; j <= p.t; ++j) {
-    float kj[E], vj[E];
-    if (j < p.t) {
-      const __nv_bfloat16* kr = p.k_cache + (size_t(b) * p.t_max + j) * kD + col;
-      const __nv_bfloat16* vr = p.v_cache + (size_t(b) * p.t_max + j) * kD + col;
-#pragma unroll
-      for (int e = 0; e < E; ++e) { kj[e] = __bfloat162float(kr[e]); vj[e] = __bfloat162float(vr[e]); }
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e) { kj[e] = kc[e]; vj[e] = vc[e]; }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) s = fmaf(q[e], kj[e], s);
-    s = warp_sum(s);
-    const float mn = fmaxf(m, s);
-    const float corr = __expf(m - mn);
-    const float pj = __expf(s - mn);
-    l = l * corr + pj;
-#pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = acc[e] * corr + pj * vj[e];
-    m = mn;
-  }
-  const float inv = 1.f / l;
-  __nv_bfloat16* o = p.out + size_t(b) * kD + col;
-#pragma unroll
-  for (int e = 0; e < E; ++e) o[e] = __float2bfloat16(acc[e] * inv);
-}
-
-// One warp per (question, head). LPK = DH/8 lanes cooperate on one key row (16 B each), 32/LPK keys per
-// warp-wide load, so every load instruction touches whole 128-byte lines of K (then V). Scores live in
-// shared memory between the two passes; K and V are each read exactly once per step.
-template <int DH>
-__global__ void __launch_bounds__(128) dec_cross_attn_kernel(const DecCrossAttnParams p) {
-  constexpr int LPK = DH / 8;
-  constexpr int KPI = 32 / LPK;
-  __shared__ float s_sc[4][kLP];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * 4 + warp;
-  if (gw >= p.B * p.nhead) return;
-  const int b = gw / p.nhead, h = gw % p.nhead;
-  const int len = p.lens ? p.lens[b] : p.const_len;
-  const int sub = lane % LPK;  // which 16-byte chunk of the head's row
-  const int grp = lane / LPK;  // which key of the KPI handled per iteration
-  float* sc = s_sc[warp];
-
-  float q[8];
-  load_bf16x8(p.q + size_t(b) * kD + h * DH + sub * 8, q);
-  const float sl2 = rsqrtf(float(DH)) * 1.4426950408889634f;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) q[e] *= sl2;
-
-  const __nv_bfloat16* kbase = p.kv + size_t(b) * kLP * p.ld_kv + p.k_col + h * DH + sub * 8;
-  const __nv_bfloat16* vbase = p.kv + size_t(b) * kLP * p.ld_kv + p.v_col + h * DH + sub * 8;
-
-  float mx = -INFINITY;
-#pragma unroll 4
-  for (int j0 = 0; j0 < len; j0 += KPI) {
-    const int j = j0 + grp;
-    float s = 0.f;
-    if (j < len) {
-      float kx[8];
-      load_bf16x8(kbase + size_t(j) * p.ld_kv, kx);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s = fmaf(q[e], kx[e], s);
-    }
-#pragma unroll
-    for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (j < len) {
-      if (sub == 0) sc[j] = s;
-      mx = fmaxf(mx, s);
-    }
-  }
-  mx = warp_max(mx);
-  __syncwarp();
-  float sum = 0.f;
-  for (int j = lane; j < len; j += 32) {
-    const float e = exp2f(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll 4
-  for (int j0 = 0; j0 < len; j0 += KPI) {
-    const int j = j0 + grp;
-    if (j < len) {
-      float vx[8];
-      load_bf16x8(vbase + size_t(j) * p.ld_kv, vx);
-      const float pj = sc[j];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
-    }
-  }
-#pragma unroll
-  for (int o = LPK; o < 32; o <<= 1) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
-  }
-  if (grp == 0) {
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] *= inv;
-    store_bf16x8(p.out + size_t(b) * kD + h * DH + sub * 8, acc);
-  }
-}
-
-// One warp per question: optional final LayerNorm, fp32 vocabulary head, argmax (lowest index wins
-// ties, like torch.max / torch.argmax on CPU), token store, next-step embedding.
-__global__ void __launch_bounds__(128) dec_head_kernel(const DecHeadParams p) {
-  __shared__ float s_x[4][kD];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + warp;
-  if (b >= p.B) return;
-  float* xs = s_x[warp];
-
-  float v[8];
-  load_f32x8(p.x_f32 + size_t(b) * kD + lane * 8, v);
-  if (p.fn_gamma) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
-    const float mean = warp_sum(s) * (1.f / kD);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / kD) + p.eps);
-    float g[8], bt[8];
-    load_f32x8(p.fn_gamma + lane * 8, g);
-    load_f32x8(p.fn_beta + lane * 8, bt);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bt[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) xs[lane * 8 + j] = v[j];
-  __syncwarp();
-
-  float best = -INFINITY;
-  int besti = 0x7fffffff;
-  for (int v0 = 0; v0 < p.V; v0 += 32) {
-    const int vi = v0 + lane;
-    float acc = 0.f;
-    if (vi < p.V) {
-      acc = p.bias[vi];
-#pragma unroll 8
-      for (int k = 0; k < kD; ++k) acc = fmaf(xs[k], __ldg(p.w_t + size_t(k) * p.V + vi), acc);
-      if (p.logits) p.logits[(size_t(b) * p.logits_T + p.t) * p.V + vi] = acc;
-      if (acc > best) { best = acc; besti = vi; }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-  }
-  if (besti >= p.V) besti = 0;  // all-NaN row: keep the index in range
-  const bool use_forced = p.forced && (p.pe_next || p.cache_store_forced);
-  long long nxt = use_forced ? p.forced[size_t(b) * p.forced_ld + p.t] : (long long)besti;
-  nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
-  if (lane == 0) {
-    if (p.tokens) p.tokens[size_t(b) * p.tok_ld + p.tok_col] = besti;
-    if (p.cache_out && !(p.n_steps && p.step >= p.n_steps[b]))
-      p.cache_out[size_t(b) * p.cache_ld + p.tok_col] = p.cache_store_forced ? int(nxt) : besti;
-  }
-  if (p.pe_next) {
-    float e[8], pe8[8], o[8];
-    load_f32x8(p.emb + size_t(nxt) * kD + lane * 8, e);
-    load_f32x8(p.pe_next + lane * 8, pe8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = e[j] + pe8[j];
-    store_bf16x8(p.x_next + size_t(b) * kD + lane * 8, o);
-  }
-}
-
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16(in[i]);
@@ -520,34 +288,6 @@ cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* 
                                const float* w1, const float* b1, int classes, float* out, cudaStream_t stream) {
   if (hidden > 1024) return cudaErrorInvalidValue;
   answer_head_kernel<<<B, 256, 0, stream>>>(memory, w0_t, b0, hidden, w1, b1, classes, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream) {
-  dec_embed_start_kernel<<<ceil_div((long long)p.B * 32, 256), 256, 0, stream>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_dec_self_attn(const DecSelfAttnParams& p, cudaStream_t stream) {
-  const int grid = ceil_div((long long)p.B * p.nhead * 32, 128);
-  const int dh = kD / p.nhead;
-  if (dh == 64) dec_self_attn_kernel<64><<<grid, 128, 0, stream>>>(p);
-  else if (dh == 128) dec_self_attn_kernel<128><<<grid, 128, 0, stream>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_dec_cross_attn(const DecCrossAttnParams& p, cudaStream_t stream) {
-  const int grid = ceil_div((long long)p.B * p.nhead, 4);
-  const int dh = kD / p.nhead;
-  if (dh == 64) dec_cross_attn_kernel<64><<<grid, 128, 0, stream>>>(p);
-  else if (dh == 128) dec_cross_attn_kernel<128><<<grid, 128, 0, stream>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream) {
-  dec_head_kernel<<<ceil_div(p.B, 4), 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
