@@ -62,7 +62,8 @@ def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
         "enc_ffn1_gemm": ("tensor", 2 * S * d * ff),
         "enc_ffn2_ln_gemm": ("tensor", 2 * S * d * ff),
         "dec_cross_kv_gemm": ("tensor", n_dec * 2 * S * d * 2 * d),
-        "dec_step_gemms": ("tensor", n_dec * T * (2 * d * 3 * d + 3 * 2 * d * d + 4 * d * ff)),
+        "dec_step_gemms": ("tensor", n_dec * T * (2 * d * 3 * d + 3 * 2 * d * d)),
+        "dec_ffn_split": ("tensor", n_dec * T * 4 * d * ff),
         # HBM-bound: every step re-reads the projected K and V of the memory (bf16), SURVEY H2
         "dec_cross_attention": ("hbm", n_dec * T * S * 2 * d * 2),
         "dec_self_attention": ("hbm", n_dec * sum((t + 1) * 2 * d * 2 for t in range(T))),

@@ -70,6 +70,7 @@ struct Workspace {
   __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dx1 = nullptr, *dq = nullptr, *dx2 = nullptr,
                 *dhid = nullptr, *dxo[2] = {nullptr, nullptr};
   float* dout = nullptr;
+  float* ffn_partial = nullptr;    // [ff/128, drows, 256] fp32 partial sums of the decode feed-forward block
   int64_t* tok = nullptr;          // [cap, kTokLd] greedy tokens of the running decode (column 0 = start token)
   __nv_bfloat16* img_t = nullptr;  // FA: transposed + cast image features [cap*196, 1024]
 };
@@ -79,11 +80,11 @@ using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint3
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
   kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFinalLn,
-  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
+  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
 };
 const char* const kTagNames[kNumTags] = {
     "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
-    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_step_gemms", "dec_self_attention",
+    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_step_gemms", "dec_ffn_split", "dec_self_attention",
     "dec_cross_attention", "dec_head_argmax", "misc"};
 
 struct ProfRec {
@@ -339,6 +340,7 @@ void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, 
   w.dxo[0] = a.take<__nv_bfloat16>(drows * kD);
   w.dxo[1] = a.take<__nv_bfloat16>(drows * kD);
   w.dout = a.take<float>(drows * kD);
+  w.ffn_partial = a.take<float>(size_t(d.dim_ff / 128) * drows * kD);
   w.tok = a.take<int64_t>(size_t(cap) * kTokLd);
   if (d.kind == B200VQA_MODEL_FA) w.img_t = a.take<__nv_bfloat16>(size_t(cap) * d.n_img_tokens * d.img_feat_dim);
 }
@@ -600,8 +602,29 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, w.dx1, L.n2w, L.n2b, w.dx2, nullptr,
                         s));
-      RC_OK(gemm_bias(h, true, w.dx2, B, kD, L.w1, d.dim_ff, L.b1, w.dhid, s));
-      RC_OK(gemm_res_ln(h, w.dhid, B, d.dim_ff, L.w2, L.b2, w.dx2, L.n3w, L.n3b, out, last ? w.dout : nullptr, s));
+      {
+        // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
+        const CUtensorMap *tx, *tw1, *tw2;
+        RC_OK(get_tmap(h, w.dx2, TmapType::kBF16, uint64_t(B), kD, kD, 128, &tx));
+        RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 128, &tw1));
+        RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 256, &tw2));
+        FfnSmallParams fp;
+        fp.M = B;
+        fp.ff = d.dim_ff;
+        fp.n_slices = d.dim_ff / 128;
+        fp.b1 = L.b1;
+        fp.b2 = L.b2;
+        fp.residual = w.dx2;
+        fp.gamma = L.n3w;
+        fp.beta = L.n3b;
+        fp.eps = d.layer_norm_eps;
+        fp.partial = w.ffn_partial;
+        fp.out = out;
+        fp.out_f32 = last ? w.dout : nullptr;
+        h->cur_tag = kTagDecFfn;
+        LAUNCH_OK(h, launch_ffn_small(*tx, *tw1, *tw2, fp, s));
+        ++h->launches;  // two kernels
+      }
       in = out;
     }
     DecHeadParams hp;

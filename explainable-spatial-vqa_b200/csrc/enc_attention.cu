@@ -33,11 +33,13 @@ struct AttnSmem {
   static constexpr int kOffVt = kOffV + kV;                // only used by v_mode 1
   static constexpr int kBarOffNoVt = kOffVt;
   static constexpr int kBarOffVt = kOffVt + kV;
-  static constexpr int bytes(bool vt) { return (vt ? kBarOffVt : kBarOffNoVt) + 128 + 1024; }
+  static constexpr int bytes(bool vt) { return (vt ? kBarOffVt : kBarOffNoVt) + 128; }
 };
 
+// dh = 64 needs 112 KB of shared memory and 256 TMEM columns per CTA: two CTAs share an SM, so one CTA's
+// softmax (CUDA cores) overlaps the other's TMA loads and tensor-core work.
 template <int DH>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, DH == 64 ? 2 : 1)
 enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const EncAttnParams p) {
   using L = AttnSmem<DH>;
@@ -60,8 +62,8 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     return;
   }
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem + L::kOffQ;
   uint8_t* sK = smem + L::kOffKP;
   uint8_t* sP = smem + L::kOffKP;

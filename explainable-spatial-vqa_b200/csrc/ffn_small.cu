@@ -1,0 +1,246 @@
+// Feed-forward block for the decode phase (M = batch rows, one position per question):
+//     y = LayerNorm(x + W2 relu(W1 x + b1) + b2)                  (torch TransformerDecoderLayer._ff_block + norm3)
+//
+// With M <= a few thousand rows a plain GEMM pair leaves the chip idle: linear2 has N = 256 (one n-tile) and
+// K = ff, so only M/128 CTAs would each stream the whole 1 MB W2 through one SM.  Here the hidden dimension is
+// split instead: CTA (m-tile, slice) computes, entirely on chip,
+//     H_slice = relu(X[128x256] . W1[slice]^T + b1[slice])        tcgen05, fp32 accum in TMEM -> bf16 in smem
+//     P_slice = H_slice[128x128] . W2[:, slice]^T                 tcgen05, A operand = the smem tile just written
+// and stores the fp32 partial P_slice [128 x 256]; ffn_reduce_ln_kernel then sums the ff/128 partials of a row
+// in a fixed order (deterministic), adds b2 + residual and applies LayerNorm.  The hidden activations never touch
+// HBM, every SM pulls 1/16 of the weights, and the two launches replace linear1 / linear2.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200vqa {
+namespace {
+
+constexpr int kFfnThreads = 192;
+constexpr int kSlice = 128;  // hidden units per CTA
+
+struct FfnSmem {
+  static constexpr int kX = 4 * 16384;    // X tile: 4 k-blocks of [128 rows x 64]
+  static constexpr int kW1 = 4 * 16384;   // W1 slice: 4 k-blocks of [128 hidden x 64]
+  static constexpr int kW2 = 2 * 32768;   // W2 slice: 2 k-blocks of [256 out x 64 hidden]
+  static constexpr int kH = 2 * 16384;    // H slice: 2 panels of [128 rows x 64 hidden]
+  static constexpr int kOffX = 0;
+  static constexpr int kOffW1 = kOffX + kX;
+  static constexpr int kOffW2 = kOffW1 + kW1;
+  static constexpr int kOffH = kOffW2 + kW2;
+  static constexpr int kOffBar = kOffH + kH;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                   const __grid_constant__ CUtensorMap tm_w2, const FfnSmallParams p) {
+  using L = FfnSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sX = smem + L::kOffX;
+  uint8_t* sW1 = smem + L::kOffW1;
+  uint8_t* sW2 = smem + L::kOffW2;
+  uint8_t* sH = smem + L::kOffH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* bar_in1 = bars + 0;  // X + W1 slice landed
+  uint64_t* bar_in2 = bars + 1;  // W2 slice landed
+  uint64_t* bar_d1 = bars + 2;   // H accumulator complete
+  uint64_t* bar_h = bars + 3;    // H (bf16) written to smem by the 128 epilogue threads
+  uint64_t* bar_d2 = bars + 4;   // partial accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int slice = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w1);
+    tma_prefetch_desc(&tm_w2);
+    mbar_init(bar_in1, 1);
+    mbar_init(bar_in2, 1);
+    mbar_init(bar_d1, 1);
+    mbar_init(bar_h, 128);
+    mbar_init(bar_d2, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t d1 = tmem_base;        // 128 columns
+  const uint32_t d2 = tmem_base + 128;  // 256 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_in1, L::kX + L::kW1);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        tma_load_2d(&tm_x, bar_in1, sX + kb * 16384, kb * 64, m0);
+        tma_load_2d(&tm_w1, bar_in1, sW1 + kb * 16384, kb * 64, slice * kSlice);
+      }
+      mbar_expect_tx(bar_in2, L::kW2);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) tma_load_2d(&tm_w2, bar_in2, sW2 + kb * 32768, slice * kSlice + kb * 64, 0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- H = X . W1_slice^T : M=128, N=128, K=256
+      mbar_wait(bar_in1, 0);
+      tc_fence_after_sync();
+      constexpr uint32_t idesc1 = make_idesc(kFmtBF16, 128, 128, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t a = smem_u32(sX) + (k / 4) * 16384 + (k % 4) * 32;
+        const uint32_t b = smem_u32(sW1) + (k / 4) * 16384 + (k % 4) * 32;
+        umma_bf16(d1, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc1, k != 0);
+      }
+      umma_commit(bar_d1);
+      // ---- P = H . W2_slice^T : M=128, N=256, K=128
+      mbar_wait(bar_h, 0);
+      mbar_wait(bar_in2, 0);
+      tc_fence_after_sync();
+      constexpr uint32_t idesc2 = make_idesc(kFmtBF16, 128, 256, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t a = smem_u32(sH) + (k / 4) * 16384 + (k % 4) * 32;
+        const uint32_t b = smem_u32(sW2) + (k / 4) * 32768 + (k % 4) * 32;
+        umma_bf16(d2, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc2, k != 0);
+      }
+      umma_commit(bar_d2);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    mbar_wait(bar_d1, 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    const float* b1 = p.b1 + slice * kSlice;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(d1 + lane_off + c * 32, v);
+      tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c * 32 + j));
+        o[j >> 1] = pack_bf16x2(fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f));
+        o[(j >> 1) + 1] =
+            pack_bf16x2(fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f));
+      }
+      // K-major, 128-byte swizzled A operand: panel = 64 hidden units, 16-byte chunk index XOR (row & 7)
+      uint8_t* prow = sH + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = (c & 1) * 4 + q;
+        *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    mbar_arrive(bar_h);
+
+    mbar_wait(bar_d2, 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    const int row = m0 + r;
+    float* prow = p.partial + (size_t(slice) * p.M + (row < p.M ? row : 0)) * kD;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[32];
+      tmem_ld32(d2 + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (row < p.M) {
+        float4* dst = reinterpret_cast<float4*>(prow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// One warp per row: y = LayerNorm(sum_s partial[s] + b2 + residual); lane owns 8 consecutive columns.
+__global__ void __launch_bounds__(256) ffn_reduce_ln_kernel(const FfnSmallParams p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.M) return;
+  float v[8];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.b2 + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.b2 + lane * 8) + 1);
+    const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + size_t(row) * kD + lane * 8);
+    const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+    v[0] = a.x + r0.x; v[1] = a.y + r0.y; v[2] = a.z + r1.x; v[3] = a.w + r1.y;
+    v[4] = b.x + r2.x; v[5] = b.y + r2.y; v[6] = b.z + r3.x; v[7] = b.w + r3.y;
+  }
+  const float* src = p.partial + size_t(row) * kD + lane * 8;
+  const size_t stride = size_t(p.M) * kD;
+#pragma unroll 4
+  for (int s = 0; s < p.n_slices; ++s) {
+    const float4 a = *reinterpret_cast<const float4*>(src + s * stride);
+    const float4 b = *reinterpret_cast<const float4*>(src + s * stride + 4);
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1 += v[j];
+  const float mean = warp_sum(s1) * (1.f / kD);
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s2 += (v[j] - mean) * (v[j] - mean);
+  const float rstd = rsqrtf(warp_sum(s2) * (1.f / kD) + p.eps);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + lane * 8));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + lane * 8) + 1);
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.beta + lane * 8));
+  const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.beta + lane * 8) + 1);
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = (v[j] - mean) * rstd * g[j] + t[j];
+  *reinterpret_cast<uint4*>(p.out + size_t(row) * kD + lane * 8) =
+      make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  if (p.out_f32) {
+    float4* dst = reinterpret_cast<float4*>(p.out_f32 + size_t(row) * kD + lane * 8);
+    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
+                             const FfnSmallParams& p, cudaStream_t stream) {
+  if (p.M <= 0) return cudaSuccess;
+  if (p.ff % kSlice != 0 || p.n_slices != p.ff / kSlice) return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e =
+        cudaFuncSetAttribute(ffn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid((p.M + 127) / 128, p.n_slices);
+  ffn_partial_kernel<<<grid, kFfnThreads, FfnSmem::kBytes, stream>>>(tm_x, tm_w1, tm_w2, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ffn_reduce_ln_kernel<<<(p.M * 32 + 255) / 256, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace b200vqa

@@ -206,6 +206,24 @@ struct PublishParams {
 };
 cudaError_t launch_publish_tokens(const PublishParams& p, cudaStream_t stream);
 
+// Decode-phase feed-forward block, hidden dimension split over CTAs (ffn_small.cu):
+//   out = LayerNorm(residual + W2 relu(W1 x + b1) + b2);  x, residual, out bf16 [M, kD]; partial fp32 [ff/128, M, kD]
+// tm_x: x [M, kD] box 128 rows; tm_w1: W1 [ff, kD] box 128 rows; tm_w2: W2 [kD, ff] box 256 rows (all 128B-swizzled)
+struct FfnSmallParams {
+  int M = 0, ff = 0, n_slices = 0;
+  const float* b1 = nullptr;
+  const float* b2 = nullptr;
+  const __nv_bfloat16* residual = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  float* partial = nullptr;
+  __nv_bfloat16* out = nullptr;
+  float* out_f32 = nullptr;  // optional fp32 copy of the output
+};
+cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
+                             const FfnSmallParams& p, cudaStream_t stream);
+
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
 cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t stream);
