@@ -114,7 +114,7 @@ struct b200vqa_handle {
   float *img_b = nullptr, *cls = nullptr, *enc_emb = nullptr, *dec_emb = nullptr, *pe_enc = nullptr, *pe_dec = nullptr;
   std::vector<LayerPacked> enc, dec;
   float *enc_fn_w = nullptr, *enc_fn_b = nullptr, *dec_fn_w = nullptr, *dec_fn_b = nullptr;
-  float *head_wt = nullptr, *head_b = nullptr;  // [d, V] transposed
+  float *head_w = nullptr, *head_b = nullptr;   // [V, d] fp32 (tf32 tensor-core operand)
   float *ans_w0t = nullptr, *ans_b0 = nullptr, *ans_w1 = nullptr, *ans_b1 = nullptr;
 
   Workspace ws;
@@ -122,6 +122,7 @@ struct b200vqa_handle {
   uint64_t launches = 0;
   int cur_tag = kTagMisc;
   bool use_graphs = true;
+  bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   bool profiling = false;
@@ -183,7 +184,7 @@ void layout_weights(b200vqa_handle* h, Arena& a) {
   }
   if (d.enc_final_norm_weight) { h->enc_fn_w = a.take<float>(D); h->enc_fn_b = a.take<float>(D); }
   if (d.dec_final_norm_weight) { h->dec_fn_w = a.take<float>(D); h->dec_fn_b = a.take<float>(D); }
-  h->head_wt = a.take<float>(size_t(D) * d.dec_vocab);
+  h->head_w = a.take<float>(size_t(D) * d.dec_vocab);
   h->head_b = a.take<float>(d.dec_vocab);
   if (d.kind == B200VQA_MODEL_IQAP) {
     h->ans_w0t = a.take<float>(size_t(D) * d.answer_hidden);
@@ -254,7 +255,7 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
     PACK_OK(copy_f32(h->dec_fn_w, d.dec_final_norm_weight, D, s));
     PACK_OK(copy_f32(h->dec_fn_b, d.dec_final_norm_bias, D, s));
   }
-  PACK_OK(launch_transpose_f32(d.head_weight, h->head_wt, d.dec_vocab, D, s));
+  PACK_OK(copy_f32(h->head_w, d.head_weight, size_t(d.dec_vocab) * D, s));
   PACK_OK(copy_f32(h->head_b, d.head_bias, d.dec_vocab, s));
   if (d.kind == B200VQA_MODEL_IQAP) {
     PACK_OK(launch_transpose_f32(d.answer_w0, h->ans_w0t, d.answer_hidden, D, s));
@@ -284,6 +285,11 @@ int validate_desc(const b200vqa_model_desc* d) {
   }
   B200VQA_REQUIRE(d->n_enc_layers >= 1 && d->n_enc_layers <= 16 && d->n_dec_layers >= 1 && d->n_dec_layers <= 16,
                   "layer counts out of range (%d encoder, %d decoder)", d->n_enc_layers, d->n_dec_layers);
+  if (d->dec_vocab > 256) {
+    set_error("decoder vocabulary %d: the fused head kernel handles up to 256 entries (reference: 44 / 170)",
+              d->dec_vocab);
+    return B200VQA_ERR_UNSUPPORTED_SHAPE;
+  }
   B200VQA_REQUIRE(d->enc_vocab > 0 && d->dec_vocab > 0 && d->pe_enc_len > 0 && d->pe_dec_len > 0,
                   "vocabulary / positional table sizes must be positive");
   B200VQA_REQUIRE(d->image_proj_weight && d->image_proj_bias && d->enc_embedding && d->dec_embedding && d->pe_enc &&
@@ -423,6 +429,7 @@ int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, 
 int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int lda, const void* W, int N,
          GemmParams p, cudaStream_t s) {
   if (M <= 0) return B200VQA_OK;
+  p.pdl = h->pdl_chain;
   const TmapType ty = tf32 ? TmapType::kF32 : TmapType::kBF16;
   // narrower tiles when there are too few 128-row tiles to occupy the SMs (the decode GEMMs, M = batch)
   int bn = 256;
@@ -431,11 +438,12 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
     if (tiles_m * (N / 256) < h->num_sms / 2 && N % 128 == 0) bn = 128;
     if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0) bn = 64;
   }
+  if (epi == kEpiHead) bn = N;  // N = padded vocabulary (one n-tile); rows >= V of W are zero-filled by TMA
   const CUtensorMap *ta, *tw, *to;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(K), uint64_t(lda), 128, &ta));
-  RC_OK(get_tmap(h, W, ty, uint64_t(N), uint64_t(K), uint64_t(K), bn, &tw));
-  if (epi == kEpiBiasPeRemap) to = ta;  // unused by that epilogue
+  RC_OK(get_tmap(h, W, ty, uint64_t(epi == kEpiHead ? p.head_V : N), uint64_t(K), uint64_t(K), bn, &tw));
+  if (epi == kEpiBiasPeRemap || epi == kEpiHead) to = ta;  // unused by those epilogues
   else RC_OK(get_tmap(h, p.out, TmapType::kBF16, uint64_t(M), uint64_t(N), uint64_t(p.ldc), 32, &to, 32));
   p.M = M;
   p.N = N;
@@ -555,6 +563,11 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
     h->cur_tag = kTagEmbed;
     LAUNCH_OK(h, launch_dec_embed_start(ep, s));
   }
+  h->pdl_chain = true;
+  struct PdlOff {
+    b200vqa_handle* h;
+    ~PdlOff() { h->pdl_chain = false; }
+  } pdl_off{h};
   for (int t = 0; t < io.steps; ++t) {
     const __nv_bfloat16* in = w.dx;
     for (int l = 0; l < d.n_dec_layers; ++l) {
@@ -580,6 +593,7 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
       sp.k_app = w.kc[l];
       sp.v_app = w.vc[l];
       sp.out = w.dattn;
+      sp.pdl = true;
       h->cur_tag = kTagDecSelfAttn;
       LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemm;
@@ -597,6 +611,7 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
       cp.lens = lens;
       cp.const_len = const_len;
       cp.out = w.dattn;
+      cp.pdl = true;
       h->cur_tag = kTagDecCrossAttn;
       LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemm;
@@ -621,34 +636,34 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
         fp.partial = w.ffn_partial;
         fp.out = out;
         fp.out_f32 = last ? w.dout : nullptr;
+        fp.fn_gamma = last ? h->dec_fn_w : nullptr;
+        fp.fn_beta = last ? h->dec_fn_b : nullptr;
+        fp.pdl = true;
         h->cur_tag = kTagDecFfn;
         LAUNCH_OK(h, launch_ffn_small(*tx, *tw1, *tw2, fp, s));
         ++h->launches;  // two kernels
       }
       in = out;
     }
-    DecHeadParams hp;
-    hp.B = B;
-    hp.V = d.dec_vocab;
-    hp.t = t;
-    hp.x_f32 = w.dout;
-    hp.fn_gamma = h->dec_fn_w;
-    hp.fn_beta = h->dec_fn_b;
-    hp.eps = d.layer_norm_eps;
-    hp.w_t = h->head_wt;
-    hp.bias = h->head_b;
-    hp.tok = w.tok;
-    hp.tok_ld = kTokLd;
-    hp.logits = io.logits;
-    hp.logits_T = io.logits_T;
-    hp.forced = io.forced;
-    hp.forced_ld = io.forced_ld;
-    hp.emb = h->dec_emb;
-    hp.vocab = d.dec_vocab;
-    hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
-    hp.x_next = w.dx;
-    h->cur_tag = kTagDecHead;
-    LAUNCH_OK(h, launch_dec_head(hp, s));
+    {
+      // vocabulary head on the tensor cores (tf32 inputs, fp32 accumulate) with argmax + next embedding fused
+      GemmParams hp;
+      hp.bias = h->head_b;
+      hp.head_V = d.dec_vocab;
+      hp.head_t = t;
+      hp.tok = w.tok;
+      hp.tok_ld = kTokLd;
+      hp.logits = io.logits;
+      hp.logits_T = io.logits_T;
+      hp.forced = io.forced;
+      hp.forced_ld = io.forced_ld;
+      hp.emb = h->dec_emb;
+      hp.vocab = d.dec_vocab;
+      hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
+      hp.x_next = w.dx;
+      h->cur_tag = kTagDecHead;
+      RC_OK(gemm(h, kEpiHead, true, w.dout, B, kD, kD, h->head_w, d.dec_vocab <= 64 ? 64 : 256, hp, s));
+    }
   }
   return B200VQA_OK;
 }
@@ -803,6 +818,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   h->device = device;
   h->num_sms = num_sms;
   if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
+  if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
   h->dec_src.assign(desc->dec_layers, desc->dec_layers + desc->n_dec_layers);

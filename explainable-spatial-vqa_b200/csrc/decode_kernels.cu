@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = lane / LPH;
+  pdl_launch_dependents();
+  pdl_wait();
   int len = p.lens ? p.lens[b] : p.const_len;
   len = len > kLP ? kLP : len;
 
@@ -174,6 +176,8 @@ __global__ void __launch_bounds__(256) dec_head_kernel(const DecHeadParams p) {
   __shared__ int s_besti[kHeadQ][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * kHeadQ;
+  pdl_launch_dependents();
+  pdl_wait();
 
   {  // warp w stages question b0 + w (optional final LayerNorm, FA's transformer.decoder.norm)
     const int b = b0 + warp;
@@ -284,15 +288,13 @@ cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream)
 
 cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
   const int dh = kD / p.nhead;
-  if (dh == 64) row_attn_kernel<64><<<p.B, kAttnWarps * 32, 0, stream>>>(p);
-  else if (dh == 128) row_attn_kernel<128><<<p.B, kAttnWarps * 32, 0, stream>>>(p);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (dh == 64) return launch_kernel(row_attn_kernel<64>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
+  if (dh == 128) return launch_kernel(row_attn_kernel<128>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream) {
-  dec_head_kernel<<<ceil_div(p.B, kHeadQ), 256, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(dec_head_kernel, dim3(ceil_div(p.B, kHeadQ)), dim3(256), 0, stream, p.pdl, p);
 }
 
 cudaError_t launch_publish_tokens(const PublishParams& p, cudaStream_t stream) {

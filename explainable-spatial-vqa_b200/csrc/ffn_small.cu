@@ -65,6 +65,7 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -74,15 +75,16 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
+      // weights first (independent of the previous kernel), activations after the dependency wait
       mbar_expect_tx(bar_in1, L::kX + L::kW1);
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        tma_load_2d(&tm_x, bar_in1, sX + kb * 16384, kb * 64, m0);
-        tma_load_2d(&tm_w1, bar_in1, sW1 + kb * 16384, kb * 64, slice * kSlice);
-      }
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tm_w1, bar_in1, sW1 + kb * 16384, kb * 64, slice * kSlice);
       mbar_expect_tx(bar_in2, L::kW2);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) tma_load_2d(&tm_w2, bar_in2, sW2 + kb * 32768, slice * kSlice + kb * 64, 0);
+      pdl_wait();
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tm_x, bar_in1, sX + kb * 16384, kb * 64, m0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -114,6 +116,7 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    pdl_wait();  // the partial-sum buffer is still being read by the previous reduce kernel until here
     mbar_wait(bar_d1, 0);
     __syncwarp();
     tc_fence_after_sync();
@@ -177,6 +180,8 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 __global__ void __launch_bounds__(256) ffn_reduce_ln_kernel(const FfnSmallParams p) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= p.M) return;
   float v[8];
   {
@@ -216,6 +221,24 @@ __global__ void __launch_bounds__(256) ffn_reduce_ln_kernel(const FfnSmallParams
   *reinterpret_cast<uint4*>(p.out + size_t(row) * kD + lane * 8) =
       make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
   if (p.out_f32) {
+    if (p.fn_gamma) {  // final decoder norm on top of norm3 (fp32, feeds the vocabulary head)
+      float a1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a1 += y[j];
+      const float m2 = warp_sum(a1) * (1.f / kD);
+      float a2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a2 += (y[j] - m2) * (y[j] - m2);
+      const float r2 = rsqrtf(warp_sum(a2) * (1.f / kD) + p.eps);
+      const float4 fg0 = __ldg(reinterpret_cast<const float4*>(p.fn_gamma + lane * 8));
+      const float4 fg1 = __ldg(reinterpret_cast<const float4*>(p.fn_gamma + lane * 8) + 1);
+      const float4 fb0 = __ldg(reinterpret_cast<const float4*>(p.fn_beta + lane * 8));
+      const float4 fb1 = __ldg(reinterpret_cast<const float4*>(p.fn_beta + lane * 8) + 1);
+      const float fg[8] = {fg0.x, fg0.y, fg0.z, fg0.w, fg1.x, fg1.y, fg1.z, fg1.w};
+      const float fb[8] = {fb0.x, fb0.y, fb0.z, fb0.w, fb1.x, fb1.y, fb1.z, fb1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (y[j] - m2) * r2 * fg[j] + fb[j];
+    }
     float4* dst = reinterpret_cast<float4*>(p.out_f32 + size_t(row) * kD + lane * 8);
     dst[0] = make_float4(y[0], y[1], y[2], y[3]);
     dst[1] = make_float4(y[4], y[5], y[6], y[7]);
@@ -236,11 +259,10 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
     attr_done = true;
   }
   dim3 grid((p.M + 127) / 128, p.n_slices);
-  ffn_partial_kernel<<<grid, kFfnThreads, FfnSmem::kBytes, stream>>>(tm_x, tm_w1, tm_w2, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(ffn_partial_kernel, grid, dim3(kFfnThreads), FfnSmem::kBytes, stream, p.pdl, tm_x, tm_w1,
+                                tm_w2, p);
   if (e != cudaSuccess) return e;
-  ffn_reduce_ln_kernel<<<(p.M * 32 + 255) / 256, 256, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(ffn_reduce_ln_kernel, dim3((p.M * 32 + 255) / 256), dim3(256), 0, stream, p.pdl, p);
 }
 
 }  // namespace b200vqa

@@ -98,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
-    if (EPI != kEpiBiasPeRemap) tma_prefetch_desc(&tm_out);
+    if (EPI != kEpiBiasPeRemap && EPI != kEpiHead) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -112,6 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_launch_dependents();  // the next kernel of the stream may start its own prologue now
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -124,6 +125,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t phase = 0;
       int cur_n = -1;
       uint32_t wphase = 0;
+      if (wstat && t_begin < t_end) {
+        // weights do not depend on the previous kernel: fetch the first W tile before waiting for it
+        const int nt = t_begin / tiles_m;
+        mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, nt * BN);
+        cur_n = nt;
+        wphase = 1;
+      }
+      pdl_wait();  // A (and everything the epilogue reads / overwrites) belongs to the previous kernel until here
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int nt = tile / tiles_m;
         const int m0 = (tile - nt * tiles_m) * kBM;
@@ -210,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     uint32_t nstore = 0;  // TMA stores issued by this warp's lane 0 (staging buffer = nstore & 1)
+    pdl_wait();
 
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int nt = tile / tiles_m;
@@ -291,6 +302,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          }
+        }
+      } else if constexpr (EPI == kEpiHead) {
+        // logits of this warp's columns, running argmax in increasing column order (first maximum wins)
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        float* lrow = (p.logits && valid) ? p.logits + (size_t(row) * p.logits_T + p.head_t) * p.head_V : nullptr;
+#pragma unroll 1
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
+          if (n0 + c * 32 >= p.head_V) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c * 32 + j;
+            if (col < p.head_V) {
+              const float lg = __uint_as_float(r[j]) + __ldg(p.bias + col);
+              if (lrow) lrow[col] = lg;
+              if (lg > best) { best = lg; besti = col; }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        // combine with the partner warp (the other half of the columns of the same rows)
+        const int partner = ew ^ 4;
+        xch[ew * 32 + lane] = make_float2(best, __int_as_float(besti));
+        named_bar_sync(1 + quarter, 64);
+        const float2 other = xch[partner * 32 + lane];
+        const int oi = __float_as_int(other.y);
+        if (other.x > best || (other.x == best && oi < besti)) { best = other.x; besti = oi; }
+        named_bar_sync(1 + quarter, 64);  // xch is reused by the next tile
+        if (besti >= p.head_V) besti = 0;  // all-NaN row: keep the index in range
+        if (valid) {
+          if (half == 0) p.tok[size_t(row) * p.tok_ld + p.head_t + 1] = besti;
+          if (p.pe_next) {
+            long long nxt = p.forced ? p.forced[size_t(row) * p.forced_ld + p.head_t] : (long long)besti;
+            nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
+            // next decoder input: this thread writes columns [128*half, 128*half + 128) of its row
+            const float* erow = p.emb + size_t(nxt) * kD + half * 128;
+            const float* prow = p.pe_next + half * 128;
+            __nv_bfloat16* xrow = p.x_next + size_t(row) * kD + half * 128;
+#pragma unroll 4
+            for (int j = 0; j < 128; j += 8) {
+              const float4 e0 = ldg4(erow + j), e1 = ldg4(erow + j + 4);
+              const float4 p0 = ldg4(prow + j), p1 = ldg4(prow + j + 4);
+              *reinterpret_cast<uint4*>(xrow + j) =
+                  make_uint4(pack_bf16x2(e0.x + p0.x, e0.y + p0.y), pack_bf16x2(e0.z + p0.z, e0.w + p0.w),
+                             pack_bf16x2(e1.x + p1.x, e1.y + p1.y), pack_bf16x2(e1.z + p1.z, e1.w + p1.w));
+            }
           }
         }
       } else {  // kEpiBiasResLN : this warp holds 32 rows x (BN/2) columns of v = acc + bias + residual in registers
@@ -421,8 +485,7 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const C
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kfn<<<grid, kGemmThreads, L::kBytes, stream>>>(tm_a, tm_w, tm_out, p);
-  return cudaGetLastError();
+  return launch_kernel(kfn, dim3(grid), dim3(kGemmThreads), L::kBytes, stream, p.pdl, tm_a, tm_w, tm_out, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -444,6 +507,7 @@ __global__ void gemm_check_kernel(const TA* __restrict__ A, const TA* __restrict
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                         const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.N % block_n != 0) return cudaErrorInvalidValue;
+  if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N || p.K != kD)) return cudaErrorInvalidValue;
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \
@@ -457,6 +521,8 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
   B200VQA_GEMM_CASE(256, kEpiBiasResLN, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, true)
+  B200VQA_GEMM_CASE(64, kEpiHead, true)
+  B200VQA_GEMM_CASE(256, kEpiHead, true)
 #undef B200VQA_GEMM_CASE
   return cudaErrorInvalidValue;
 }

@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include "kernels.h"
 
 #include <cstring>
 #include <mutex>
@@ -25,6 +26,12 @@ EncodeTiledFn resolve_encode() {
   return fn;
 }
 }  // namespace
+
+namespace {
+bool g_pdl = true;
+}
+bool pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(bool on) { g_pdl = on; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;

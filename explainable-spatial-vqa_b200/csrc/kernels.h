@@ -2,11 +2,33 @@
 // Nothing here crosses the shared-library boundary; the public surface is include/b200vqa.h.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 namespace b200vqa {
+
+// Launch helper: plain <<<>>> semantics, optionally with programmatic dependent launch (the kernel must call
+// pdl_wait() before it touches anything its predecessor produced or still reads).
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Padded per-question row count of the encoder activations (sequence rows live at [b*kLP, b*kLP+len)).
 constexpr int kLP = 256;
@@ -19,11 +41,14 @@ enum GemmEpilogue : int {
   kEpiBias = 0,       // bf16 out = acc + bias
   kEpiBiasRelu = 1,   // bf16 out = relu(acc + bias)
   kEpiBiasResLN = 2,  // bf16 out = LayerNorm(acc + bias + residual) * gamma + beta   (N == 256)
-  kEpiBiasPeRemap = 3 // bf16 out[row'] = acc + bias + pe[p]; row' = item*rows_out + off + p
+  kEpiBiasPeRemap = 3,// bf16 out[row'] = acc + bias + pe[p]; row' = item*rows_out + off + p
+  kEpiHead = 4        // vocabulary head of one decode position: logits = acc + bias (N = padded vocabulary), argmax ->
+                      // tok[row, t+1], next input x_next[row] = emb[next] + pe[t+1]   (IQAP:230-236, FA:142-145)
 };
 
 struct GemmParams {
   int M = 0, N = 0, K = 0;
+  bool pdl = false;                  // launch with programmatic dependent launch (decode chain)
   const float* bias = nullptr;       // [N] fp32 (may be null)
   __nv_bfloat16* out = nullptr;      // bf16 output
   int ldc = 0;                       // output leading dimension (elements)
@@ -40,6 +65,19 @@ struct GemmParams {
   int row_off = 0;                   // first output row inside the item
   const float* pe = nullptr;         // [*, N] fp32 positional-encoding table
   int pe_off = 0;                    // pe row = pe_off + p
+  // kEpiHead (A = fp32 decoder output [M, 256] read as tf32, W = fp32 head weight [V, 256])
+  int head_V = 0;                    // real vocabulary size (columns >= V are padding)
+  int head_t = 0;                    // decode position
+  int64_t* tok = nullptr;            // [M, tok_ld]; argmax (lowest index wins ties) written to column t+1
+  int tok_ld = 0;
+  float* logits = nullptr;           // optional [M, logits_T, V]; row t
+  int logits_T = 0;
+  const int64_t* forced = nullptr;   // optional teacher forcing: position t+1 is fed forced[row*forced_ld + t]
+  int forced_ld = 0;
+  const float* emb = nullptr;        // [vocab, 256] decoder embedding
+  int vocab = 0;
+  const float* pe_next = nullptr;    // pe row t+1, null on the last position
+  __nv_bfloat16* x_next = nullptr;   // [M, 256]
 };
 
 // A/W tensor maps: 2D, 128-byte swizzle, box = {128 B of K, 128 rows (A) | BN rows (W)}.
@@ -144,6 +182,7 @@ cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream)
 // projected encoder memory.  Key row j of question b is at k + (b*rows_per_q + j)*ld: 256 contiguous bf16.
 struct RowAttnParams {
   int B = 0, nhead = 4;
+  bool pdl = false;
   const __nv_bfloat16* q = nullptr;  // [B, ldq], columns 0..255
   int ldq = 0;
   const __nv_bfloat16* k = nullptr;
@@ -169,6 +208,7 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream);
 // forced token if given.
 struct DecHeadParams {
   int B = 0, V = 0, t = 0;
+  bool pdl = false;
   const float* x_f32 = nullptr;       // [B,kD] fp32 output of the last decoder layer's norm3
   const float* fn_gamma = nullptr;    // final decoder norm (FA) or null
   const float* fn_beta = nullptr;
@@ -211,6 +251,7 @@ cudaError_t launch_publish_tokens(const PublishParams& p, cudaStream_t stream);
 // tm_x: x [M, kD] box 128 rows; tm_w1: W1 [ff, kD] box 128 rows; tm_w2: W2 [kD, ff] box 256 rows (all 128B-swizzled)
 struct FfnSmallParams {
   int M = 0, ff = 0, n_slices = 0;
+  bool pdl = false;
   const float* b1 = nullptr;
   const float* b2 = nullptr;
   const __nv_bfloat16* residual = nullptr;
@@ -219,7 +260,9 @@ struct FfnSmallParams {
   float eps = 1e-5f;
   float* partial = nullptr;
   __nv_bfloat16* out = nullptr;
-  float* out_f32 = nullptr;  // optional fp32 copy of the output
+  float* out_f32 = nullptr;  // optional fp32 copy of the output ...
+  const float* fn_gamma = nullptr;  // ... after a second LayerNorm when given (nn.Transformer's decoder.norm, FA:42)
+  const float* fn_beta = nullptr;
 };
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
