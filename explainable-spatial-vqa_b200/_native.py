@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200vqa_profile_tag_name": (C.c_char_p, [C.c_int]),
     "b200vqa_profile_begin": (C.c_int, [_vp]),
     "b200vqa_profile_end": (C.c_int, [_vp, _vp, _vp]),
+    "b200vqa_profile_delay": (C.c_int, [_vp, C.c_double, _vp]),
     "b200vqa_iqap_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
@@ -179,6 +180,9 @@ class Handle:
 
     def profile_begin(self):
         check(self._lib.b200vqa_profile_begin(self._h), "b200vqa_profile_begin")
+
+    def profile_delay(self, ms: float):
+        check(self._lib.b200vqa_profile_delay(self._h, float(ms), stream_ptr(self.device)), "b200vqa_profile_delay")
 
     def profile_end(self) -> dict:
         """{kernel class: (total ms, launches)} since profile_begin (synchronises the device)."""

@@ -125,6 +125,10 @@ struct b200vqa_handle {
   bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
+  int decode_branches = 4;            // concurrent question ranges inside the decode graph
+  cudaStream_t br_stream[7] = {};
+  cudaEvent_t br_done[7] = {};
+  cudaEvent_t br_fork = nullptr;
   bool profiling = false;
   std::vector<ProfRec> prof;
 
@@ -537,90 +541,86 @@ struct DecodeIO {
 // The launch sequence of one greedy decode: cross K|V projection of the memory, start embedding, then `steps`
 // positions x layers.  Every argument is a library-owned buffer or a value in the graph key, so the same
 // sequence can be captured once and replayed (run_decoder).
-int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
-                    const DecodeIO& io, cudaStream_t s) {
+// Decode positions 0..steps-1 for the questions [b_lo, b_lo + B) of the current chunk on stream `s`: a chain of
+// small kernels per position (PDL-linked).  `br` selects this branch's slice of the partial-sum buffer.
+int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens, int const_len, const DecodeIO& io,
+                        cudaStream_t s) {
   Workspace& w = h->ws;
   const auto& d = h->d;
-  const int M = B * kLP;
-  // cross-attention K|V of the memory: once per question (the reference recomputes it every step)
-  h->cur_tag = kTagDecCrossKv;
-  for (int l = 0; l < d.n_dec_layers; ++l) {
-    const MhaPacked& ca = h->dec[l].cross_attn;
-    RC_OK(gemm_bias(h, false, memory, M, kD, ca.w_in + size_t(kD) * kD, 2 * kD, ca.b_in + kD, w.ckv[l], s));
-  }
-  {
-    DecEmbedParams ep;
-    ep.B = B;
-    ep.emb = h->dec_emb;
-    ep.vocab = d.dec_vocab;
-    ep.pe = h->pe_dec;
-    ep.start_token = std::min(std::max(io.start_token, 0), d.dec_vocab - 1);
-    ep.start_tokens = io.start_tokens;
-    ep.start_ld = io.start_ld;
-    ep.x = w.dx;
-    ep.tok = w.tok;
-    ep.tok_ld = kTokLd;
-    h->cur_tag = kTagEmbed;
-    LAUNCH_OK(h, launch_dec_embed_start(ep, s));
-  }
+  const size_t r0 = size_t(b_lo);
+  __nv_bfloat16* dx = w.dx + r0 * kD;
+  __nv_bfloat16* dqkv = w.dqkv + r0 * 3 * kD;
+  __nv_bfloat16* dattn = w.dattn + r0 * kD;
+  __nv_bfloat16* dx1 = w.dx1 + r0 * kD;
+  __nv_bfloat16* dq = w.dq + r0 * kD;
+  __nv_bfloat16* dx2 = w.dx2 + r0 * kD;
+  __nv_bfloat16* dxo[2] = {w.dxo[0] + r0 * kD, w.dxo[1] + r0 * kD};
+  float* dout = w.dout + r0 * kD;
+  float* partial = w.ffn_partial + r0 * size_t(d.dim_ff / 128) * kD;
+  int64_t* tok = w.tok + r0 * kTokLd;
+  const int32_t* lens_b = lens ? lens + b_lo : nullptr;
+  float* logits = io.logits ? io.logits + r0 * io.logits_T * d.dec_vocab : nullptr;
+  const int64_t* forced = io.forced ? io.forced + r0 * io.forced_ld : nullptr;
   h->pdl_chain = true;
   struct PdlOff {
     b200vqa_handle* h;
     ~PdlOff() { h->pdl_chain = false; }
   } pdl_off{h};
   for (int t = 0; t < io.steps; ++t) {
-    const __nv_bfloat16* in = w.dx;
+    const __nv_bfloat16* in = dx;
     for (int l = 0; l < d.n_dec_layers; ++l) {
       const LayerPacked& L = h->dec[l];
       const bool last = l == d.n_dec_layers - 1;
-      __nv_bfloat16* out = w.dxo[l & 1];
+      __nv_bfloat16* out = dxo[l & 1];
+      __nv_bfloat16* kc = w.kc[l] + r0 * w.t_max * kD;
+      __nv_bfloat16* vc = w.vc[l] + r0 * w.t_max * kD;
+      const __nv_bfloat16* ckv = w.ckv[l] + r0 * kLP * 2 * kD;
       h->cur_tag = kTagDecGemm;
-      RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.dqkv, s));
+      RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, dqkv, s));
       RowAttnParams sp;
       sp.B = B;
       sp.nhead = d.nhead;
-      sp.q = w.dqkv;
+      sp.q = dqkv;
       sp.ldq = 3 * kD;
-      sp.k = w.kc[l];
-      sp.v = w.vc[l];
+      sp.k = kc;
+      sp.v = vc;
       sp.rows_per_q = w.t_max;
       sp.ld = kD;
       sp.const_len = t + 1;
-      sp.new_k = w.dqkv + kD;
-      sp.new_v = w.dqkv + 2 * kD;
+      sp.new_k = dqkv + kD;
+      sp.new_v = dqkv + 2 * kD;
       sp.ld_new = 3 * kD;
       sp.append_pos = t;
-      sp.k_app = w.kc[l];
-      sp.v_app = w.vc[l];
-      sp.out = w.dattn;
+      sp.k_app = kc;
+      sp.v_app = vc;
+      sp.out = dattn;
       sp.pdl = true;
       h->cur_tag = kTagDecSelfAttn;
       LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemm;
-      RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.dx1, nullptr, s));
-      RC_OK(gemm_bias(h, false, w.dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, w.dq, s));
+      RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s));
+      RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
       RowAttnParams cp;
       cp.B = B;
       cp.nhead = d.nhead;
-      cp.q = w.dq;
+      cp.q = dq;
       cp.ldq = kD;
-      cp.k = w.ckv[l];
-      cp.v = w.ckv[l] + kD;
+      cp.k = ckv;
+      cp.v = ckv + kD;
       cp.rows_per_q = kLP;
       cp.ld = 2 * kD;
-      cp.lens = lens;
+      cp.lens = lens_b;
       cp.const_len = const_len;
-      cp.out = w.dattn;
+      cp.out = dattn;
       cp.pdl = true;
       h->cur_tag = kTagDecCrossAttn;
       LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemm;
-      RC_OK(gemm_res_ln(h, w.dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, w.dx1, L.n2w, L.n2b, w.dx2, nullptr,
-                        s));
+      RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s));
       {
         // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
         const CUtensorMap *tx, *tw1, *tw2;
-        RC_OK(get_tmap(h, w.dx2, TmapType::kBF16, uint64_t(B), kD, kD, 128, &tx));
+        RC_OK(get_tmap(h, dx2, TmapType::kBF16, uint64_t(B), kD, kD, 128, &tx));
         RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 128, &tw1));
         RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 256, &tw2));
         FfnSmallParams fp;
@@ -629,13 +629,13 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
         fp.n_slices = d.dim_ff / 128;
         fp.b1 = L.b1;
         fp.b2 = L.b2;
-        fp.residual = w.dx2;
+        fp.residual = dx2;
         fp.gamma = L.n3w;
         fp.beta = L.n3b;
         fp.eps = d.layer_norm_eps;
-        fp.partial = w.ffn_partial;
+        fp.partial = partial;
         fp.out = out;
-        fp.out_f32 = last ? w.dout : nullptr;
+        fp.out_f32 = last ? dout : nullptr;
         fp.fn_gamma = last ? h->dec_fn_w : nullptr;
         fp.fn_beta = last ? h->dec_fn_b : nullptr;
         fp.pdl = true;
@@ -651,21 +651,89 @@ int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const
       hp.bias = h->head_b;
       hp.head_V = d.dec_vocab;
       hp.head_t = t;
-      hp.tok = w.tok;
+      hp.tok = tok;
       hp.tok_ld = kTokLd;
-      hp.logits = io.logits;
+      hp.logits = logits;
       hp.logits_T = io.logits_T;
-      hp.forced = io.forced;
+      hp.forced = forced;
       hp.forced_ld = io.forced_ld;
       hp.emb = h->dec_emb;
       hp.vocab = d.dec_vocab;
       hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
-      hp.x_next = w.dx;
+      hp.x_next = dx;
       h->cur_tag = kTagDecHead;
-      RC_OK(gemm(h, kEpiHead, true, w.dout, B, kD, kD, h->head_w, d.dec_vocab <= 64 ? 64 : 256, hp, s));
+      RC_OK(gemm(h, kEpiHead, true, dout, B, kD, kD, h->head_w, d.dec_vocab <= 64 ? 64 : 256, hp, s));
     }
   }
   return B200VQA_OK;
+}
+
+// Work that precedes the per-position chains: cross-attention K|V of the memory - once per question (the reference
+// recomputes it every step) - and the start embedding.
+int enqueue_decode_prologue(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const DecodeIO& io,
+                            cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  const int M = B * kLP;
+  h->cur_tag = kTagDecCrossKv;
+  for (int l = 0; l < d.n_dec_layers; ++l) {
+    const MhaPacked& ca = h->dec[l].cross_attn;
+    RC_OK(gemm_bias(h, false, memory, M, kD, ca.w_in + size_t(kD) * kD, 2 * kD, ca.b_in + kD, w.ckv[l], s));
+  }
+  DecEmbedParams ep;
+  ep.B = B;
+  ep.emb = h->dec_emb;
+  ep.vocab = d.dec_vocab;
+  ep.pe = h->pe_dec;
+  ep.start_token = std::min(std::max(io.start_token, 0), d.dec_vocab - 1);
+  ep.start_tokens = io.start_tokens;
+  ep.start_ld = io.start_ld;
+  ep.x = w.dx;
+  ep.tok = w.tok;
+  ep.tok_ld = kTokLd;
+  h->cur_tag = kTagEmbed;
+  LAUNCH_OK(h, launch_dec_embed_start(ep, s));
+  return B200VQA_OK;
+}
+
+int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                    const DecodeIO& io, cudaStream_t s) {
+  RC_OK(enqueue_decode_prologue(h, B, memory, io, s));
+  return enqueue_decode_rows(h, 0, B, lens, const_len, io, s);
+}
+
+// Graph-capture form: the batch is split into independent branches (questions never interact) that the GPU runs
+// concurrently, so one branch's latency-bound chain of small GEMMs overlaps another branch's HBM-bound
+// cross-attention.
+int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                             const DecodeIO& io, cudaStream_t s) {
+  RC_OK(enqueue_decode_prologue(h, B, memory, io, s));
+  int nbr = h->decode_branches;
+  while (nbr > 1 && B / nbr < 128) --nbr;
+  if (nbr <= 1) return enqueue_decode_rows(h, 0, B, lens, const_len, io, s);
+  for (int i = 0; i < nbr - 1; ++i) {
+    if (!h->br_stream[i]) {
+      B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking));
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->br_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (!h->br_fork) B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->br_fork, cudaEventDisableTiming));
+  B200VQA_CUDA_OK(cudaEventRecord(h->br_fork, s));
+  // branch boundaries on multiples of 128 rows so every branch starts on its own GEMM tile
+  const int per = ((B + nbr - 1) / nbr + 127) / 128 * 128;
+  int rc = B200VQA_OK;
+  for (int i = 0; i < nbr && rc == B200VQA_OK; ++i) {
+    const int lo = i * per, hi = std::min(B, lo + per);
+    if (lo >= hi) break;
+    cudaStream_t bs = i == 0 ? s : h->br_stream[i - 1];
+    if (i > 0) B200VQA_CUDA_OK(cudaStreamWaitEvent(bs, h->br_fork, 0));
+    rc = enqueue_decode_rows(h, lo, hi - lo, lens, const_len, io, bs);
+    if (i > 0) {
+      B200VQA_CUDA_OK(cudaEventRecord(h->br_done[i - 1], bs));
+      B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->br_done[i - 1], 0));
+    }
+  }
+  return rc;
 }
 
 // Greedy decode into ws.tok.  The plain (no logits / no teacher forcing) sequence depends only on
@@ -686,7 +754,7 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
     cudaGraph_t graph = nullptr;
     if (!h->cap_stream) B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     B200VQA_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_decoder(h, B, memory, lens, const_len, io, h->cap_stream);
+    int rc = enqueue_decoder_branched(h, B, memory, lens, const_len, io, h->cap_stream);
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc != B200VQA_OK) {
       if (graph) cudaGraphDestroy(graph);
@@ -819,6 +887,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   h->num_sms = num_sms;
   if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
+  if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
   h->dec_src.assign(desc->dec_layers, desc->dec_layers + desc->n_dec_layers);
@@ -885,6 +954,11 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (int i = 0; i < 7; ++i) {
+    if (h->br_stream[i]) cudaStreamDestroy(h->br_stream[i]);
+    if (h->br_done[i]) cudaEventDestroy(h->br_done[i]);
+  }
+  if (h->br_fork) cudaEventDestroy(h->br_fork);
   delete h;
 }
 
@@ -910,6 +984,15 @@ B200VQA_API int b200vqa_profile_begin(b200vqa_handle* h) {
   }
   h->prof.clear();
   h->profiling = true;
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_profile_delay(b200vqa_handle* h, double ms, void* stream) {
+  B200VQA_REQUIRE(h != nullptr && ms >= 0 && ms <= 200, "bad arguments");
+  RC_OK(set_device(h));
+  int khz = 0;
+  B200VQA_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+  B200VQA_CUDA_OK(launch_delay((long long)(ms * khz), static_cast<cudaStream_t>(stream)));
   return B200VQA_OK;
 }
 

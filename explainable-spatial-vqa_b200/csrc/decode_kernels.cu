@@ -92,18 +92,25 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   const __nv_bfloat16* kbase = p.k + size_t(b) * p.rows_per_q * p.ld + lane * 8;
   const __nv_bfloat16* vbase = p.v + size_t(b) * p.rows_per_q * p.ld + lane * 8;
 
-  for (int j0 = warp; j0 < len; j0 += kAttnWarps * kKeysInFlight) {
-    uint4 raw[kKeysInFlight];
+  // software-pipelined: the next batch of rows is in flight while the current one is consumed, and the first
+  // batch of V rows is requested before the softmax barrier so the HBM stream never drains
+  constexpr int kStep = kAttnWarps * kKeysInFlight;
+  auto load_rows = [&](const __nv_bfloat16* base, int j0, uint4 (&raw)[kKeysInFlight]) {
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;
-      raw[u] = (j < len) ? ld_stream16(kbase + size_t(j) * p.ld) : make_uint4(0, 0, 0, 0);
+      raw[u] = (j < len) ? ld_stream16(base + size_t(j) * p.ld) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 cur[kKeysInFlight], nxt[kKeysInFlight];
+  load_rows(kbase, warp, cur);
+  for (int j0 = warp; j0 < len; j0 += kStep) {
+    if (j0 + kStep < len) load_rows(kbase, j0 + kStep, nxt);
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;
       float kx[8];
-      unpack8(raw[u], kx);
+      unpack8(cur[u], kx);
       float s = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) s = fmaf(q[e], kx[e], s);
@@ -111,7 +118,10 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
       for (int o = LPH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if ((lane % LPH) == 0 && j < len) s_sc[head][j] = s;
     }
+#pragma unroll
+    for (int u = 0; u < kKeysInFlight; ++u) cur[u] = nxt[u];
   }
+  load_rows(vbase, warp, cur);  // first V batch: in flight across the softmax
   __syncthreads();
 
   if (warp < p.nhead) {  // softmax statistics of head `warp`
@@ -132,24 +142,21 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int j0 = warp; j0 < len; j0 += kAttnWarps * kKeysInFlight) {
-    uint4 raw[kKeysInFlight];
-#pragma unroll
-    for (int u = 0; u < kKeysInFlight; ++u) {
-      const int j = j0 + u * kAttnWarps;
-      raw[u] = (j < len) ? ld_stream16(vbase + size_t(j) * p.ld) : make_uint4(0, 0, 0, 0);
-    }
+  for (int j0 = warp; j0 < len; j0 += kStep) {
+    if (j0 + kStep < len) load_rows(vbase, j0 + kStep, nxt);
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;
       if (j < len) {
         float vx[8];
-        unpack8(raw[u], vx);
+        unpack8(cur[u], vx);
         const float pj = s_sc[head][j];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < kKeysInFlight; ++u) cur[u] = nxt[u];
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) s_red[warp][lane * 8 + e] = acc[e];

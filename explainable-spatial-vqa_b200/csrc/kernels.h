@@ -267,6 +267,8 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+cudaError_t launch_delay(long long cycles, cudaStream_t stream);
+
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
 cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t stream);

@@ -150,6 +150,9 @@ B200VQA_API int b200vqa_profile_num_tags(void);
 B200VQA_API const char* b200vqa_profile_tag_name(int tag);
 B200VQA_API int b200vqa_profile_begin(b200vqa_handle* h);
 B200VQA_API int b200vqa_profile_end(b200vqa_handle* h, float* ms_per_tag, int32_t* launches_per_tag);
+/* Enqueues a kernel that keeps `stream` busy for about `ms` milliseconds: called before a profiled step so the host
+ * can enqueue the whole step behind it and the events see back-to-back kernels, not host launch latency. */
+B200VQA_API int b200vqa_profile_delay(b200vqa_handle* h, double ms, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* IQAP                                                                                                   */
