@@ -176,6 +176,39 @@ def cpu_fa(n_questions, recompute=True):
     return float(n_steps.sum()) / dt, dt
 
 
+def gpu_eager_iqap(dev, sample_b):
+    """Context only: the reference's algorithm (oracle, recompute-every-step form, fp32) run with PyTorch's own
+    CUDA kernels on this GPU - what the unmodified reference would do with device='cuda'.  program-steps/s."""
+    from oracle import executor_oracle as orc
+    from explainable_spatial_vqa_b200 import inference_transformer_iqap as iqap
+    torch.manual_seed(0)
+    sd = {k: v.to(dev) for k, v in iqap.VQAModel(85, 256, 256, 32, 44, T_PROG, 196).eval().state_dict().items()}
+    img, q = orc.iqap_inputs(sample_b, seed=1234)
+    img, q = img.to(dev), q.to(dev)
+    orc.iqap_forward(sd, img[:8], q[:8], recompute=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    orc.iqap_forward(sd, img, q, recompute=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return sample_b * T_PROG / (e0.elapsed_time(e1) * 1e-3)
+
+
+def h2d_probe(dev, nbytes=512 << 20):
+    """Pinned host -> device copy bandwidth of this box (GB/s): the ceiling of the e2e number."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -252,6 +285,9 @@ def run_ours(args):
         units_per_step = B * T_PROG
         counts = [B] * world
 
+        def step_local():
+            return model(img, q)
+
         def step():
             ans, prog = model(img, q)
             if world > 1:
@@ -278,6 +314,9 @@ def run_ours(args):
         func, deps, n_steps = func.to(dev), deps.to(dev), n_steps.to(dev)
         units_per_step = int(n_steps.sum())
         counts = [B] * world
+
+        def step_local():
+            return fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
 
         def step():
             cache = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
@@ -337,7 +376,7 @@ def run_ours(args):
         h.profile_begin()
         for _ in range(prof_steps):
             h.profile_delay(12.0)  # the host enqueues the step while the GPU is held: events see back-to-back kernels
-            step()
+            step_local()  # rank-local: no collective outside the lock-step timed loop
             torch.cuda.synchronize()
         prof = h.profile_end()
         total = sum(v[0] for v in prof.values())
@@ -358,11 +397,31 @@ def run_ours(args):
                 ach = per_launch / dur / 1e9
                 roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy)"}
+            # DRAM bytes per launch of this kernel class from the committed `ncu --set full` capture, if any
+            tpath = os.path.join(REPO, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tr = json.load(f).get(top)
+                if tr:
+                    roofline["traffic"] = tr["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = "profiles/" + tr["source"]
             roofline["algorithmic_per_launch"] = per_launch
             roofline["avg_launch_ms"] = dur * 1e3
             # whole-step tensor-core utilisation: algorithmic FLOPs of the model / step time / peak
             roofline["model_flops_frac_of_bf16_peak"] = (IQAP_FLOPS_PER_QUESTION * B / (ms / args.steps * 1e-3)) / (
                 peaks["bf16_tflops_sustained"] * 1e12)
+
+    extra = {}
+    if rank == 0:
+        try:
+            extra["h2d_gbs_measured"] = h2d_probe(dev)
+            if args.workload == "iqap" and world == 1 and not args.no_cpu_baseline:
+                extra["torch_eager_gpu_fp32"] = {
+                    "value": gpu_eager_iqap(dev, 256), "unit": "program-steps/s",
+                    "what": "oracle (reference algorithm, recompute-every-step, fp32) on this GPU with PyTorch's CUDA "
+                            "kernels, 256 questions - context only"}
+        except Exception as e:  # pragma: no cover - context numbers must never break the bench line
+            extra["context_error"] = repr(e)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,7 +448,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "program-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / max(1, args.steps // 2)},
             "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "context": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -405,7 +464,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="iqap", choices=["iqap", "fa"])
     ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
-    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1086,7 +1086,7 @@ B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img,
   RC_OK(check_decode_len(h, program_len));
   RC_OK(set_device(h));
   const auto& d = h->d;
-  if (chunk <= 0) chunk = 128;
+  if (chunk <= 0) chunk = 512;  // decode is latency-bound: few large chunks beat many small ones
   chunk = std::min({chunk, B, default_cap(h)});
   RC_OK(ensure_workspace(h, chunk, program_len));
   cudaStream_t s = static_cast<cudaStream_t>(stream);

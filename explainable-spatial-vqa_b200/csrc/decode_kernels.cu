@@ -4,7 +4,7 @@
 //
 //   dec_embed_start   x0 = emb[start] + pe[0]                                   (IQAP:205-216, FA:136-139)
 //   row_attn          one query row against len key/value rows, all heads       (IQAP:223-227, FA:141)
-//   dec_head          [final LayerNorm] -> vocabulary logits (fp32) -> argmax -> next embedding   (IQAP:230-236, FA:142-145)
+//   (the vocabulary head + argmax + next embedding is the kEpiHead epilogue of the tensor-core GEMM, gemm.cu)
 //   publish_tokens    library token buffer -> programs / ys / HBM step cache    (IQAP:239, FA:120-121)
 #include <algorithm>
 
@@ -170,107 +170,6 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Head: 8 questions per CTA (256 threads).  Thread (q = tid & 7, g = tid >> 3) accumulates the logits of
-// vocabulary entries g, g+32, ... for question q in fp32 from the x rows staged in shared memory; the
-// transposed head weight [kD, V] is read through L1 (45 KB for IQAP, 174 KB for FA).
-// ------------------------------------------------------------------------------------------------
-constexpr int kHeadQ = 8;
-
-__global__ void __launch_bounds__(256) dec_head_kernel(const DecHeadParams p) {
-  __shared__ float s_x[kHeadQ][kD + 1];
-  __shared__ float s_best[kHeadQ][32];
-  __shared__ int s_besti[kHeadQ][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b0 = blockIdx.x * kHeadQ;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  {  // warp w stages question b0 + w (optional final LayerNorm, FA's transformer.decoder.norm)
-    const int b = b0 + warp;
-    float v[8];
-    if (b < p.B) load_f32x8(p.x_f32 + size_t(b) * kD + lane * 8, v);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    }
-    if (p.fn_gamma) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[j];
-      const float mean = warp_sum(s) * (1.f / kD);
-      float qv = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qv += (v[j] - mean) * (v[j] - mean);
-      const float rstd = rsqrtf(warp_sum(qv) * (1.f / kD) + p.eps);
-      float g[8], bt[8];
-      load_f32x8(p.fn_gamma + lane * 8, g);
-      load_f32x8(p.fn_beta + lane * 8, bt);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bt[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s_x[warp][lane * 8 + j] = v[j];
-  }
-  __syncthreads();
-
-  const int qi = threadIdx.x & (kHeadQ - 1);
-  const int g = threadIdx.x >> 3;
-  const int b = b0 + qi;
-  float best = -INFINITY;
-  int besti = 0x7fffffff;
-  const float* xs = s_x[qi];
-  for (int v0 = g; v0 < p.V; v0 += 64) {  // two vocabulary entries per pass for ILP
-    const int v1 = v0 + 32;
-    const bool has1 = v1 < p.V;
-    float a0 = p.bias[v0], a1 = has1 ? p.bias[v1] : 0.f;
-    const float* w0 = p.w_t + v0;
-    const float* w1 = p.w_t + (has1 ? v1 : v0);
-#pragma unroll 8
-    for (int k = 0; k < kD; ++k) {
-      const float xk = xs[k];
-      a0 = fmaf(xk, __ldg(w0 + size_t(k) * p.V), a0);
-      a1 = fmaf(xk, __ldg(w1 + size_t(k) * p.V), a1);
-    }
-    if (b < p.B && p.logits) {
-      float* lrow = p.logits + (size_t(b) * p.logits_T + p.t) * p.V;
-      lrow[v0] = a0;
-      if (has1) lrow[v1] = a1;
-    }
-    if (a0 > best) { best = a0; besti = v0; }
-    if (has1 && a1 > best) { best = a1; besti = v1; }
-  }
-  s_best[qi][g] = best;
-  s_besti[qi][g] = besti;
-  __syncthreads();
-
-  {  // warp w: argmax over the 32 candidates of question b0 + w (first maximum wins ties)
-    const int bq = b0 + warp;
-    float bb = s_best[warp][lane];
-    int bi = s_besti[warp][lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, bb, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
-    }
-    if (bi >= p.V) bi = 0;  // all-NaN row: keep the index in range
-    if (bq < p.B) {
-      long long nxt = (p.forced && p.pe_next) ? p.forced[size_t(bq) * p.forced_ld + p.t] : (long long)bi;
-      nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
-      if (lane == 0) p.tok[size_t(bq) * p.tok_ld + p.t + 1] = bi;
-      if (p.pe_next) {
-        float e[8], pe8[8], o[8];
-        load_f32x8(p.emb + size_t(nxt) * kD + lane * 8, e);
-        load_f32x8(p.pe_next + lane * 8, pe8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = e[j] + pe8[j];
-        store_bf16x8(p.x_next + size_t(bq) * kD + lane * 8, o);
-      }
-    }
-  }
-}
-
 __global__ void publish_tokens_kernel(const PublishParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * p.n_cols) return;
@@ -298,10 +197,6 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
   if (dh == 64) return launch_kernel(row_attn_kernel<64>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
   if (dh == 128) return launch_kernel(row_attn_kernel<128>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
   return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream) {
-  return launch_kernel(dec_head_kernel, dim3(ceil_div(p.B, kHeadQ)), dim3(256), 0, stream, p.pdl, p);
 }
 
 cudaError_t launch_publish_tokens(const PublishParams& p, cudaStream_t stream) {

@@ -4,79 +4,73 @@
 // (IQAP:118,173; FA:42,135 -> torch functional.py:6244+): softmax(q k^T / sqrt(dh)) v per head, with a
 // key-length mask for the batched FA path (the reference is batch-1 and never pads).
 //
-// One CTA per (question, head, 128-query tile). The whole K and V of a head (<= 256 rows) sit in shared
-// memory, so there is no online-softmax rescaling:
-//   warp 0     TMA: Q tile, K and V (128B-swizzled boxes of the packed q|k|v activations)
-//   warp 1     tcgen05.mma  S[128 x keys] = Q K^T  into TMEM, later  O[128 x dh] = P V
-//   warps 2-5  one query row per thread: tcgen05.ld S, masked softmax in fp32 (exp2), P -> smem as the
-//              bf16 K-major A operand of the second MMA, then O / rowsum -> bf16 global
-// V is consumed directly as an MN-major B operand (v_mode 0); v_mode 1 transposes it in shared memory
-// first (kept as a cross-check of the MN-major descriptor path).
+// One CTA per (question, head) handles BOTH 128-query tiles of the sequence (<= 256 rows), so K and V are
+// fetched once.  The whole K and V of a head sit in shared memory - no online-softmax rescaling:
+//   warp 0      TMA: Q tile 0, Q tile 1, K, V (128B-swizzled boxes of the packed q|k|v activations)
+//   warp 1      tcgen05.mma  S0 = Q0 K^T, S1 = Q1 K^T (two 256-column TMEM accumulators), later O0 = P0 V, O1 = P1 V
+//   warps 2-5   softmax group of tile 0, warps 6-9 softmax group of tile 1 - one query row per thread:
+//               tcgen05.ld S, masked softmax in fp32 (exp2), P -> smem as the bf16 K-major A operand of the
+//               second MMA, then O / rowsum -> bf16 global
+// The two groups run concurrently on different scheduler partitions, and tile 0's P.V overlaps tile 1's
+// softmax.  V is consumed directly as an MN-major B operand (no transpose).  P tiles reuse the shared memory of
+// K and Q once both score MMAs have retired.
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace b200vqa {
 namespace {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 constexpr int kKeysMax = 256;
 
 template <int DH>
 struct AttnSmem {
   static constexpr int kPanels = DH / 64;
-  static constexpr int kQ = 128 * DH * 2;                 // 16 / 32 KB
-  static constexpr int kKP = 65536;                        // K (256 x DH) aliased later by P (128 x 256)
-  static constexpr int kV = kKeysMax * DH * 2;             // 32 / 64 KB
-  static constexpr int kOffQ = 0;
-  static constexpr int kOffKP = kQ;
-  static constexpr int kOffV = kOffKP + kKP;
-  static constexpr int kOffVt = kOffV + kV;                // only used by v_mode 1
-  static constexpr int kBarOffNoVt = kOffVt;
-  static constexpr int kBarOffVt = kOffVt + kV;
-  static constexpr int bytes(bool vt) { return (vt ? kBarOffVt : kBarOffNoVt) + 128; }
+  static constexpr int kQ = 128 * DH * 2;       // one query tile: 16 / 32 KB
+  static constexpr int kK = kKeysMax * DH * 2;  // 32 / 64 KB
+  static constexpr int kV = kK;
+  static constexpr int kP = 128 * kKeysMax * 2;  // 64 KB per probability tile
+  // dh = 64 : region A = [K | Q0 | Q1] (64 KB, later P0), region B = P1 (64 KB), V (32 KB)          -> 160 KB
+  // dh = 128: region A = K (64 KB, later P0), region B = [Q0 | Q1] (64 KB, later P1), V (64 KB)     -> 192 KB
+  static constexpr int kOffK = 0;
+  static constexpr int kOffQ0 = (DH == 64) ? kK : kP;
+  static constexpr int kOffQ1 = kOffQ0 + kQ;
+  static constexpr int kOffP0 = 0;
+  static constexpr int kOffP1 = kP;
+  static constexpr int kOffV = 2 * kP;
+  static constexpr int kOffBar = kOffV + kV;
+  static constexpr int kBytes = kOffBar + 128;
 };
 
-// dh = 64 needs 112 KB of shared memory and 256 TMEM columns per CTA: two CTAs share an SM, so one CTA's
-// softmax (CUDA cores) overlaps the other's TMA loads and tensor-core work.
 template <int DH>
-__global__ void __launch_bounds__(kAttnThreads, DH == 64 ? 2 : 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const EncAttnParams p) {
   using L = AttnSmem<DH>;
   constexpr int kPanels = L::kPanels;
 
-  const int mt = blockIdx.x & 1;
-  const int h = (blockIdx.x >> 1) % p.nhead;
-  const int b = (blockIdx.x >> 1) / p.nhead;
-  const int len = p.lens ? p.lens[b] : p.const_len;
+  const int h = blockIdx.x % p.nhead;
+  const int b = blockIdx.x / p.nhead;
+  int len = p.lens ? p.lens[b] : p.const_len;
+  len = len < 1 ? 1 : (len > kKeysMax ? kKeysMax : len);
+  const bool two = len > 128;  // the second query tile holds valid rows
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const size_t row0 = size_t(b) * kLP + mt * 128;
-
-  if (mt * 128 >= len) {
-    // a tile that holds only padding rows: keep them finite (they are masked as keys downstream)
-    for (int i = threadIdx.x; i < 128 * DH / 8; i += kAttnThreads) {
-      const int r = i / (DH / 8), c = i % (DH / 8);
-      reinterpret_cast<uint4*>(p.out + (row0 + r) * kD + h * DH)[c] = make_uint4(0, 0, 0, 0);
-    }
-    return;
-  }
+  const size_t row0 = size_t(b) * kLP;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem + L::kOffQ;
-  uint8_t* sK = smem + L::kOffKP;
-  uint8_t* sP = smem + L::kOffKP;
+  uint8_t* sK = smem + L::kOffK;
+  uint8_t* sQ[2] = {smem + L::kOffQ0, smem + L::kOffQ1};
+  uint8_t* sP[2] = {smem + L::kOffP0, smem + L::kOffP1};
   uint8_t* sV = smem + L::kOffV;
-  uint8_t* sVt = smem + L::kOffVt;
-  const bool use_vt = p.v_mode == 1;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (use_vt ? L::kBarOffVt : L::kBarOffNoVt));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_s = bars + 2;  // [2] score accumulator of tile t complete
+  uint64_t* bar_p = bars + 4;  // [2] P of tile t written (128 arrivals)
+  uint64_t* bar_o = bars + 6;  // [2] output accumulator of tile t complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int keys16 = (len + 15) & ~15;  // keys processed by the tensor core (multiple of the UMMA K / N step)
 
@@ -85,12 +79,14 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tma_prefetch_desc(&tm_kv);
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_s[t], 1);
+      mbar_init(&bar_p[t], 128);
+      mbar_init(&bar_o[t], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -98,134 +94,128 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_qk, L::kQ + kKeysMax * DH * 2);
+      mbar_expect_tx(bar_qk, 2 * L::kQ + L::kK);
 #pragma unroll
       for (int pn = 0; pn < kPanels; ++pn) {
-        tma_load_2d(&tm_q, bar_qk, sQ + pn * 16384, h * DH + pn * 64, int(row0));
-        tma_load_2d(&tm_kv, bar_qk, sK + pn * 32768, kD + h * DH + pn * 64, b * kLP);
+        tma_load_2d(&tm_kv, bar_qk, sK + pn * 32768, kD + h * DH + pn * 64, int(row0));
+        tma_load_2d(&tm_q, bar_qk, sQ[0] + pn * 16384, h * DH + pn * 64, int(row0));
+        tma_load_2d(&tm_q, bar_qk, sQ[1] + pn * 16384, h * DH + pn * 64, int(row0) + 128);
       }
       mbar_expect_tx(bar_v, L::kV);
 #pragma unroll
       for (int pn = 0; pn < kPanels; ++pn)
-        tma_load_2d(&tm_kv, bar_v, sV + pn * 32768, 2 * kD + h * DH + pn * 64, b * kLP);
+        tma_load_2d(&tm_kv, bar_v, sV + pn * 32768, 2 * kD + h * DH + pn * 64, int(row0));
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---- S = Q K^T : M=128, N=keys16, K=DH
+      // ---- S_t = Q_t K^T : M=128, N=keys16, K=DH
       mbar_wait(bar_qk, 0);
       tc_fence_after_sync();
       const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
+      for (int t = 0; t < 2; ++t) {
+        if (t == 0 || two) {
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k) {
-        const uint32_t qa = smem_u32(sQ) + (k / 4) * 16384 + (k % 4) * 32;
-        const uint32_t ka = smem_u32(sK) + (k / 4) * 32768 + (k % 4) * 32;
-        umma_bf16(tmem_base, make_smem_desc_sw128(qa, 16, 1024), make_smem_desc_sw128(ka, 16, 1024), idesc_s,
-                  k != 0);
+          for (int k = 0; k < DH / 16; ++k) {
+            const uint32_t qa = smem_u32(sQ[t]) + (k / 4) * 16384 + (k % 4) * 32;
+            const uint32_t ka = smem_u32(sK) + (k / 4) * 32768 + (k % 4) * 32;
+            umma_bf16(tmem_base + t * 256, make_smem_desc_sw128(qa, 16, 1024), make_smem_desc_sw128(ka, 16, 1024),
+                      idesc_s, k != 0);
+          }
+        }
+        umma_commit(&bar_s[t]);  // bar_s[1] also tells the softmax groups that K and Q are no longer read
       }
-      umma_commit(bar_s);
-
-      // ---- O = P V : M=128, N=DH, K=keys16
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after_sync();
+      // ---- O_t = P_t V : M=128, N=DH, K=keys16   (V is the MN-major B operand)
+      const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
       const int nkk = keys16 / 16;
-      if (!use_vt) {
-        const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);  // B (= V) is MN-major
+      mbar_wait(bar_v, 0);
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !two) break;
+        mbar_wait(&bar_p[t], 0);
+        tc_fence_after_sync();
         for (int kk = 0; kk < nkk; ++kk) {
-          const uint32_t pa = smem_u32(sP) + (kk / 4) * 16384 + (kk % 4) * 32;
+          const uint32_t pa = smem_u32(sP[t]) + (kk / 4) * 16384 + (kk % 4) * 32;
           const uint32_t va = smem_u32(sV) + kk * 2048;  // 16 key rows of 128 B
-          umma_bf16(tmem_base, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 32768, 1024), idesc_o,
-                    kk != 0);
+          umma_bf16(tmem_base + t * 256, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 32768, 1024),
+                    idesc_o, kk != 0);
         }
-      } else {
-        const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 0);
-        for (int kk = 0; kk < nkk; ++kk) {
-          const uint32_t pa = smem_u32(sP) + (kk / 4) * 16384 + (kk % 4) * 32;
-          const uint32_t va = smem_u32(sVt) + (kk / 4) * (DH * 128) + (kk % 4) * 32;
-          umma_bf16(tmem_base, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 16, 1024), idesc_o,
-                    kk != 0);
-        }
+        umma_commit(&bar_o[t]);
       }
-      umma_commit(bar_o);
     }
   } else {
-    const int quarter = warp & 3;
+    const int t = (warp - 2) >> 2;   // query tile of this softmax group
+    const int quarter = warp & 3;    // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
-    const int tid = (warp - 2) * 32 + lane;
-    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(t * 256);
     const float sl2 = p.scale * 1.4426950408889634f;
+    __nv_bfloat16* orow = p.out + (row0 + t * 128 + r) * kD + h * DH;
 
-    if (use_vt) {
-      // V [key][d] (TMA swizzled) -> V^T [d][key] K-major swizzled, element-wise (cross-check path only)
-      mbar_wait(bar_v, 0);
-      for (int i = tid; i < kKeysMax * DH; i += 128) {
-        const int k = i / DH, d = i % DH;
-        const uint32_t src = (d / 64) * 32768 + k * 128 + ((((d % 64) / 8) ^ (k & 7)) << 4) + (d & 7) * 2;
-        const uint32_t dst = (k / 64) * (DH * 128) + d * 128 + ((((k % 64) / 8) ^ (d & 7)) << 4) + (k & 7) * 2;
-        *reinterpret_cast<uint16_t*>(sVt + dst) = *reinterpret_cast<const uint16_t*>(sV + src);
+    if (t == 1 && !two) {
+      // a tile that holds only padding rows: keep them finite (they are masked as keys downstream)
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0, 0, 0, 0);
+    } else {
+      mbar_wait(&bar_s[t], 0);
+      __syncwarp();
+      tc_fence_after_sync();
+      const int nchunks = (len + 31) / 32;
+
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
-    }
-
-    mbar_wait(bar_s, 0);
-    __syncwarp();
-    tc_fence_after_sync();
-    const int nchunks = (len + 31) / 32;
-
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c * 32, v);
-      tmem_ld_wait();
+      // P_t overwrites K / Q: both score MMAs must have retired
+      if (t == 0) mbar_wait(&bar_s[1], 0);
+      const float mxs = mx * sl2;
+      float sum = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    const float mxs = mx * sl2;
-    float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c * 32, v);
-      tmem_ld_wait();
-      uint32_t o[16];
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = (c * 32 + j < len) ? exp2f(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
+          const float p1 = (c * 32 + j + 1 < len) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - mxs) : 0.f;
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          const float2 pr = __bfloat1622float2(pb);
+          sum += pr.x + pr.y;  // normalise by what the tensor core will actually sum
+          o[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        }
+        uint8_t* prow = sP[t] + (c >> 1) * 16384 + r * 128;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float p0 = (c * 32 + j < len) ? exp2f(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
-        float p1 = (c * 32 + j + 1 < len) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - mxs) : 0.f;
-        const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-        const float2 pr = __bfloat1622float2(pb);
-        sum += pr.x + pr.y;
-        o[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
       }
-      uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = (c & 1) * 4 + q;
-        *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
-            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      }
-    }
-    // keys in [32*nchunks, keys16) cannot exist (keys16 <= 32*nchunks); P is complete for the MMA
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    mbar_arrive(bar_p);
+      // keys in [32*nchunks, keys16) cannot exist (keys16 <= 32*nchunks); P is complete for the MMA
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_p[t]);
 
-    mbar_wait(bar_o, 0);
-    __syncwarp();
-    tc_fence_after_sync();
-    const float inv = 1.f / sum;
-    __nv_bfloat16* orow = p.out + (row0 + r) * kD + h * DH;
+      mbar_wait(&bar_o[t], 0);
+      __syncwarp();
+      tc_fence_after_sync();
+      const float inv = 1.f / sum;
 #pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c * 32, v);
-      tmem_ld_wait();
-      uint32_t o[16];
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2)
-        o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-      uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+        for (int j = 0; j < 32; j += 2)
+          o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
     }
   }
 
@@ -234,7 +224,7 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 1) {
     __syncwarp();
     tc_fence_after_sync();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -243,14 +233,13 @@ cudaError_t launch_dh(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const E
                       cudaStream_t stream) {
   using L = AttnSmem<DH>;
   auto kfn = enc_attention_kernel<DH>;
-  static int smem_set = 0;
-  const int bytes = L::bytes(p.v_mode == 1);
-  if (smem_set < bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
     if (e != cudaSuccess) return e;
-    smem_set = bytes;
+    attr_done = true;
   }
-  kfn<<<p.B * p.nhead * 2, kAttnThreads, bytes, stream>>>(tm_q, tm_kv, p);
+  kfn<<<p.B * p.nhead, kAttnThreads, L::kBytes, stream>>>(tm_q, tm_kv, p);
   return cudaGetLastError();
 }
 

@@ -203,31 +203,6 @@ struct RowAttnParams {
 };
 cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream);
 
-// Output head for decode position t: (optional final LayerNorm) -> Linear(kD, V) fp32 -> argmax (lowest index
-// wins ties, like torch.max / torch.argmax) -> tok[b, t+1]; next-step input x = emb[next] + pe[t+1] where next =
-// forced token if given.
-struct DecHeadParams {
-  int B = 0, V = 0, t = 0;
-  bool pdl = false;
-  const float* x_f32 = nullptr;       // [B,kD] fp32 output of the last decoder layer's norm3
-  const float* fn_gamma = nullptr;    // final decoder norm (FA) or null
-  const float* fn_beta = nullptr;
-  float eps = 1e-5f;
-  const float* w_t = nullptr;         // [kD, V] fp32 (transposed head weight)
-  const float* bias = nullptr;        // [V]
-  int64_t* tok = nullptr;             // [B, tok_ld]; argmax written to column t+1
-  int tok_ld = 0;
-  float* logits = nullptr;            // optional [B, logits_T, V]; row t
-  int logits_T = 0;
-  const int64_t* forced = nullptr;    // optional teacher-forcing tokens; position t+1 is fed forced[b*forced_ld + t]
-  int forced_ld = 0;
-  const float* emb = nullptr;         // decoder embedding for the next input
-  int vocab = 0;
-  const float* pe_next = nullptr;     // pe row t+1 (null on the last step)
-  __nv_bfloat16* x_next = nullptr;    // [B,kD]
-};
-cudaError_t launch_dec_head(const DecHeadParams& p, cudaStream_t stream);
-
 // tok[B, tok_ld] -> caller layout.
 //   out_i64 : out[b*out_ld + j] = tok[b, src_col0 + j], j < n_cols                       (IQAP programs, FA `ys`)
 //   out_i32 : FA step cache row: out[b*out_ld + j] = (j == 0 || !forced) ? tok[b, j] : forced[b*forced_ld + j-1],

@@ -223,7 +223,7 @@ class VQAModel(nn.Module):
         return programs
 
     @torch.no_grad()
-    def forward_host(self, image_features_cpu, questions_cpu, chunk=128):
+    def forward_host(self, image_features_cpu, questions_cpu, chunk=512):
         """End-to-end call with HOST tensors (pinned for full PCIe speed): upload, compute and download are
         pipelined inside the library; returns CPU tensors.  This is what bench.py times as `e2e`."""
         h = self._native()

@@ -6,6 +6,7 @@ test-suite.  Every rank must call the collectives in the same order.
 """
 from __future__ import annotations
 
+import datetime
 import os
 from typing import Sequence
 
@@ -54,7 +55,9 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
         if backend == "nccl":
             torch.cuda.set_device(local)
             kwargs["device_id"] = torch.device("cuda", local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+        # a rank that falls out of step must fail fast, not hold N GPUs for the default 10-minute watchdog
+        timeout = datetime.timedelta(seconds=int(os.environ.get("B200VQA_DIST_TIMEOUT_S", "120")))
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=timeout, **kwargs)
     return rank, local, world
 
 

@@ -51,7 +51,7 @@ def mha(sd, prefix, x_q, x_kv, nhead, attn_mask=None, key_len=None):
     if attn_mask is not None:
         s = s + attn_mask
     if key_len is not None:
-        dead = torch.arange(Lk)[None, :] >= key_len[:, None]
+        dead = torch.arange(Lk, device=s.device)[None, :] >= key_len[:, None]
         s = s.masked_fill(dead[:, None, None, :], float("-inf"))
     o = torch.softmax(s, dim=-1) @ v
     o = o.transpose(1, 2).reshape(B, Lq, d)
@@ -73,13 +73,13 @@ def encoder_layer(sd, prefix, x, nhead, key_len=None):
     return layer_norm(sd, prefix + "norm2.", x + ffn(sd, prefix, x))
 
 
-def causal_mask(n):
-    return torch.full((n, n), float("-inf")).triu(1)
+def causal_mask(n, device=None):
+    return torch.full((n, n), float("-inf"), device=device).triu(1)
 
 
 def decoder_layer(sd, prefix, x, memory, nhead, mem_len=None):
     """Post-norm TransformerDecoderLayer over the whole prefix x (B, t, d) with a causal mask."""
-    x = layer_norm(sd, prefix + "norm1.", x + mha(sd, prefix + "self_attn.", x, x, nhead, causal_mask(x.shape[1])))
+    x = layer_norm(sd, prefix + "norm1.", x + mha(sd, prefix + "self_attn.", x, x, nhead, causal_mask(x.shape[1], x.device)))
     x = layer_norm(sd, prefix + "norm2.", x + mha(sd, prefix + "multihead_attn.", x, memory, nhead, key_len=mem_len))
     return layer_norm(sd, prefix + "norm3.", x + ffn(sd, prefix, x))
 
@@ -114,7 +114,7 @@ class _CachedDecoder:
         qh = q.view(B, 1, self.nhead, self.dh).transpose(1, 2) * (1.0 / math.sqrt(self.dh))
         s = qh @ k.transpose(-1, -2)
         if key_len is not None:
-            dead = torch.arange(k.shape[2])[None, :] >= key_len[:, None]
+            dead = torch.arange(k.shape[2], device=k.device)[None, :] >= key_len[:, None]
             s = s.masked_fill(dead[:, None, None, :], float("-inf"))
         return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, 1, self.d)
 
@@ -167,7 +167,7 @@ def iqap_decode(sd, memory, T=27, start_token=1, nhead=4, forced=None, recompute
     fed forced[:, t] instead of the argmax (teacher forcing); tokens still hold the argmax."""
     B = memory.shape[0]
     emb, pe = sd["program_decoder_embedding.weight"], sd["pos_decoder.pe"][:, 0]
-    prefix = torch.full((B, 1), start_token, dtype=torch.long)                               # IQAP:205
+    prefix = torch.full((B, 1), start_token, dtype=torch.long, device=memory.device)         # IQAP:205
     dec = None if recompute else _CachedDecoder(sd, "transformer_decoder.layers.", memory, nhead)
     n_layers = count_layers(sd, "transformer_decoder.layers.")
     toks, logits = [], []
@@ -242,7 +242,7 @@ def fa_greedy_decode(sd, image_features, src_text, start_token, max_len, nhead, 
     per-question src_len (the reference is batch-1 and never pads, FA:136)."""
     memory, key_len = fa_encode(sd, image_features.float(), src_text.long(), nhead, src_len)
     B = memory.shape[0]
-    ys = torch.full((B, 1), start_token, dtype=torch.long)                                   # FA:136
+    ys = torch.full((B, 1), start_token, dtype=torch.long, device=memory.device)             # FA:136
     fed = ys.clone()
     emb, pe = sd["text_embedding.weight"], sd["pos_decoder.pe"][0]
     dec = None if recompute else _CachedDecoder(sd, "transformer.decoder.layers.", memory, nhead, key_len)
