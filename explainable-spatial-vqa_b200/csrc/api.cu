@@ -80,11 +80,11 @@ using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint3
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
   kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFinalLn,
-  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
+  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
 };
 const char* const kTagNames[kNumTags] = {
     "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
-    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_step_gemms", "dec_ffn_split", "dec_self_attention",
+    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_proj_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
     "dec_cross_attention", "dec_head_argmax", "misc"};
 
 struct ProfRec {
@@ -125,7 +125,7 @@ struct b200vqa_handle {
   bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
-  int decode_branches = 4;            // concurrent question ranges inside the decode graph
+  int decode_branches = 8;            // concurrent question ranges inside the decode graph
   cudaStream_t br_stream[7] = {};
   cudaEvent_t br_done[7] = {};
   cudaEvent_t br_fork = nullptr;
@@ -597,8 +597,9 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       sp.pdl = true;
       h->cur_tag = kTagDecSelfAttn;
       LAUNCH_OK(h, launch_row_attn(sp, s));
-      h->cur_tag = kTagDecGemm;
+      h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s));
+      h->cur_tag = kTagDecGemm;
       RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
       RowAttnParams cp;
       cp.B = B;
@@ -615,7 +616,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       cp.pdl = true;
       h->cur_tag = kTagDecCrossAttn;
       LAUNCH_OK(h, launch_row_attn(cp, s));
-      h->cur_tag = kTagDecGemm;
+      h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s));
       {
         // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
