@@ -234,13 +234,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * BN);
 
       if constexpr (EPI == kEpiBias || EPI == kEpiBiasRelu) {
-#pragma unroll 1
+        // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
+        uint32_t rbuf[2][32];
+        tmem_ld32(taddr + half * 32, rbuf[0]);
+#pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
           const int c = half + 2 * i;
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
+          uint32_t(&r)[32] = rbuf[i & 1];
           tmem_ld_wait();
-          if (i == kMyChunks - 1) {  // all TMEM reads of this stage are done -> hand it back to the MMA warp
+          if (i + 1 < kMyChunks) {
+            tmem_ld32(taddr + (c + 2) * 32, rbuf[(i + 1) & 1]);
+          } else {  // all TMEM reads of this stage are done -> hand it back to the MMA warp
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);

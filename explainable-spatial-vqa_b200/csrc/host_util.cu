@@ -86,18 +86,20 @@ static int encode_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t
 }
 
 int require_sm100(int device, int* num_sms) {
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  int major = 0, minor = 0, sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
-    set_error("cudaGetDeviceProperties(%d) failed: %s", device, cudaGetErrorString(e));
+    set_error("cudaDeviceGetAttribute(%d) failed: %s", device, cudaGetErrorString(e));
     return B200VQA_ERR_CUDA;
   }
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; libb200vqa is built for sm_100a (B200) only and has no other path", device,
-              prop.major, prop.minor);
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libb200vqa is built for sm_100a (B200) only and has no other path", device, major,
+              minor);
     return B200VQA_ERR_UNSUPPORTED_ARCH;
   }
-  if (num_sms) *num_sms = prop.multiProcessorCount;
+  if (num_sms) *num_sms = sms;
   return B200VQA_OK;
 }
 
