@@ -63,7 +63,7 @@ class DbgGemmArgs(C.Structure):
                 ("A", _vp), ("W", _vp), ("bias", _vp), ("out", _vp), ("ldc", C.c_int32),
                 ("residual", _vp), ("gamma", _vp), ("beta", _vp), ("out_f32", _vp),
                 ("rows_in", C.c_int32), ("rows_out", C.c_int32), ("row_off", C.c_int32), ("pe_off", C.c_int32),
-                ("pe", _vp)]
+                ("pe", _vp), ("clk", _vp)]
 
 
 # name -> (restype, argtypes); the not-gpu test-suite checks every symbol of include/b200vqa.h is here and exported

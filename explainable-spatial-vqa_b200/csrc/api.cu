@@ -615,7 +615,8 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       cp.out = dattn;
       cp.pdl = true;
       h->cur_tag = kTagDecCrossAttn;
-      LAUNCH_OK(h, launch_row_attn(cp, s));
+      static const bool skip_cross = getenv("B200VQA_DEBUG_SKIP_CROSS") != nullptr;  // timing experiments only
+      if (!skip_cross) LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s));
       {
@@ -1359,6 +1360,7 @@ B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   p.row_off = a->row_off;
   p.pe = a->pe;
   p.pe_off = a->pe_off;
+  p.dbg_clk = a->clk;
   B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, to, p, num_sms,
                               static_cast<cudaStream_t>(stream)));
   return B200VQA_OK;

@@ -26,9 +26,9 @@ struct FfnSmem {
   static constexpr int kOffX = 0;
   static constexpr int kOffW1 = kOffX + kX;
   static constexpr int kOffW2 = kOffW1 + kW1;
-  static constexpr int kOffH = kOffW2 + kW2;
-  static constexpr int kOffBar = kOffH + kH;
-  static constexpr int kBytes = kOffBar + 64;
+  static constexpr int kOffH = kOffX;  // H is written after the first GEMM has retired: it reuses X's shared memory
+  static constexpr int kOffBar = kOffW2 + kW2;
+  static constexpr int kBytes = kOffBar + 64;  // 192 KB: leaves room for row-attention blocks of other branches
 };
 
 __global__ void __launch_bounds__(kFfnThreads, 1)

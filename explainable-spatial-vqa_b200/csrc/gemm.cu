@@ -79,6 +79,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // optional clock64() stamps of CTA 0's pipeline stages (tools/microbench_gemm.py); a null pointer costs one branch
+  const bool dbg = p.dbg_clk != nullptr && blockIdx.x == 0;
+#define B200VQA_STAMP(i) \
+  if (dbg) p.dbg_clk[i] = clock64()
+  if (threadIdx.x == 0) B200VQA_STAMP(0);
 
   constexpr int elem_bytes = TF32 ? 4 : 2;
   constexpr int bk = kKBytes / elem_bytes;           // elements of K per k-block
@@ -117,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) B200VQA_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -134,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         wphase = 1;
       }
       pdl_wait();  // A (and everything the epilogue reads / overwrites) belongs to the previous kernel until here
+      B200VQA_STAMP(2);
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int nt = tile / tiles_m;
         const int m0 = (tile - nt * tiles_m) * kBM;
@@ -183,6 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
+          if (kb == 0) B200VQA_STAMP(4);
+          if (kb == num_kb - 1) B200VQA_STAMP(5);
           uint32_t sa, sb;
           if (wstat) {
             sa = smem_u32(sAring + stage * L::kStageA);
@@ -231,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(&acc_full[as], aphase);
       __syncwarp();
       tc_fence_after_sync();
+      if (ew == 0 && lane == 0) B200VQA_STAMP(6);
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * BN);
 
       if constexpr (EPI == kEpiBias || EPI == kEpiBiasRelu) {
@@ -463,7 +473,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
       if (++as == kAccStages) { as = 0; aphase ^= 1; }
     }
+    if (ew == 0 && lane == 0) B200VQA_STAMP(7);
     if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the bulk stores reading it
+    if (ew == 0 && lane == 0) B200VQA_STAMP(8);
   }
 
   tc_fence_before_sync();
@@ -473,6 +485,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tc_fence_after_sync();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+  if (threadIdx.x == 0) B200VQA_STAMP(9);
+#undef B200VQA_STAMP
 }
 
 template <int BN, int EPI, bool TF32>

@@ -49,6 +49,7 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M = 0, N = 0, K = 0;
   bool pdl = false;                  // launch with programmatic dependent launch (decode chain)
+  long long* dbg_clk = nullptr;      // optional: CTA 0 writes clock64() stamps of its pipeline stages (tools/ only)
   const float* bias = nullptr;       // [N] fp32 (may be null)
   __nv_bfloat16* out = nullptr;      // bf16 output
   int ldc = 0;                       // output leading dimension (elements)

@@ -238,6 +238,7 @@ typedef struct b200vqa_dbg_gemm_args {
   float* out_f32;
   int32_t rows_in, rows_out, row_off, pe_off;
   const float* pe;
+  long long* clk; /* optional device int64[16]: clock64() stamps of CTA 0's pipeline stages (tools/microbench_gemm.py) */
 } b200vqa_dbg_gemm_args;
 B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* args, void* stream);
 B200VQA_API int b200vqa_dbg_gemm_check(int a_is_f32, const void* A, const void* W, const float* bias, float* out, int M, int N,

@@ -31,9 +31,22 @@ def run(M, N, K, epi, bn, iters=200):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
     print(f"M={M:7d} N={N:5d} K={K:5d} epi={epi} bn={bn:3d}: {us:8.2f} us  {2*M*N*K/us/1e6:8.1f} TFLOP/s")
+    if M <= 1024:
+        clk = torch.zeros(16, dtype=torch.int64, device="cuda")
+        a.clk = clk.data_ptr()
+        for _ in range(3):
+            lib.b200vqa_dbg_gemm(C.byref(a), s)
+        torch.cuda.synchronize()
+        c = clk.cpu().tolist()
+        names = ["entry", "setup done", "pdl_wait done", "W landed", "A[0] landed", "A[last] landed", "acc ready (epi)",
+                 "epi stores issued", "stores drained", "exit"]
+        print("   stage cycles since entry:", ", ".join(f"{n}={c[i] - c[0]}" for i, n in enumerate(names) if c[i]))
 
 if __name__ == "__main__":
-    for cfg in [(1024, 256, 256, 2, 256), (1024, 256, 256, 0, 256), (1024, 256, 256, 0, 64), (1024, 768, 256, 0, 64),
-                (128, 256, 256, 2, 256), (128, 256, 256, 0, 64), (1024, 256, 2048, 2, 256),
-                (262144, 2048, 256, 1, 256), (262144, 256, 2048, 2, 256), (262144, 768, 256, 0, 256), (262144, 256, 256, 2, 256)]:
+    cfgs = [(1024, 256, 256, 2, 256), (1024, 256, 256, 0, 256), (1024, 256, 256, 0, 64), (1024, 768, 256, 0, 64),
+            (128, 256, 256, 2, 256), (128, 256, 256, 0, 64), (1024, 256, 2048, 2, 256),
+            (262144, 2048, 256, 1, 256), (262144, 256, 2048, 2, 256), (262144, 768, 256, 0, 256), (262144, 256, 256, 2, 256)]
+    if len(sys.argv) > 1:
+        cfgs = cfgs[: int(sys.argv[1])]
+    for cfg in cfgs:
         run(*cfg)
