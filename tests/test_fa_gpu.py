@@ -188,3 +188,40 @@ def test_nhead4_two_layers_long_text():
     ref_ys, ref_lg = orc.fa_greedy_decode(sd, img, src, 0, 20, 4, src_len=src_len.long())
     ys, lg = fa.greedy_decode(m, img, src, 0, 20, DEV, src_len=src_len, forced=ref_ys[:, 1:], want_logits=True)
     assert common.rel_err(lg, ref_lg) < common.LOGIT_REL_TOL
+
+
+def test_full_size_chain_properties(model):
+    """BASELINE config 3 shape at a size the test can afford (512 ragged programs, up to 25 steps): determinism,
+    split invariance, untouched rows beyond n_steps, and dependency gathering checked against the oracle on
+    sampled questions (teacher-forced so every step sees oracle-identical inputs)."""
+    B = 512
+    func, deps, n_steps = orc.fa_programs(B, seed=99)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randn(B, 1024, 14, 14, device="cuda", generator=g).relu_()
+    c1 = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+    c2 = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+    assert torch.equal(c1, c2)
+    lo = fa.run_inference_chain_batched(model, img[:200], func[:200], deps[:200], n_steps[:200], 0, 20)
+    hi = fa.run_inference_chain_batched(model, img[200:], func[200:], deps[200:], n_steps[200:], 0, 20)
+    assert torch.equal(torch.cat([lo, hi]), c1)
+    c1 = c1.cpu()
+    for b in range(B):
+        n = int(n_steps[b])
+        assert bool((c1[b, n:] == -1).all()) and bool((c1[b, :n, 0] == 0).all())
+        assert int(c1[b, :n].min()) >= 0 and int(c1[b, :n].max()) < 170
+    sd = cpu_sd(model)
+    rev = orc.fa_vocab(170)
+    rows = [3, 200, 511]
+    S = func.shape[1]
+    forced = torch.zeros(B, S, 19, dtype=torch.long)
+    ref_lg = {}
+    for r in rows:
+        c, lg = orc.fa_run_chain(sd, img[r:r + 1].cpu(), orc.chain_strings(func[r], deps[r], n_steps[r]), rev, 0, 20, 2)
+        for i in range(int(n_steps[r])):
+            forced[r, i] = torch.tensor(c[i][1:])
+        ref_lg[r] = torch.stack([lg[i] for i in range(int(n_steps[r]))])
+    cache, logits = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20, forced=forced, want_logits=True)
+    for r in rows:
+        n = int(n_steps[r])
+        assert torch.equal(cache[r, :n, 1:].cpu().long(), forced[r, :n])
+        assert common.rel_err(logits[r, :n], ref_lg[r]) < common.LOGIT_REL_TOL, r

@@ -129,3 +129,35 @@ def test_cpu_tensors_raise(model):
 def test_empty_batch(model):
     a, p = model(torch.zeros(0, 196, 1024, device="cuda"), torch.zeros(0, 46, dtype=torch.long, device="cuda"))
     assert a.shape == (0, 32) and p.shape == (0, 27)
+
+
+def test_full_size_batch_properties(model):
+    """BASELINE config 2 size (1024 questions): size-independent properties - determinism, invariance to how the
+    batch is split (no cross-question arithmetic, chunking and decode branches are invisible), and oracle parity
+    on sampled rows."""
+    B = 1024
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    img = torch.randn(B, 196, 1024, device="cuda", generator=g).relu_()
+    _, q = orc.iqap_inputs(B, seed=77, relu=False)
+    q = q.cuda()
+    a1, p1 = model(img, q)
+    a2, p2 = model(img, q)
+    assert torch.equal(a1, a2) and torch.equal(p1, p2)
+    a_lo, p_lo = model(img[:300], q[:300])
+    a_hi, p_hi = model(img[300:], q[300:])
+    assert torch.equal(torch.cat([a_lo, a_hi]), a1) and torch.equal(torch.cat([p_lo, p_hi]), p1)
+    rows = [0, 1, 127, 128, 511, 512, 777, 1023]
+    sd = cpu_sd(model)
+    ref = orc.iqap_forward(sd, img[rows].cpu(), q[rows].cpu())
+    ans, prog, logits, _ = model.forward_detailed(img, q, forced_programs=None, want_logits=True)
+    assert torch.equal(ans, a1)  # eager (logit-returning) and graph-replayed paths agree bitwise
+    assert common.rel_err(ans[rows], ref["answer"]) < common.LOGIT_REL_TOL
+    # free-running logits agree with the oracle up to each row's first token difference
+    for k, r in enumerate(rows):
+        same = (prog[r].cpu() == ref["programs"][k])
+        t_end = int((~same).float().argmax()) + 1 if not bool(same.all()) else 27
+        assert common.rel_err(logits[r, :t_end], ref["logits"][k, :t_end]) < common.LOGIT_REL_TOL, r
+        mg = common.margins(ref["logits"][k])
+        first_tie = next((t for t in range(27) if float(mg[t]) < 0.02), 27)
+        assert t_end >= first_tie, (r, t_end, first_tie)  # a difference may only start at a near-tie
+    assert int(p1.min()) >= 0 and int(p1.max()) < 44
