@@ -57,6 +57,12 @@ class ModelDesc(C.Structure):
                 ("answer_w0", _vp), ("answer_b0", _vp), ("answer_w1", _vp), ("answer_b1", _vp)]
 
 
+class LstmDesc(C.Structure):
+    _fields_ = [("vocab", C.c_int32), ("embedding_dim", C.c_int32), ("hidden_dim", C.c_int32), ("prog_vocab", C.c_int32),
+                ("embedding", _vp), ("enc_w_ih", _vp), ("enc_w_hh", _vp), ("enc_b_ih", _vp), ("enc_b_hh", _vp),
+                ("dec_w_ih", _vp), ("dec_w_hh", _vp), ("dec_b_ih", _vp), ("dec_b_hh", _vp), ("fc_w", _vp), ("fc_b", _vp)]
+
+
 class DbgGemmArgs(C.Structure):
     _fields_ = [("epilogue", C.c_int32), ("tf32", C.c_int32), ("block_n", C.c_int32),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
@@ -88,6 +94,10 @@ SIGNATURES = {
     "b200vqa_fa_forward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
     "b200vqa_fa_run_chain": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
                                        _vp, _vp]),
+    "b200vqa_lstm_create": (C.c_int, [C.POINTER(LstmDesc), C.c_int, C.POINTER(_vp)]),
+    "b200vqa_lstm_destroy": (None, [_vp]),
+    "b200vqa_lstm_launch_count": (C.c_uint64, [_vp]),
+    "b200vqa_lstm_generate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_dbg_gemm": (C.c_int, [C.POINTER(DbgGemmArgs), _vp]),
     "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

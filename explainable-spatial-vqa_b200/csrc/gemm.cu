@@ -103,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
-    if (EPI != kEpiBiasPeRemap && EPI != kEpiHead) tma_prefetch_desc(&tm_out);
+    if (EPI != kEpiBiasPeRemap && EPI != kEpiHead && EPI != kEpiLstm) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -318,6 +318,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
           }
         }
+      } else if constexpr (EPI == kEpiLstm) {
+        // chunks half, half+2, half+4, half+6 of this tile = gates i, f, g, o of 32 hidden units of this row
+        const int hidden = p.N >> 2;
+        float v[kMyChunks][32];
+        long long tokv = p.lstm_tokens ? p.lstm_tokens[size_t(valid ? row : 0) * p.lstm_tok_ld + p.lstm_tok_col]
+                                       : (long long)p.lstm_token_const;
+        tokv = tokv < 0 ? 0 : (tokv >= p.lstm_vocab ? p.lstm_vocab - 1 : tokv);
+        const float* trow = p.lstm_table + size_t(tokv) * p.N + n0;
+#pragma unroll
+        for (int i = 0; i < kMyChunks; ++i) {
+          const int c = half + 2 * i;
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = ldg4(trow + c * 32 + j);
+            v[i][j] = __uint_as_float(r[j]) + t4.x;
+            v[i][j + 1] = __uint_as_float(r[j + 1]) + t4.y;
+            v[i][j + 2] = __uint_as_float(r[j + 2]) + t4.z;
+            v[i][j + 3] = __uint_as_float(r[j + 3]) + t4.w;
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        if (valid) {
+          const int u0 = (n0 >> 2) + half * 32;  // first hidden unit of this thread
+          float* crow = p.lstm_c + size_t(row) * hidden + u0;
+          __nv_bfloat16* hrow = p.lstm_h + size_t(row) * hidden + u0;
+          float* hfrow = p.lstm_h_f32 ? p.lstm_h_f32 + size_t(row) * hidden + u0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float cprev[8], hn[8];
+            *reinterpret_cast<float4*>(cprev) = *reinterpret_cast<const float4*>(crow + j);
+            *reinterpret_cast<float4*>(cprev + 4) = *reinterpret_cast<const float4*>(crow + j + 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float ig = 1.f / (1.f + expf(-v[0][j + e]));
+              const float fg = 1.f / (1.f + expf(-v[1][j + e]));
+              const float gg = tanhf(v[2][j + e]);
+              const float og = 1.f / (1.f + expf(-v[3][j + e]));
+              const float cn = fg * cprev[e] + ig * gg;
+              cprev[e] = cn;
+              hn[e] = og * tanhf(cn);
+            }
+            *reinterpret_cast<float4*>(crow + j) = *reinterpret_cast<const float4*>(cprev);
+            *reinterpret_cast<float4*>(crow + j + 4) = *reinterpret_cast<const float4*>(cprev + 4);
+            *reinterpret_cast<uint4*>(hrow + j) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                                             pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
+            if (hfrow) {
+              *reinterpret_cast<float4*>(hfrow + j) = *reinterpret_cast<const float4*>(hn);
+              *reinterpret_cast<float4*>(hfrow + j + 4) = *reinterpret_cast<const float4*>(hn + 4);
+            }
+          }
+        }
       } else if constexpr (EPI == kEpiHead) {
         // logits of this warp's columns, running argmax in increasing column order (first maximum wins)
         float best = -INFINITY;
@@ -525,7 +581,8 @@ __global__ void gemm_check_kernel(const TA* __restrict__ A, const TA* __restrict
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                         const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.N % block_n != 0) return cudaErrorInvalidValue;
-  if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N || p.K != kD)) return cudaErrorInvalidValue;
+  if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N)) return cudaErrorInvalidValue;
+  if (epilogue == kEpiLstm && (block_n != 256 || p.N % 256 != 0)) return cudaErrorInvalidValue;
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \
@@ -539,6 +596,7 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
   B200VQA_GEMM_CASE(256, kEpiBiasResLN, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, true)
+  B200VQA_GEMM_CASE(256, kEpiLstm, false)
   B200VQA_GEMM_CASE(64, kEpiHead, true)
   B200VQA_GEMM_CASE(256, kEpiHead, true)
 #undef B200VQA_GEMM_CASE

@@ -42,8 +42,10 @@ enum GemmEpilogue : int {
   kEpiBiasRelu = 1,   // bf16 out = relu(acc + bias)
   kEpiBiasResLN = 2,  // bf16 out = LayerNorm(acc + bias + residual) * gamma + beta   (N == 256)
   kEpiBiasPeRemap = 3,// bf16 out[row'] = acc + bias + pe[p]; row' = item*rows_out + off + p
-  kEpiHead = 4        // vocabulary head of one decode position: logits = acc + bias (N = padded vocabulary), argmax ->
+  kEpiHead = 4,       // vocabulary head of one decode position: logits = acc + bias (N = padded vocabulary), argmax ->
                       // tok[row, t+1], next input x_next[row] = emb[next] + pe[t+1]   (IQAP:230-236, FA:142-145)
+  kEpiLstm = 5        // one LSTM time step of the program generator: gates = acc (h_prev . W_hh^T) + table[token]
+                      // (embedding . W_ih^T + biases, precomputed per vocabulary entry); c, h updated in the epilogue
 };
 
 struct GemmParams {
@@ -79,6 +81,15 @@ struct GemmParams {
   int vocab = 0;
   const float* pe_next = nullptr;    // pe row t+1, null on the last position
   __nv_bfloat16* x_next = nullptr;   // [M, 256]
+  // kEpiLstm (N = 4 * hidden; columns permuted so that an n-tile holds i|f|g|o of 64 hidden units, 64 columns each)
+  const float* lstm_table = nullptr;    // [vocab, N] fp32, same column permutation
+  const int64_t* lstm_tokens = nullptr; // token of row r = lstm_tokens[r * lstm_tok_ld + lstm_tok_col]; null -> lstm_token_const
+  int lstm_tok_ld = 0, lstm_tok_col = 0;
+  int lstm_token_const = 0;
+  int lstm_vocab = 0;
+  float* lstm_c = nullptr;              // [M, hidden] fp32 cell state, updated in place
+  __nv_bfloat16* lstm_h = nullptr;      // [M, hidden] bf16 new hidden state (the next step's A operand: ping-pong)
+  float* lstm_h_f32 = nullptr;          // optional fp32 copy (feeds the tf32 vocabulary head)
 };
 
 // A/W tensor maps: 2D, 128-byte swizzle, box = {128 B of K, 128 rows (A) | BN rows (W)}.

@@ -220,6 +220,42 @@ B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_b
                          const int32_t* h_active, float* opt_logits, const int64_t* opt_forced, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------- */
+/* LSTM program generator: question tokens -> program tokens                           */
+/* ---------------------------------------------------------------------------------------------------- */
+typedef struct b200vqa_lstm b200vqa_lstm;
+
+/* fp32 device pointers in torch's nn.LSTM / nn.Embedding / nn.Linear state-dict layout (gate order i|f|g|o). */
+typedef struct b200vqa_lstm_desc {
+  int32_t vocab;         /* embedding rows (question vocabulary; program tokens index the same table) */
+  int32_t embedding_dim; /* 256 */
+  int32_t hidden_dim;    /* 512 */
+  int32_t prog_vocab;    /* fc rows */
+  const float* embedding; /* [vocab, 256] */
+  const float* enc_w_ih;  /* encoder.weight_ih_l0 [2048, 256] */
+  const float* enc_w_hh;  /* encoder.weight_hh_l0 [2048, 512] */
+  const float* enc_b_ih;
+  const float* enc_b_hh;
+  const float* dec_w_ih;
+  const float* dec_w_hh;
+  const float* dec_b_ih;
+  const float* dec_b_hh;
+  const float* fc_w;      /* [prog_vocab, 512] */
+  const float* fc_b;
+} b200vqa_lstm_desc;
+
+/* Replaces Seq2SeqModel.__init__ + load_state_dict (code/run_model_lstm_qp.py:277-289). */
+B200VQA_API int b200vqa_lstm_create(const b200vqa_lstm_desc* desc, int device, b200vqa_lstm** out);
+B200VQA_API void b200vqa_lstm_destroy(b200vqa_lstm* h);
+B200VQA_API uint64_t b200vqa_lstm_launch_count(const b200vqa_lstm* h);
+/* Replaces Seq2SeqModel.forward (code/run_model_lstm_qp.py:291-319): questions [B, q_len] i64 -> programs
+ * [B, program_len] i64 (greedy).  opt_logits NULL or [B, program_len, prog_vocab] f32; opt_forced NULL or
+ * [B, program_len] i64: decoder step t+1 is fed opt_forced[b, t] (teacher forcing = the `program_targets` branch
+ * shifted by the start token).  Asynchronous on `stream`. */
+B200VQA_API int b200vqa_lstm_generate(b200vqa_lstm* h, const int64_t* questions, int q_len, int B, int program_len,
+                                      int start_token, int64_t* programs, float* opt_logits,
+                                      const int64_t* opt_forced, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------- */
 /* Kernel-level entry points used by the test-suite only (not part of the drop-in surface)               */
 /* ---------------------------------------------------------------------------------------------------- */
 typedef struct b200vqa_dbg_gemm_args {

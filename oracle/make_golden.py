@@ -110,9 +110,32 @@ def golden_fa():
     print("fa: chain final =", final)
 
 
+def golden_lstm():
+    import run_model_lstm_qp as ref_qp
+    from oracle import lstm_oracle
+    torch.manual_seed(0)
+    model = ref_qp.Seq2SeqModel(85, 256, 512, 44, 27, 1).eval()
+    q = lstm_oracle.questions(6, seed=4242)
+    captured = []
+    hook = model.fc.register_forward_hook(lambda m, i, o: captured.append(o.detach()[:, 0].clone()))
+    with torch.no_grad():
+        programs = model(q)
+    hook.remove()
+    logits = torch.stack(captured, dim=1)  # (B, 27, 44)
+    with torch.no_grad():
+        tgt = torch.cat([torch.ones(6, 1, dtype=torch.long), programs[:, :-1]], dim=1)
+        tf_logits = model(q, tgt)  # teacher-forced branch fed [<START>, p0..p25] reproduces the greedy logits
+    keys, sums, asums = pack_checksums(model.state_dict())
+    np.savez_compressed(os.path.join(OUT, "lstm_qp.npz"), torch_version=torch.__version__, sd_keys=keys, sd_sums=sums,
+                        sd_abs_sums=asums, questions=q.numpy(), programs=programs.numpy(), logits=logits.numpy(),
+                        tf_logits=tf_logits.numpy())
+    print("lstm: programs[0] =", programs[0].tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     golden_iqap()
     golden_fa()
+    golden_lstm()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
