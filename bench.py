@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the batched Program Executor inference path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload iqap|fa]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload iqap|fa|e2e]
 
 A "step" is one pass of the hot path over one batch of synthetic input on every GPU:
   iqap (default, BASELINE configs[1]): VQAModel.forward on 1024 questions per GPU = encoder + answer head +
        27 greedy program positions; 1 question = 27 program-steps.
   fa   (configs[2]): run_inference_chain_batched on 4096 questions per GPU with CLEVR-shaped ragged programs;
        1 chain element = 1 program-step.
+  e2e  (configs[3]): LSTM program generator decode on the questions + device program->chain glue + the FA executor
+       on 4096 questions per GPU (synthetic CLEVR-shaped prefix programs drive the executor: a random-init generator
+       does not emit valid programs; its decode is executed and timed all the same).
 `value` is whole-job program-steps/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the
 same metric through the public host-buffer call (pinned host inputs uploaded and results downloaded inside
 the timed region).  N > 1: one process per GPU under torchrun, questions sharded, no per-step collective in
@@ -157,8 +160,9 @@ def cpu_iqap(sample_b, repeats, recompute=True):
     return sample_b * T_PROG / best, best
 
 
-def cpu_fa(n_questions, recompute=True):
-    """program-steps/s of the oracle chain (batch-1 loop, the reference's only mode)."""
+def cpu_fa(n_questions, recompute=True, with_generator=False):
+    """program-steps/s of the oracle chain (batch-1 loop, the reference's only mode); `with_generator` adds the LSTM
+    program generator's decode of the same questions (config 4)."""
     from oracle import executor_oracle as orc
     from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
     torch.set_num_threads(os.cpu_count() or 1)
@@ -170,6 +174,13 @@ def cpu_fa(n_questions, recompute=True):
     rev = orc.fa_vocab(170)
     orc.fa_run_chain(sd, img[:1], orc.chain_strings(func[0], deps[0], 2), rev, 0, 20, 2, recompute=recompute)
     t0 = time.perf_counter()
+    if with_generator:
+        from oracle import lstm_oracle
+        from explainable_spatial_vqa_b200 import run_model_lstm_qp as qp
+        torch.manual_seed(1)
+        gsd = qp.Seq2SeqModel(85, 256, 512, 44, T_PROG, 1).eval().state_dict()
+        t0 = time.perf_counter()
+        lstm_oracle.generate(gsd, lstm_oracle.questions(n_questions))
     for b in range(n_questions):
         orc.fa_run_chain(sd, img[b:b + 1], orc.chain_strings(func[b], deps[b], n_steps[b]), rev, 0, 20, 2,
                          recompute=recompute)
@@ -223,7 +234,7 @@ def run_reference(args):
             v, dt = cpu_iqap(sample, 1)
             u = sample * T_PROG
         else:
-            v, dt = cpu_fa(sample)
+            v, dt = cpu_fa(sample, with_generator=args.workload == "e2e")
             u = v * dt
         if i >= args.warmup:
             times.append(dt)
@@ -251,6 +262,13 @@ def workload_config(args):
                 "batch_per_gpu": args.batch, "program_len": T_PROG,
                 "l2": "inputs are 822 MB of fp32 features per step (> 126 MB L2), activations 2.4 GB",
                 "gather": "per step: all_gather of answers + programs (NCCL) when n_gpus > 1"}
+    if args.workload == "e2e":
+        return {"workload": f"end to end: LSTM program generator (85/256/512/44, 46 -> 27 tokens) + device program->chain "
+                            f"glue + FA executor, batch {args.batch} questions per GPU, synthetic CLEVR-shaped prefix "
+                            "programs of 2..25 nodes drive the executor",
+                "batch_per_gpu": args.batch,
+                "l2": "per-step activations exceed L2 (4096 questions x 128 KB encoder rows)",
+                "gather": "per step: all_gather of the final-step tokens (NCCL) when n_gpus > 1"}
     return {"workload": f"FA executor (MultiModalTransformer V=170 nhead 2, 1+1 layers, ff 512), batch {args.batch} "
                         "questions per GPU, CLEVR-shaped ragged programs of 2..25 steps, 20 tokens per step",
             "batch_per_gpu": args.batch,
@@ -311,16 +329,35 @@ def run_ours(args):
         model = fa.MultiModalTransformer(170, 256, 2, 1, 1, 512, 0.1, 50, 196).eval().to(dev)
         g = torch.Generator(device=dev).manual_seed(4321 + rank)
         img = torch.randn(B, 1024, 14, 14, device=dev, generator=g).relu_()
-        func, deps, n_steps = orc.fa_programs(B, seed=4321 + rank)
-        func, deps, n_steps = func.to(dev), deps.to(dev), n_steps.to(dev)
+        generator = None
+        if args.workload == "e2e":
+            from explainable_spatial_vqa_b200 import run_model_lstm_qp as qp
+            from oracle import lstm_oracle
+            torch.manual_seed(1)
+            generator = qp.Seq2SeqModel(85, 256, 512, 44, T_PROG, 1).eval().to(dev)
+            questions = lstm_oracle.questions(B, seed=4242 + rank).to(dev)
+            synth_programs, node_counts = lstm_oracle.prefix_programs(B, seed=777 + rank)
+            synth_programs = synth_programs.to(dev)
+            arity, fmap = lstm_oracle.program_arity().to(dev), lstm_oracle.program_func_map().to(dev)
+            func, deps, n_steps = qp.programs_to_chain(synth_programs, arity, fmap)
+        else:
+            func, deps, n_steps = orc.fa_programs(B, seed=4321 + rank)
+            func, deps, n_steps = func.to(dev), deps.to(dev), n_steps.to(dev)
         units_per_step = int(n_steps.sum())
         counts = [B] * world
 
+        def chain():
+            if generator is None:
+                return fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+            generator(questions)  # greedy program decode, all on the device
+            f, d, n = qp.programs_to_chain(synth_programs, arity, fmap)  # device glue: prefix program -> chain
+            return fa.run_inference_chain_batched(model, img, f, d, n, 0, 20)
+
         def step_local():
-            return fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+            return chain()
 
         def step():
-            cache = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+            cache = chain()
             if world > 1:
                 last = cache[torch.arange(B, device=dev), (n_steps - 1).long()]
                 sharding.gather_varlen(last, counts)
@@ -330,12 +367,22 @@ def run_ours(args):
         img_host.copy_(img)
         f_h, d_h, n_h = func.cpu().pin_memory(), deps.cpu().pin_memory(), n_steps.cpu().pin_memory()
 
+        if generator is not None:
+            q_h, p_h = questions.cpu().pin_memory(), synth_programs.cpu().pin_memory()
+
         def step_e2e():
-            cache = fa.run_inference_chain_batched(model, img_host.to(dev, non_blocking=True), f_h.to(dev, non_blocking=True),
-                                                   d_h.to(dev, non_blocking=True), n_h.to(dev, non_blocking=True), 0, 20)
+            if generator is None:
+                cache = fa.run_inference_chain_batched(model, img_host.to(dev, non_blocking=True),
+                                                       f_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True),
+                                                       n_h.to(dev, non_blocking=True), 0, 20)
+            else:
+                generator(q_h.to(dev, non_blocking=True))
+                f, d, n = qp.programs_to_chain(p_h.to(dev, non_blocking=True), arity, fmap)
+                cache = fa.run_inference_chain_batched(model, img_host.to(dev, non_blocking=True), f, d, n, 0, 20)
             return cache.cpu()
 
-        h2d = img_host.numel() * 4 + f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4
+        h2d = img_host.numel() * 4 + (f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4 if generator is None
+                                      else q_h.numel() * 8 + p_h.numel() * 8)
         d2h = B * func.shape[1] * 20 * 4
 
     def barrier():
@@ -441,7 +488,7 @@ def run_ours(args):
             what = f"{sample} of the {B} questions, best of 2 ({dt:.1f} s each)"
         else:
             sample = args.cpu_sample or 4
-            v, dt = cpu_fa(sample)
+            v, dt = cpu_fa(sample, with_generator=args.workload == "e2e")
             what = f"{sample} of the {B} questions as a batch-1 loop ({dt:.1f} s)"
         cpu_baseline = {"value": v, "unit": "program-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                         "cpu": cpu_model_name(),
@@ -472,7 +519,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="iqap", choices=["iqap", "fa"])
+    ap.add_argument("--workload", default="iqap", choices=["iqap", "fa", "e2e"])
     ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
     ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=None)

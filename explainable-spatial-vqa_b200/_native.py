@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200vqa_lstm_destroy": (None, [_vp]),
     "b200vqa_lstm_launch_count": (C.c_uint64, [_vp]),
     "b200vqa_lstm_generate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "b200vqa_programs_to_chain": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_dbg_gemm": (C.c_int, [C.POINTER(DbgGemmArgs), _vp]),
     "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

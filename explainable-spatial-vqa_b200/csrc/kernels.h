@@ -254,6 +254,18 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+// programs [B,T] i64 (prefix order) -> func [B,S], deps [B,S,2], n_steps [B] (all int32) in execution order
+struct ProgToChainParams {
+  int B = 0, T = 0, S = 0, prog_vocab = 0;
+  const int64_t* programs = nullptr;
+  const int32_t* arity = nullptr;     // [prog_vocab]: inputs of each token (0 / 1 / 2), negative = end of program
+  const int32_t* func_map = nullptr;  // [prog_vocab]: chain function token of each program token
+  int32_t* func = nullptr;
+  int32_t* deps = nullptr;
+  int32_t* n_steps = nullptr;
+};
+cudaError_t launch_programs_to_chain(const ProgToChainParams& p, cudaStream_t stream);
+
 cudaError_t launch_delay(long long cycles, cudaStream_t stream);
 
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.

@@ -233,6 +233,27 @@ B200VQA_API void b200vqa_lstm_destroy(b200vqa_lstm* h) {
 
 B200VQA_API uint64_t b200vqa_lstm_launch_count(const b200vqa_lstm* h) { return h ? h->launches : 0; }
 
+B200VQA_API int b200vqa_programs_to_chain(const int64_t* programs, int B, int T, const int32_t* arity,
+                                          const int32_t* func_map, int prog_vocab, int S, int32_t* func, int32_t* deps,
+                                          int32_t* n_steps, void* stream) {
+  B200VQA_REQUIRE(B >= 0 && T >= 1 && T <= 64 && S >= 1 && prog_vocab >= 1, "shape out of range (B %d, T %d, S %d)", B, T, S);
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(programs && arity && func_map && func && deps && n_steps, "a required buffer is NULL");
+  ProgToChainParams p;
+  p.B = B;
+  p.T = T;
+  p.S = S;
+  p.prog_vocab = prog_vocab;
+  p.programs = programs;
+  p.arity = arity;
+  p.func_map = func_map;
+  p.func = func;
+  p.deps = deps;
+  p.n_steps = n_steps;
+  B200VQA_CUDA_OK(launch_programs_to_chain(p, static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
 B200VQA_API int b200vqa_lstm_generate(b200vqa_lstm* h, const int64_t* questions, int q_len, int B, int program_len,
                                       int start_token, int64_t* programs, float* opt_logits, const int64_t* opt_forced,
                                       void* stream) {

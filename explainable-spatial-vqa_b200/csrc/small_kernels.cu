@@ -246,6 +246,63 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+// Program -> chain glue on the device (reference preprocess_questions/utils_programs.py:100-156 `prefix_to_list`):
+// a program in PREFIX order becomes chain elements in execution order (= post-order: inputs before consumers, root
+// last, exactly tree_to_list's numbering) with dependency pointers.  One thread per question; malformed programs
+// (a terminator before the tree closes, more than S nodes) are truncated, never out of bounds.
+__global__ void programs_to_chain_kernel(const ProgToChainParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  constexpr int kMax = 64;
+  int st_node[kMax], st_rem[kMax], tokv[kMax], child[kMax][2], nchild[kMax];
+  int sp = 0, cnt = 0;
+  const int T = p.T < kMax ? p.T : kMax;
+  int32_t* func = p.func + size_t(b) * p.S;
+  int32_t* deps = p.deps + size_t(b) * p.S * 2;
+  auto emit = [&](int node) {
+    const int idx = cnt < p.S ? cnt : p.S - 1;  // truncated programs overwrite the last slot, never past it
+    func[idx] = p.func_map[tokv[node]];
+    deps[idx * 2] = nchild[node] > 0 ? child[node][0] : -1;
+    deps[idx * 2 + 1] = nchild[node] > 1 ? child[node][1] : -1;
+    if (cnt < p.S) ++cnt;
+    return idx;
+  };
+  for (int pos = 0; pos < T; ++pos) {
+    long long tok = p.programs[size_t(b) * p.T + pos];
+    if (tok < 0 || tok >= p.prog_vocab) break;
+    const int a = p.arity[tok];
+    if (a < 0) break;  // <NULL> / <START> / <END>: end of program
+    st_node[sp] = pos;
+    st_rem[sp] = a > 2 ? 2 : a;
+    tokv[pos] = int(tok);
+    nchild[pos] = 0;
+    ++sp;
+    while (sp > 0 && st_rem[sp - 1] == 0) {
+      const int node = st_node[--sp];
+      const int idx = emit(node);
+      if (sp > 0) {
+        const int parent = st_node[sp - 1];
+        if (nchild[parent] < 2) child[parent][nchild[parent]++] = idx;
+        --st_rem[sp - 1];
+      }
+    }
+    if (sp == 0) break;  // the tree is complete
+  }
+  while (sp > 0) {  // truncated program: close the open nodes with the inputs they have
+    const int node = st_node[--sp];
+    const int idx = emit(node);
+    if (sp > 0) {
+      const int parent = st_node[sp - 1];
+      if (nchild[parent] < 2) child[parent][nchild[parent]++] = idx;
+    }
+  }
+  for (int i = cnt; i < p.S; ++i) {
+    func[i] = 0;
+    deps[i * 2] = deps[i * 2 + 1] = -1;
+  }
+  p.n_steps[b] = cnt;
+}
+
 // Holds the stream busy for `cycles` SM clocks: lets the host enqueue a whole step behind it so that the
 // profiler's event timestamps see back-to-back kernels instead of host launch latency.
 __global__ void delay_kernel(long long cycles) {
@@ -296,6 +353,12 @@ cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* 
                                const float* w1, const float* b1, int classes, float* out, cudaStream_t stream) {
   if (hidden > 1024) return cudaErrorInvalidValue;
   answer_head_kernel<<<B, 256, 0, stream>>>(memory, w0_t, b0, hidden, w1, b1, classes, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_programs_to_chain(const ProgToChainParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  programs_to_chain_kernel<<<(p.B + 127) / 128, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _native as nat
 
-__all__ = ["Seq2SeqModel", "get_data_info", "prefix_program_to_deps"]
+__all__ = ["Seq2SeqModel", "get_data_info", "prefix_program_to_deps", "programs_to_chain"]
 
 
 class Seq2SeqModel(nn.Module):
@@ -158,3 +158,25 @@ def prefix_program_to_deps(arity):
 
     place(tree, n - 1)
     return order, deps
+
+
+@torch.no_grad()
+def programs_to_chain(programs, arity, func_map, max_steps=25):
+    """Device version of `prefix_program_to_deps` for a batch: programs (B, T) i64 CUDA tensor in prefix order,
+    arity / func_map (Vp,) i32 -> (func (B,S) i32, deps (B,S,2) i32, n_steps (B,) i32) ready for
+    `run_inference_chain_batched`.  No host round trip between the generator and the executor."""
+    if not programs.is_cuda:
+        raise nat.NativeError("programs must be a CUDA tensor (no CPU path)")
+    dev = programs.device
+    prog = programs.to(torch.int64).contiguous()
+    ar = arity.to(dev, torch.int32).contiguous()
+    fm = func_map.to(dev, torch.int32).contiguous()
+    B, T = prog.shape
+    func = torch.empty(B, max_steps, dtype=torch.int32, device=dev)
+    deps = torch.empty(B, max_steps, 2, dtype=torch.int32, device=dev)
+    n_steps = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().b200vqa_programs_to_chain(nat.ptr(prog), B, T, nat.ptr(ar), nat.ptr(fm), ar.numel(),
+                                                      int(max_steps), nat.ptr(func), nat.ptr(deps), nat.ptr(n_steps),
+                                                      nat.stream_ptr(dev)), "b200vqa_programs_to_chain")
+    return func, deps, n_steps

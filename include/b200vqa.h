@@ -255,6 +255,14 @@ B200VQA_API int b200vqa_lstm_generate(b200vqa_lstm* h, const int64_t* questions,
                                       int start_token, int64_t* programs, float* opt_logits,
                                       const int64_t* opt_forced, void* stream);
 
+/* Program -> chain glue (reference preprocess_questions/utils_programs.py:100-156, prefix_to_list): programs [B,T]
+ * i64 in PREFIX order -> chain arrays in execution order (inputs before consumers, root last): func [B,S] i32 =
+ * func_map[token], deps [B,S,2] i32 (-1 = none), n_steps [B] i32.  arity [prog_vocab] i32 gives each token's input
+ * count (0 / 1 / 2; negative ends the program).  All device pointers; feeds b200vqa_fa_run_chain directly. */
+B200VQA_API int b200vqa_programs_to_chain(const int64_t* programs, int B, int T, const int32_t* arity,
+                                          const int32_t* func_map, int prog_vocab, int S, int32_t* func,
+                                          int32_t* deps, int32_t* n_steps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Kernel-level entry points used by the test-suite only (not part of the drop-in surface)               */
 /* ---------------------------------------------------------------------------------------------------- */

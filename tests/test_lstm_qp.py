@@ -96,3 +96,25 @@ def test_gpu_decisive_head_free_running_exact():
         assert torch.equal(prog[b, :t_end], ref_prog[b, :t_end]), b
         exact += t_end
     assert exact >= 27, exact
+
+
+@pytest.mark.gpu
+def test_gpu_programs_to_chain_matches_host_glue():
+    progs, counts = lstm_oracle.prefix_programs(300, seed=5)
+    arity, fmap = lstm_oracle.program_arity(), lstm_oracle.program_func_map()
+    func, deps, n_steps = qp.programs_to_chain(progs.cuda(), arity, fmap, max_steps=25)
+    func, deps, n_steps = func.cpu(), deps.cpu(), n_steps.cpu()
+    assert torch.equal(n_steps.long(), counts)
+    for b in range(300):
+        n = int(counts[b])
+        toks = progs[b, :n].tolist()
+        order, ref_deps = qp.prefix_program_to_deps([int(arity[t]) for t in toks])
+        assert func[b, :n].tolist() == [int(fmap[toks[p]]) for p in order], b
+        assert deps[b, :n].tolist() == ref_deps, b
+        assert bool((deps[b, n:] == -1).all())
+        for i in range(n):
+            assert all(int(d) < i for d in deps[b, i]), (b, i)  # inputs always precede their consumer
+    # malformed programs never write out of bounds: no terminator / unknown ids / more nodes than max_steps
+    bad = torch.randint(0, 60, (64, 27))
+    f2, d2, n2 = qp.programs_to_chain(bad.cuda(), arity, fmap, max_steps=8)
+    assert int(n2.max()) <= 8 and int(n2.min()) >= 0 and int(d2.max()) < 8
