@@ -89,6 +89,7 @@ SIGNATURES = {
     "b200vqa_iqap_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "b200vqa_iqap_forward_host_async": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "b200vqa_fa_project_images": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "b200vqa_fa_step": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_fa_forward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
@@ -271,3 +272,49 @@ def check_layer_contract(layer, what: str) -> None:
 def weights_version(module: torch.nn.Module):
     """Changes whenever a parameter/buffer is modified in place or replaced (load_state_dict, .to(), .cuda())."""
     return tuple((id(t), t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class HandlePool:
+    """Per-module pool of native handles ("slots").  Slot 0 serves the plain reference-style calls on the caller's
+    stream.  Further slots each own a handle (packed weights, workspace, CUDA graphs) and a stream, so independent
+    batches can be in flight at once: the decode phase is a latency-bound chain of small kernels, and a second
+    batch's kernels fill the bubbles (`submit` / `drain` on the modules)."""
+
+    def __init__(self, module, desc_builder):
+        self._module = module
+        self._builder = desc_builder
+        self._handles = {}
+        self._versions = {}
+        self._streams = {}
+
+    def get(self, slot: int = 0) -> Handle:
+        module = self._module
+        version = weights_version(module)
+        dev = next(module.parameters()).device
+        h = self._handles.get(slot)
+        if h is not None and h.device != dev:
+            h.close()
+            h = None
+        if h is None:
+            h = Handle(self._builder, dev)
+            self._handles[slot] = h
+        elif self._versions.get(slot) != version:
+            h.refresh(self._builder)
+        self._versions[slot] = version
+        return h
+
+    def stream(self, slot: int) -> "torch.cuda.Stream":
+        dev = next(self._module.parameters()).device
+        st = self._streams.get(slot)
+        if st is None or st.device != dev:
+            st = torch.cuda.Stream(device=dev)
+            self._streams[slot] = st
+        return st
+
+    def drain(self):
+        """Makes the caller's current stream wait for every slot stream (results of all submits become usable)."""
+        for st in self._streams.values():
+            torch.cuda.current_stream(st.device).wait_stream(st)
+
+    def launch_count(self) -> int:
+        return sum(h.launch_count() for h in self._handles.values())

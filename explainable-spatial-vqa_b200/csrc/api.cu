@@ -1078,8 +1078,8 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
   return B200VQA_OK;
 }
 
-B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
-                              float* h_answer, int64_t* h_programs, int chunk, void* stream) {
+static int iqap_forward_host_impl(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
+                                  float* h_answer, int64_t* h_programs, int chunk, void* stream, bool sync) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
   B200VQA_REQUIRE(B >= 0, "negative batch");
@@ -1146,8 +1146,19 @@ B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img,
   B200VQA_CUDA_OK(cudaMemcpyAsync(h_answer, d_ans, size_t(B) * d.num_classes * sizeof(float), cudaMemcpyDeviceToHost, s));
   B200VQA_CUDA_OK(cudaMemcpyAsync(h_programs, d_prog, size_t(B) * program_len * sizeof(int64_t),
                                   cudaMemcpyDeviceToHost, s));
-  B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  if (sync) B200VQA_CUDA_OK(cudaStreamSynchronize(s));
   return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
+                              float* h_answer, int64_t* h_programs, int chunk, void* stream) {
+  return iqap_forward_host_impl(h, h_img, h_q, B, program_len, h_answer, h_programs, chunk, stream, true);
+}
+
+B200VQA_API int b200vqa_iqap_forward_host_async(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B,
+                                                int program_len, float* h_answer, int64_t* h_programs, int chunk,
+                                                void* stream) {
+  return iqap_forward_host_impl(h, h_img, h_q, B, program_len, h_answer, h_programs, chunk, stream, false);
 }
 
 // ------------------------------------------------------------------------------------------------ FA

@@ -66,8 +66,7 @@ class MultiModalTransformer(nn.Module):
         self.transformer = nn.Transformer(d_model, nhead, num_encoder_layers, num_decoder_layers, dim_feedforward,
                                           dropout, batch_first=True)
         self.output_linear = nn.Linear(d_model, vocab_size)
-        self._handle = None
-        self._handle_version = None
+        self._pool = nat.HandlePool(self, self._build_desc)
 
     # ------------------------------------------------------------------ native handle
     def _build_desc(self):
@@ -113,21 +112,15 @@ class MultiModalTransformer(nn.Module):
         d.dec_layers = dec_arr
         return d, keep
 
-    def _native(self) -> nat.Handle:
-        version = nat.weights_version(self)
-        dev = self.image_proj.weight.device
-        if self._handle is not None and self._handle.device != dev:
-            self._handle.close()
-            self._handle = None
-        if self._handle is None:
-            self._handle = nat.Handle(self._build_desc, dev)
-        elif version != self._handle_version:
-            self._handle.refresh(self._build_desc)
-        self._handle_version = version
-        return self._handle
+    def _native(self, slot: int = 0) -> nat.Handle:
+        return self._pool.get(slot)
 
     def native_launch_count(self) -> int:
-        return self._native().launch_count()
+        return self._pool.launch_count()
+
+    def drain(self):
+        """Results of every pipelined call (`slot > 0`) become valid on the caller's current stream."""
+        self._pool.drain()
 
     # ------------------------------------------------------------------ reference surface
     @torch.no_grad()
@@ -181,10 +174,10 @@ def tokenize_field(text: str, field: str) -> list:
 # batched executor
 # ---------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def project_images(model, image_features):
+def project_images(model, image_features, slot=0):
     """(B,1024,14,14) or (B,1024,196) f32 -> opaque bf16 image tokens (B,196,d) with the positional rows
     0..195 folded in; computed once per question and reused by every program step."""
-    h = model._native()
+    h = model._native(slot)
     img = _dev(image_features, "image_features", torch.float32)
     B = img.shape[0]
     img = img.reshape(B, model.image_proj.in_features, -1)
@@ -245,7 +238,7 @@ def chain_to_arrays(final_chain, rev_vocab, max_steps=None):
 
 @torch.no_grad()
 def run_inference_chain_batched(model, image_features, func, deps, n_steps, start_token=0, max_infer_len=20,
-                                forced=None, want_logits=False, img_tokens=None, sort_by_steps=True):
+                                forced=None, want_logits=False, img_tokens=None, sort_by_steps=True, slot=0):
     """Executes B programs at once with the inference cache in HBM.
 
     func (B,S) i32, deps (B,S,2) i32 (-1 = none), n_steps (B,) i32  ->  cache (B,S,max_infer_len) i32 where
@@ -253,7 +246,21 @@ def run_inference_chain_batched(model, image_features, func, deps, n_steps, star
     i >= n_steps[b] stay -1.  Questions are processed longest-program-first so that finished questions drop
     out of later steps (`sort_by_steps`); results are returned in the caller's order.
     """
-    h = model._native()
+    if slot > 0:
+        # pipelined submission: the whole call runs on the slot's own handle + stream; results are valid after
+        # model.drain() (independent batches overlap: one batch's small decode kernels fill the other's bubbles)
+        st = model._pool.stream(slot)
+        st.wait_stream(torch.cuda.current_stream(st.device))
+        with torch.cuda.stream(st):
+            return _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced,
+                                  want_logits, img_tokens, sort_by_steps, slot)
+    return _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced, want_logits,
+                          img_tokens, sort_by_steps, 0)
+
+
+def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced, want_logits,
+                   img_tokens, sort_by_steps, slot):
+    h = model._native(slot)
     dev = model.image_proj.weight.device
     func = _dev(func.to(dev), "func", torch.int32)
     deps = _dev(deps.to(dev), "deps", torch.int32)
@@ -262,7 +269,7 @@ def run_inference_chain_batched(model, image_features, func, deps, n_steps, star
     if tuple(deps.shape) != (B, S, MAX_DEPS) or tuple(n_steps.shape) != (B,):
         raise ValueError("deps must be (B,S,2) and n_steps (B,)")
     if img_tokens is None:
-        img_tokens = project_images(model, image_features.to(dev))
+        img_tokens = project_images(model, image_features.to(dev), slot)
     T = max_infer_len - 1
     order = None
     active = None

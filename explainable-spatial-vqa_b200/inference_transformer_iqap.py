@@ -104,8 +104,8 @@ class VQAModel(nn.Module):
         self.transformer_decoder = nn.TransformerDecoder(dec_layer, num_layers=2)
         self.program_output = nn.Linear(embedding_dim, program_vocab_size)
         self._nhead = 4
-        self._handle = None
-        self._handle_version = None
+        self._pool = nat.HandlePool(self, self._build_desc)
+        self._next_slot = 0
 
     # ------------------------------------------------------------------ native handle
     def _build_desc(self):
@@ -149,18 +149,8 @@ class VQAModel(nn.Module):
         d.dec_layers = dec_arr
         return d, keep
 
-    def _native(self) -> nat.Handle:
-        version = nat.weights_version(self)
-        dev = self.image_proj.weight.device
-        if self._handle is not None and self._handle.device != dev:
-            self._handle.close()
-            self._handle = None
-        if self._handle is None:
-            self._handle = nat.Handle(self._build_desc, dev)
-        elif version != self._handle_version:
-            self._handle.refresh(self._build_desc)
-        self._handle_version = version
-        return self._handle
+    def _native(self, slot: int = 0) -> nat.Handle:
+        return self._pool.get(slot)
 
     @staticmethod
     def _check_input(t, what, dtype):
@@ -178,11 +168,11 @@ class VQAModel(nn.Module):
 
     @torch.no_grad()
     def forward_detailed(self, image_features, questions, forced_programs=None, want_logits=False,
-                         want_memory=False):
+                         want_memory=False, slot=0):
         """Extended entry used by the parity tests: optionally teacher-forces the decoder with
         `forced_programs` (B, 27) and returns the per-position program logits (B, 27, Vp) and the encoder
         memory (S, B, d) next to the reference's two outputs."""
-        h = self._native()
+        h = self._native(slot)
         img = self._check_input(image_features, "image_features", torch.float32)
         q = self._check_input(questions, "questions", torch.int64)
         B = img.shape[0]
@@ -242,7 +232,50 @@ class VQAModel(nn.Module):
         return answer, programs
 
     def native_launch_count(self) -> int:
-        return self._native().launch_count()
+        return self._pool.launch_count()
+
+    # ------------------------------------------------------------------ pipelined submission (no reference equivalent)
+    @torch.no_grad()
+    def submit(self, image_features, questions, depth=2):
+        """Asynchronous forward of an independent batch on one of `depth` internal (handle, stream) slots, taken
+        round-robin.  Returns (answer_output, programs) whose contents are valid only after `drain()` (or after the
+        caller's stream waited for the slot stream).  Inputs are consumed in the caller's stream order."""
+        slot = 1 + self._next_slot % depth
+        self._next_slot += 1
+        st = self._pool.stream(slot)
+        self.last_submit_stream = st
+        st.wait_stream(torch.cuda.current_stream(st.device))
+        with torch.cuda.stream(st):
+            answer, programs, _, _ = self.forward_detailed(image_features, questions, slot=slot)
+        return answer, programs
+
+    @torch.no_grad()
+    def submit_host(self, image_features_cpu, questions_cpu, chunk=512, depth=2):
+        """`forward_host` without the final synchronisation, on a round-robin slot: the upload of this batch overlaps
+        the decode tail of the previous one.  Returns pinned CPU tensors that are valid after `drain_host()`."""
+        slot = 1 + self._next_slot % depth
+        self._next_slot += 1
+        h = self._native(slot)
+        st = self._pool.stream(slot)
+        img = image_features_cpu.to(torch.float32).contiguous()
+        q = questions_cpu.to(torch.int64).contiguous()
+        B, T = img.shape[0], Config.PROGRAM_SEQ_LEN
+        answer = torch.empty(B, self.answer_classifier[3].out_features, dtype=torch.float32).pin_memory()
+        programs = torch.empty(B, T, dtype=torch.int64).pin_memory()
+        with torch.cuda.device(st.device):
+            nat.check(nat.lib().b200vqa_iqap_forward_host_async(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
+                                                                nat.ptr(programs), int(chunk), C.c_void_p(st.cuda_stream)),
+                      "b200vqa_iqap_forward_host_async")
+        return answer, programs
+
+    def drain(self):
+        """Results of every `submit` become valid on the caller's current stream."""
+        self._pool.drain()
+
+    def drain_host(self):
+        """Blocks the host until every `submit_host` has delivered its results."""
+        for st in list(self._pool._streams.values()):
+            st.synchronize()
 
 
 def get_data_info(questions_h5_path):

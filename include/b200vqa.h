@@ -178,6 +178,11 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
  * compute. Returns once h_answer / h_programs are valid. This is the call bench.py times for "e2e". */
 B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_image_features, const int64_t* h_questions, int B,
                               int program_len, float* h_answer, int64_t* h_programs, int chunk, void* stream);
+/* Same without the final synchronisation: the (pinned) result buffers are valid once `stream` has drained.  With two
+ * handles on two streams the upload of one batch overlaps the latency-bound decode tail of the previous one. */
+B200VQA_API int b200vqa_iqap_forward_host_async(b200vqa_handle* h, const float* h_image_features,
+                                                const int64_t* h_questions, int B, int program_len, float* h_answer,
+                                                int64_t* h_programs, int chunk, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* FA (step-wise executor with the inference cache)                                                       */

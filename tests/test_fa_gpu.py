@@ -225,3 +225,15 @@ def test_full_size_chain_properties(model):
         n = int(n_steps[r])
         assert torch.equal(cache[r, :n, 1:].cpu().long(), forced[r, :n])
         assert common.rel_err(logits[r, :n], ref_lg[r]) < common.LOGIT_REL_TOL, r
+
+
+def test_pipelined_chain_slots_match_serial(model):
+    B = 48
+    func, deps, n_steps = orc.fa_programs(B, seed=31, max_steps=7)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    img = torch.randn(B, 1024, 14, 14, device="cuda", generator=g).relu_()
+    ref = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)
+    a = fa.run_inference_chain_batched(model, img[:24], func[:24], deps[:24], n_steps[:24], 0, 20, slot=1)
+    b = fa.run_inference_chain_batched(model, img[24:], func[24:], deps[24:], n_steps[24:], 0, 20, slot=2)
+    model.drain()
+    assert torch.equal(torch.cat([a, b]), ref)

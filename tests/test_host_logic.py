@@ -136,7 +136,7 @@ assert sharding.max_over_ranks(float(rank + 1)) == float(world)
 assert sharding.sum_over_ranks(1.0) == float(world)
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+os.write(1, ("rank %d ok\n" % rank).encode())  # one write() per rank: the two ranks share the pipe
 """
 
 

@@ -161,3 +161,17 @@ def test_full_size_batch_properties(model):
         first_tie = next((t for t in range(27) if float(mg[t]) < 0.02), 27)
         assert t_end >= first_tie, (r, t_end, first_tie)  # a difference may only start at a near-tie
     assert int(p1.min()) >= 0 and int(p1.max()) < 44
+
+
+def test_pipelined_submit_matches_serial_forward(model):
+    """submit() runs independent batches on internal (handle, stream) slots; results equal the serial call bitwise."""
+    img, q = orc.iqap_inputs(96, seed=21)
+    img, q = img.cuda(), q.cuda()
+    ref_a, ref_p = model(img, q)
+    outs = [model.submit(img[i * 32:(i + 1) * 32], q[i * 32:(i + 1) * 32], depth=2) for i in range(3)]
+    model.drain()
+    assert torch.equal(torch.cat([o[0] for o in outs]), ref_a) and torch.equal(torch.cat([o[1] for o in outs]), ref_p)
+    h = [model.submit_host(img[i * 48:(i + 1) * 48].cpu().pin_memory(), q[i * 48:(i + 1) * 48].cpu().pin_memory())
+         for i in range(2)]
+    model.drain_host()
+    assert torch.equal(torch.cat([o[0] for o in h]), ref_a.cpu()) and torch.equal(torch.cat([o[1] for o in h]), ref_p.cpu())
