@@ -458,63 +458,66 @@ def run_ours(args):
         total = sum(v[0] for v in prof.values())
         kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps,
                        "share": v[0] / total} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        # algorithmic work of every kernel class per bench step (whole batch of this rank)
         if args.workload == "iqap":
-            work = iqap_work_per_question()
+            work = {k: (kind, per_q * B) for k, (kind, per_q) in iqap_work_per_question().items()}
+        else:
+            d_, ff_, V_, T_ = D, 512, 170, 19
+            ns, dp = n_steps.cpu(), deps.cpu()
+            S_ = dp.shape[1]
+            valid = ((dp >= 0) & (dp < torch.arange(S_)[None, :, None])).sum(-1)      # consumed dependencies per step
+            active = (torch.arange(S_)[None, :] < ns[:, None])
+            L = (196 + 1 + 20 * valid) * active                                       # sequence rows of every executed step
+            Lsum, L2sum, nstep = float(L.sum()), float((L.double() ** 2).sum()), float(active.sum())
+            work = {
+                "enc_qkv_gemm": ("tensor", 2 * d_ * 3 * d_ * Lsum), "enc_attention": ("tensor", 4 * d_ * L2sum),
+                "enc_outproj_ln_gemm": ("tensor", 2 * d_ * d_ * Lsum), "enc_ffn1_gemm": ("tensor", 2 * d_ * ff_ * Lsum),
+                "enc_ffn2_ln_gemm": ("tensor", 2 * d_ * ff_ * Lsum), "dec_cross_kv_gemm": ("tensor", 2 * d_ * 2 * d_ * Lsum),
+                "enc_final_ln": ("hbm", Lsum * d_ * 2 * 2), "embed_gather": ("hbm", Lsum * d_ * 2 * 2),
+                "dec_proj_gemm": ("tensor", nstep * T_ * (2 * d_ * 3 * d_ + 2 * d_ * d_)),
+                "dec_outproj_ln_gemm": ("tensor", nstep * T_ * 4 * d_ * d_),
+                "dec_ffn_split": ("tensor", nstep * T_ * 4 * d_ * ff_),
+                "dec_head_argmax": ("tensor", nstep * T_ * 2 * d_ * V_),
+                "dec_self_attention": ("hbm", nstep * sum((t + 1) * 2 * d_ * 2 for t in range(T_))),
+                # HBM-bound: every decode position re-reads the projected K|V of the memory (1 KB per key row)
+                "dec_cross_attention": ("hbm", Lsum * 1024 * T_),
+            }
 
-            def roof(name):
-                kind, per_q = work[name]
-                per_launch = per_q * B / kernels[name]["launches_per_step"]
-                dur = kernels[name]["ms_per_step"] / kernels[name]["launches_per_step"] * 1e-3
-                if kind == "tensor":
-                    ach = per_launch / dur / 1e12
-                    r = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                         "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
-                else:
-                    ach = per_launch / dur / 1e9
-                    r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy)"}
-                return r, per_launch, dur
+        def roof(name):
+            kind, total = work[name]
+            per_launch = total / kernels[name]["launches_per_step"]
+            dur = kernels[name]["ms_per_step"] / kernels[name]["launches_per_step"] * 1e-3
+            if kind == "tensor":
+                ach = per_launch / dur / 1e12
+                r = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+            else:
+                ach = per_launch / dur / 1e9
+                r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy)"}
+            return r, per_launch, dur
 
-            top = next(k for k in kernels if k in work)  # kernel class with the largest share of the step
-            roofline, per_launch, dur = roof(top)
-            for k in kernels:
-                if k in work:
-                    rk, _, _ = roof(k)
-                    kernels[k].update(bound=rk["bound"], achieved=rk["achieved"], unit=rk["unit"], frac=rk["frac"])
-            # DRAM bytes per launch of this kernel class from the committed `ncu --set full` capture, if any
-            tpath = os.path.join(REPO, "profiles", "traffic.json")
-            if os.path.exists(tpath):
-                with open(tpath) as f:
-                    tr = json.load(f).get(top)
-                if tr:
-                    roofline["traffic"] = tr["dram_bytes_per_launch"]
-                    roofline["traffic_source"] = "profiles/" + tr["source"]
-            roofline["algorithmic_per_launch"] = per_launch
-            roofline["avg_launch_ms"] = dur * 1e3
+        top = next(k for k in kernels if k in work)  # kernel class with the largest share of the step
+        roofline, per_launch, dur = roof(top)
+        for k in kernels:
+            if k in work:
+                rk, _, _ = roof(k)
+                kernels[k].update(bound=rk["bound"], achieved=rk["achieved"], unit=rk["unit"], frac=rk["frac"])
+        # DRAM bytes per launch of this kernel class from the committed `ncu --set full` capture, if any
+        tpath = os.path.join(REPO, "profiles", "traffic.json")
+        if args.workload == "iqap" and os.path.exists(tpath):
+            with open(tpath) as f:
+                tr = json.load(f).get(top)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = "profiles/" + tr["source"]
+        roofline["algorithmic_per_launch"] = per_launch
+        roofline["avg_launch_ms"] = dur * 1e3
+        if args.workload == "iqap":
             # whole-step tensor-core utilisation: algorithmic FLOPs of the model / step time / peak
             roofline["model_flops_frac_of_bf16_peak"] = (IQAP_FLOPS_PER_QUESTION * B / (ms / args.steps * 1e-3)) / (
                 peaks["bf16_tflops_sustained"] * 1e12)
-
-    if (rank == 0 or world == 1) and args.workload != "iqap" and kernels and "dec_cross_attention" in kernels:
-        # FA / e2e: the dominant class is the decoder cross-attention (HBM-bound re-read of the projected memory K|V,
-        # 1 KB per key row, once per decode position).  Algorithmic bytes from the actual ragged programs.
-        ns, dp = n_steps.cpu(), deps.cpu()
-        S_ = dp.shape[1]
-        valid = ((dp >= 0) & (dp < torch.arange(S_)[None, :, None])).sum(-1)          # consumed dependencies per step
-        active = torch.arange(S_)[None, :] < ns[:, None]
-        rows = ((196 + 1 + 20 * valid) * active).sum().item()                        # key rows over all executed steps
-        bytes_per_step = rows * 1024 * 19                                             # 19 decode positions each
-        k = kernels["dec_cross_attention"]
-        dur = k["ms_per_step"] * 1e-3
-        ach = bytes_per_step / dur / 1e9
-        if next(iter(kernels)) == "dec_cross_attention":
-            roofline = {"kernel": "dec_cross_attention", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                        "peak_source": peaks["source"] + " (copy)",
-                        "algorithmic_per_launch": bytes_per_step / k["launches_per_step"],
-                        "avg_launch_ms": k["ms_per_step"] / k["launches_per_step"]}
-        k.update(bound="hbm", achieved=ach, unit="GB/s", frac=ach / peaks["hbm_gbs"])
 
     extra = {}
     if rank == 0:
@@ -572,7 +575,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="iqap", choices=["iqap", "fa", "e2e"])
     ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
-    ap.add_argument("--e2e-chunk", type=int, default=512)
+    ap.add_argument("--e2e-chunk", type=int, default=1024)
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="independent batches in flight (1 = strictly serial steps)")
     ap.add_argument("--cpu-sample", type=int, default=None)
