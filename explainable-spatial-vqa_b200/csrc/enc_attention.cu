@@ -8,19 +8,20 @@
 // fetched once.  The whole K and V of a head sit in shared memory - no online-softmax rescaling:
 //   warp 0      TMA: Q tile 0, Q tile 1, K, V (128B-swizzled boxes of the packed q|k|v activations)
 //   warp 1      tcgen05.mma  S0 = Q0 K^T, S1 = Q1 K^T (two 256-column TMEM accumulators), later O0 = P0 V, O1 = P1 V
-//   warps 2-5   softmax group of tile 0, warps 6-9 softmax group of tile 1 - one query row per thread:
-//               tcgen05.ld S, masked softmax in fp32 (exp2), P -> smem as the bf16 K-major A operand of the
-//               second MMA, then O / rowsum -> bf16 global
-// The two groups run concurrently on different scheduler partitions, and tile 0's P.V overlaps tile 1's
-// softmax.  V is consumed directly as an MN-major B operand (no transpose).  P tiles reuse the shared memory of
-// K and Q once both score MMAs have retired.
+//   warps 2-9   softmax group of tile 0, warps 10-17 softmax group of tile 1.  A query row is shared by TWO threads
+//               (same TMEM lane, alternating 32-column chunks) so the per-row dependent chain is halved; the pair
+//               exchanges its row maximum and row sum through shared memory.  tcgen05.ld S, masked softmax in fp32
+//               (exp2), P -> smem as the bf16 K-major A operand of the second MMA, then O / rowsum -> bf16 global
+// The groups run concurrently on all four scheduler partitions, and tile 0's P.V overlaps tile 1's softmax.
+// V is consumed directly as an MN-major B operand (no transpose).  P tiles reuse the shared memory of K and Q
+// once both score MMAs have retired.
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace b200vqa {
 namespace {
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 64 + 512;  // TMA warp, MMA warp, 2 tiles x 8 softmax warps
 constexpr int kKeysMax = 256;
 
 template <int DH>
@@ -38,7 +39,8 @@ struct AttnSmem {
   static constexpr int kOffP0 = 0;
   static constexpr int kOffP1 = kP;
   static constexpr int kOffV = 2 * kP;
-  static constexpr int kOffBar = kOffV + kV;
+  static constexpr int kOffXch = kOffV + kV;          // [2 tiles][2 halves][128 rows] float2 (max, sum)
+  static constexpr int kOffBar = kOffXch + 2 * 2 * 128 * 8;
   static constexpr int kBytes = kOffBar + 128;
 };
 
@@ -68,7 +70,7 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;  // [2] score accumulator of tile t complete
-  uint64_t* bar_p = bars + 4;  // [2] P of tile t written (128 arrivals)
+  uint64_t* bar_p = bars + 4;  // [2] P of tile t written (256 arrivals: two threads per row)
   uint64_t* bar_o = bars + 6;  // [2] output accumulator of tile t complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -81,7 +83,7 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     mbar_init(bar_v, 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar_s[t], 1);
-      mbar_init(&bar_p[t], 128);
+      mbar_init(&bar_p[t], 256);
       mbar_init(&bar_o[t], 1);
     }
     fence_mbar_init();
@@ -142,17 +144,23 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
   } else {
-    const int t = (warp - 2) >> 2;   // query tile of this softmax group
-    const int quarter = warp & 3;    // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const int t = (warp - 2) >> 3;          // query tile of this softmax group
+    const int hc = ((warp - 2) >> 2) & 1;   // which half of the row's 32-column chunks (alternating) this thread takes
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;      // query row inside the tile == TMEM lane
     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(t * 256);
     const float sl2 = p.scale * 1.4426950408889634f;
     __nv_bfloat16* orow = p.out + (row0 + t * 128 + r) * kD + h * DH;
+    float2* xch = reinterpret_cast<float2*>(smem + L::kOffXch);  // [t][hc][r]
+    float2* mine = xch + (t * 2 + hc) * 128 + r;
+    const float2* theirs = xch + (t * 2 + (hc ^ 1)) * 128 + r;
+    const uint32_t pair_bar = 1 + t * 4 + quarter;  // the two warps sharing these 32 rows
+    constexpr int kOutCols = DH / 2;                 // output columns written by this thread
 
     if (t == 1 && !two) {
       // a tile that holds only padding rows: keep them finite (they are masked as keys downstream)
 #pragma unroll
-      for (int c = 0; c < DH / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < kOutCols / 8; ++c) reinterpret_cast<uint4*>(orow + hc * kOutCols)[c] = make_uint4(0, 0, 0, 0);
     } else {
       mbar_wait(&bar_s[t], 0);
       __syncwarp();
@@ -160,7 +168,7 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const int nchunks = (len + 31) / 32;
 
       float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = hc; c < nchunks; c += 2) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
@@ -168,11 +176,14 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int j = 0; j < 32; ++j)
           if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
+      mine->x = mx;
+      named_bar_sync(pair_bar, 64);
+      mx = fmaxf(mx, theirs->x);
       // P_t overwrites K / Q: both score MMAs must have retired
       if (t == 0) mbar_wait(&bar_s[1], 0);
       const float mxs = mx * sl2;
       float sum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = hc; c < nchunks; c += 2) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
@@ -194,7 +205,9 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
               make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         }
       }
-      // keys in [32*nchunks, keys16) cannot exist (keys16 <= 32*nchunks); P is complete for the MMA
+      // (with an odd chunk count the last 32-column half of the final 64-key panel is never written; the PV MMA
+      //  reads keys16 <= 32*nchunks columns, so it is never read either)
+      mine->y = sum;
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&bar_p[t]);
@@ -202,17 +215,18 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(&bar_o[t], 0);
       __syncwarp();
       tc_fence_after_sync();
-      const float inv = 1.f / sum;
+      named_bar_sync(pair_bar, 64);  // partner's partial row sum is visible
+      const float inv = 1.f / (sum + theirs->y);
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
+      for (int c = 0; c < kOutCols / 32; ++c) {
         uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + hc * kOutCols + c * 32, v);
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
           o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+        uint4* dst = reinterpret_cast<uint4*>(orow + hc * kOutCols + c * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
