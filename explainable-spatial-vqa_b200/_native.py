@@ -287,6 +287,13 @@ class HandlePool:
         self._versions = {}
         self._streams = {}
 
+    def __getstate__(self):
+        # native handles, streams and packed weights never travel through pickle / deepcopy: they are rebuilt lazily
+        return {"_module": self._module, "_builder": self._builder, "_handles": {}, "_versions": {}, "_streams": {}}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
     def get(self, slot: int = 0) -> Handle:
         module = self._module
         version = weights_version(module)

@@ -615,8 +615,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       cp.out = dattn;
       cp.pdl = true;
       h->cur_tag = kTagDecCrossAttn;
-      static const bool skip_cross = getenv("B200VQA_DEBUG_SKIP_CROSS") != nullptr;  // timing experiments only
-      if (!skip_cross) LAUNCH_OK(h, launch_row_attn(cp, s));
+      LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s));
       {

@@ -159,3 +159,18 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "program-steps/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_modules_survive_deepcopy_and_pickle():
+    """Native handles never travel through copy / pickle; the copy rebuilds its own lazily."""
+    import copy
+    import io
+    m = common.seeded_iqap()
+    m2 = copy.deepcopy(m)
+    assert m2._pool._module is m2 and m2._pool._handles == {}
+    buf = io.BytesIO()
+    torch.save(m.state_dict(), buf)
+    buf.seek(0)
+    m2.load_state_dict(torch.load(buf))
+    f2 = copy.deepcopy(common.seeded_fa())
+    assert f2._pool._module is f2
