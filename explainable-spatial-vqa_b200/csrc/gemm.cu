@@ -34,8 +34,11 @@ namespace {
 constexpr int kBM = 128;          // rows per tile = UMMA M
 constexpr int kKBytes = 128;      // bytes of K per k-block = one 128B swizzle row
 constexpr int kUmmaKBytes = 32;   // bytes of K per tcgen05.mma (16 bf16 / 8 tf32)
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+// epilogue warps: 8 (two per TMEM lane quarter); the LayerNorm epilogue is instruction-latency-bound with two warps per
+// scheduler, so it runs 16 (four per quarter, 64 of the 256 columns each)
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiBiasResLN ? 16 : 8; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + epi_warps(epi) * 32; }
+constexpr int kMaxEpiWarps = 16;
 constexpr int kAccStages = 2;
 constexpr int kStages = 4;
 constexpr int kWstatMaxKb = 4;    // W-stationary when the whole K fits in 4 k-blocks
@@ -45,17 +48,18 @@ struct GemmSmem {
   static constexpr int kStageA = kBM * kKBytes;             // 16 KB
   static constexpr int kStageB = BN * kKBytes;              // 8 / 16 / 32 KB
   static constexpr int kRing = kStages * (kStageA + kStageB);  // streaming ring == W (4 blocks) + A ring
-  static constexpr int kStgPerWarp = 2 * 2048;              // two 32-row x 64-byte staging tiles per epilogue warp
+  // staging: 32 KB = 8 warps x two 32-row x 64-byte tiles (double-buffered) or 16 warps x one tile
   static constexpr int kOffStg = kRing;
-  static constexpr int kOffXch = kOffStg + kEpiWarps * kStgPerWarp;  // LayerNorm pair exchange
-  static constexpr int kOffBar = kOffXch + kEpiWarps * 32 * 8;
+  static constexpr int kOffXch = kOffStg + 32768;           // LayerNorm / argmax exchange between the warps of a quarter
+  static constexpr int kOffBar = kOffXch + 2048;
   static constexpr int kBytes = kOffBar + 128 /*barriers + tmem ptr*/;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int BN, int EPI, bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   using L = GemmSmem<BN>;
@@ -63,7 +67,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
   static_assert(EPI != kEpiBiasResLN || BN == 256, "LN epilogue needs the whole row in one tile");
   constexpr int kChunks = BN / 32;            // 32-column chunks per tile
-  constexpr int kMyChunks = kChunks / 2;      // per epilogue warp
+  constexpr int kEpiWarps = epi_warps(EPI);
+  constexpr int kSplit = kEpiWarps / 4;           // warps sharing a TMEM lane quarter (they split the columns)
+  constexpr int kMyChunks = kChunks / kSplit;     // per epilogue warp
+  constexpr int kStgPerWarp = 32768 / kEpiWarps;  // 4 KB (two buffers) or 2 KB (one buffer)
+  constexpr uint32_t kStgMask = kStgPerWarp == 4096 ? 1u : 0u;
+  static_assert(kChunks % kSplit == 0, "column chunks must divide among the warps of a quarter");
 
   // 128-byte swizzled operand tiles need 1024-byte alignment; the whole 227 KB budget is in use, so there is no
   // slack to round up - the alignment attribute is relied upon and checked
@@ -222,10 +231,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
-    const int half = ew >> 2;      // which of the two warps of this quarter: takes chunks half, half+2, ...
+    const int half = ew >> 2;      // which of the kSplit warps of this quarter: takes chunks half, half+kSplit, ...
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* stg = smem + L::kOffStg + ew * L::kStgPerWarp;
-    float2* xch = reinterpret_cast<float2*>(smem + L::kOffXch);  // [kEpiWarps][32]
+    uint8_t* stg = smem + L::kOffStg + ew * kStgPerWarp;
+    float2* xch = reinterpret_cast<float2*>(smem + L::kOffXch);  // [8][32] float2 (8-warp epilogues)
+    float* xchf = reinterpret_cast<float*>(smem + L::kOffXch);   // [16][32] float  (LayerNorm epilogue)
     int as = 0;
     uint32_t aphase = 0;
     uint32_t nstore = 0;  // TMA stores issued by this warp's lane 0 (staging buffer = nstore & 1)
@@ -237,6 +247,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int n0 = nt * BN;
       const int row = m0 + row_in_tile;
       const bool valid = row < p.M;
+      // LayerNorm epilogue: while the operands / MMAs of this tile are still in flight, pull bias | gamma | beta
+      // into L1 and request the first residual chunk, so no L2 round trip sits inside the dependent chunk loops
+      [[maybe_unused]] uint4 rnext[4];
+      if constexpr (EPI == kEpiBiasResLN) {
+        if (ew == 0 && lane < 24) {
+          const float* src = lane < 8 ? p.bias + n0 : (lane < 16 ? p.gamma : p.beta);
+          prefetch_l1(src + (lane & 7) * 32);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int grow = m0 + quarter * 32 + (lane >> 2) + 8 * k;
+          rnext[k] = grow < p.M ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + half * 32 +
+                                                                    (lane & 3) * 8)
+                                : make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(&acc_full[as], aphase);
       __syncwarp();
       tc_fence_after_sync();
@@ -249,11 +275,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tmem_ld32(taddr + half * 32, rbuf[0]);
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           uint32_t(&r)[32] = rbuf[i & 1];
           tmem_ld_wait();
           if (i + 1 < kMyChunks) {
-            tmem_ld32(taddr + (c + 2) * 32, rbuf[(i + 1) & 1]);
+            tmem_ld32(taddr + (c + kSplit) * 32, rbuf[(i + 1) & 1]);
           } else {  // all TMEM reads of this stage are done -> hand it back to the MMA warp
             tc_fence_before_sync();
             __syncwarp();
@@ -272,8 +298,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             o[j >> 1] = pack_bf16x2(v0, v1);
             o[(j >> 1) + 1] = pack_bf16x2(v2, v3);
           }
-          uint8_t* buf = stg + (nstore & 1) * 2048;
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+          uint8_t* buf = stg + (nstore & kStgMask) * 2048;
+          if (lane == 0) { if (kStgMask) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }  // the store that last used this buffer has read it
           __syncwarp();
           uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
@@ -294,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const float* perow = p.pe + size_t(p.pe_off + (valid ? pos : 0)) * p.N + n0;
 #pragma unroll 1
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -328,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const float* trow = p.lstm_table + size_t(tokv) * p.N + n0;
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -381,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         float* lrow = (p.logits && valid) ? p.logits + (size_t(row) * p.logits_T + p.head_t) * p.head_V : nullptr;
 #pragma unroll 1
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           if (n0 + c * 32 >= p.head_V) break;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
@@ -434,19 +460,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           // residual chunk (32 rows x 64 B): coalesced 16-byte loads (8 rows per instruction), transposed through smem
-          uint8_t* buf = stg + (i & 1) * 2048;
+          uint8_t* buf = stg + (i & kStgMask) * 2048;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rr = (lane >> 2) + 8 * k;
-            const int grow = m0 + quarter * 32 + rr;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (grow < p.M)
-              val = *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + c * 32 + (lane & 3) * 8);
-            *reinterpret_cast<uint4*>(buf + rr * 64 + (lane & 3) * 16) = val;
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(buf + ((lane >> 2) + 8 * k) * 64 + (lane & 3) * 16) = rnext[k];
+          if (i + 1 < kMyChunks) {  // next chunk's residual is in flight while this one is combined
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int grow = m0 + quarter * 32 + (lane >> 2) + 8 * k;
+              rnext[k] = grow < p.M ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 +
+                                                                        (c + kSplit) * 32 + (lane & 3) * 8)
+                                    : make_uint4(0, 0, 0, 0);
+            }
           }
           __syncwarp();
           tmem_ld_wait();
@@ -471,16 +500,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
 
-        // row statistics over all BN columns: exchange partial sums with the partner warp of this quarter
-        const int partner = ew ^ 4;
+        // row statistics over all BN columns: the kSplit warps of this quarter exchange partial sums (two-pass)
+        const int xbase = (ew & 3) * 32 + lane;  // slot of warp (ew & 3) + 4*j is xchf[xbase + 128*j]
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i)
 #pragma unroll
           for (int j = 0; j < 32; ++j) s += v[i][j];
-        xch[ew * 32 + lane].x = s;
-        named_bar_sync(1 + quarter, 64);
-        const float mean = (s + xch[partner * 32 + lane].x) * (1.f / BN);
+        xchf[ew * 32 + lane] = s;
+        named_bar_sync(1 + quarter, kSplit * 32);
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < kSplit; ++j) tot += xchf[xbase + 128 * j];
+        const float mean = tot * (1.f / BN);
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i)
@@ -489,15 +521,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const float d = v[i][j] - mean;
             sq = fmaf(d, d, sq);
           }
-        xch[ew * 32 + lane].y = sq;
-        named_bar_sync(1 + quarter, 64);
-        const float rstd = rsqrtf((sq + xch[partner * 32 + lane].y) * (1.f / BN) + p.eps);
-        // (xch is rewritten only after the next tile's first barrier of this pair, which orders the reads above)
+        named_bar_sync(1 + quarter, kSplit * 32);  // every partner has read the sums before they are overwritten
+        xchf[ew * 32 + lane] = sq;
+        named_bar_sync(1 + quarter, kSplit * 32);
+        float tsq = 0.f;
+#pragma unroll
+        for (int j = 0; j < kSplit; ++j) tsq += xchf[xbase + 128 * j];
+        const float rstd = rsqrtf(tsq * (1.f / BN) + p.eps);
+        named_bar_sync(1 + quarter, kSplit * 32);  // ... and the squares before the next tile's sums
 
         float* frow = (p.out_f32 && valid) ? p.out_f32 + size_t(row) * BN : nullptr;
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
-          const int c = half + 2 * i;
+          const int c = half + kSplit * i;
           const float* gptr = p.gamma + c * 32;
           const float* btptr = p.beta + c * 32;
           uint32_t o[16];
@@ -512,8 +548,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
             if (frow) *reinterpret_cast<float4*>(frow + c * 32 + j) = make_float4(y0, y1, y2, y3);
           }
-          uint8_t* buf = stg + (nstore & 1) * 2048;
-          if (lane == 0) tma_store_wait_read<1>();
+          uint8_t* buf = stg + (nstore & kStgMask) * 2048;
+          if (lane == 0) { if (kStgMask) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           __syncwarp();
           uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
@@ -559,7 +595,7 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const C
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  return launch_kernel(kfn, dim3(grid), dim3(kGemmThreads), L::kBytes, stream, p.pdl, tm_a, tm_w, tm_out, p);
+  return launch_kernel(kfn, dim3(grid), dim3(gemm_threads(EPI)), L::kBytes, stream, p.pdl, tm_a, tm_w, tm_out, p);
 }
 
 // ------------------------------------------------------------------------------------------
