@@ -58,6 +58,28 @@ struct GemmSmem {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// Writes one 32-row x 32-column bf16 chunk (row per lane in registers) to global memory with coalesced stores:
+// transpose through a 2 KB shared tile, then every store instruction covers 8 rows x 64 contiguous bytes.  Plain
+// (generic-proxy) stores: a shared->global TMA store would need a fence.proxy.async per chunk (~450 cycles measured).
+__device__ __forceinline__ void store_chunk_bf16(uint8_t* buf, const uint32_t (&o)[16], __nv_bfloat16* out, int ldc,
+                                                 int row0, int col0, int M, int lane) {
+  // 16-byte units of a 64-byte row are XOR-swizzled with (row >> 1) & 3: both the row-per-lane writes and the
+  // 8-rows-per-instruction reads are then bank-conflict free (un-swizzled, the writes are 4-way conflicted and the
+  // 8 epilogue warps saturate the shared-memory pipe: ~380 cycles per chunk measured)
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = (lane >> 2) + 8 * k;
+    const uint4 val = *reinterpret_cast<const uint4*>(buf + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+    if (row0 + rr < M) *reinterpret_cast<uint4*>(out + size_t(row0 + rr) * ldc + col0 + (lane & 3) * 8) = val;
+  }
+  __syncwarp();
+}
+
 template <int BN, int EPI, bool TF32>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
@@ -112,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
-    if (EPI != kEpiBiasPeRemap && EPI != kEpiHead && EPI != kEpiLstm) tma_prefetch_desc(&tm_out);
+    (void)tm_out;  // outputs leave through coalesced plain stores (store_chunk_bf16); kept for ABI stability
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -238,7 +260,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     float* xchf = reinterpret_cast<float*>(smem + L::kOffXch);   // [16][32] float  (LayerNorm epilogue)
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t nstore = 0;  // TMA stores issued by this warp's lane 0 (staging buffer = nstore & 1)
+    uint32_t nstore = 0;  // chunks written by this warp (staging buffer = nstore & kStgMask)
+    [[maybe_unused]] float* btab = reinterpret_cast<float*>(smem + L::kOffXch);  // bias of the current n-tile
+    [[maybe_unused]] int btab_nt = -1;
     pdl_wait();
 
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -247,6 +271,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int n0 = nt * BN;
       const int row = m0 + row_in_tile;
       const bool valid = row < p.M;
+      if constexpr (EPI == kEpiBias || EPI == kEpiBiasRelu) {
+        // bias of this n-tile into shared memory (once per n-tile, while the operands are still in flight): the
+        // chunk loops then read it with broadcast LDS instead of paying an L2 round trip per chunk
+        if (nt != btab_nt) {
+          named_bar_sync(6, kEpiWarps * 32);  // everyone is done with the previous n-tile's table
+          for (int i = ew * 32 + lane; i < BN; i += kEpiWarps * 32) btab[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+          named_bar_sync(6, kEpiWarps * 32);
+          btab_nt = nt;
+        }
+      }
       // LayerNorm epilogue: while the operands / MMAs of this tile are still in flight, pull bias | gamma | beta
       // into L1 and request the first residual chunk, so no L2 round trip sits inside the dependent chunk loops
       [[maybe_unused]] uint4 rnext[4];
@@ -286,10 +320,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (lane == 0) mbar_arrive(&acc_empty[as]);
           }
           uint32_t o[16];
-          const float* bptr = p.bias + n0 + c * 32;
+          const float* bptr = btab + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b4 = p.bias ? ldg4(bptr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b4 = *reinterpret_cast<const float4*>(bptr + j);
             float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
             float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
             if (EPI == kEpiBiasRelu) {
@@ -298,18 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             o[j >> 1] = pack_bf16x2(v0, v1);
             o[(j >> 1) + 1] = pack_bf16x2(v2, v3);
           }
-          uint8_t* buf = stg + (nstore & kStgMask) * 2048;
-          if (lane == 0) { if (kStgMask) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }  // the store that last used this buffer has read it
-          __syncwarp();
-          uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tm_out, buf, n0 + c * 32, m0 + quarter * 32);
-            tma_store_commit();
-          }
+          store_chunk_bf16(stg + (nstore & kStgMask) * 2048, o, p.out, p.ldc, m0 + quarter * 32, n0 + c * 32, p.M, lane);
           ++nstore;
         }
       } else if constexpr (EPI == kEpiBiasPeRemap) {
@@ -455,9 +478,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       } else {  // kEpiBiasResLN : this warp holds 32 rows x (BN/2) columns of v = acc + bias + residual in registers
         float v[kMyChunks][32];
-        // the previous tile's stores may still read the staging buffers that now receive the residual
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
           const int c = half + kSplit * i;
@@ -467,7 +487,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           uint8_t* buf = stg + (i & kStgMask) * 2048;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(buf + ((lane >> 2) + 8 * k) * 64 + (lane & 3) * 16) = rnext[k];
+            *reinterpret_cast<uint4*>(buf + ((lane >> 2) + 8 * k) * 64 +
+                                      (((lane & 3) ^ ((((lane >> 2) + 8 * k) >> 1) & 3)) << 4)) = rnext[k];
           if (i + 1 < kMyChunks) {  // next chunk's residual is in flight while this one is combined
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -482,7 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const float* bptr = p.bias + n0 + c * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(buf + lane * 64 + q * 16);
+            const uint4 rv = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
             const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
             const float4 b0 = ldg4(bptr + q * 8), b1 = ldg4(bptr + q * 8 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -548,26 +569,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
             if (frow) *reinterpret_cast<float4*>(frow + c * 32 + j) = make_float4(y0, y1, y2, y3);
           }
-          uint8_t* buf = stg + (nstore & kStgMask) * 2048;
-          if (lane == 0) { if (kStgMask) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          __syncwarp();
-          uint4* dst = reinterpret_cast<uint4*>(buf + lane * 64);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tm_out, buf, n0 + c * 32, m0 + quarter * 32);
-            tma_store_commit();
-          }
+          store_chunk_bf16(stg + (nstore & kStgMask) * 2048, o, p.out, p.ldc, m0 + quarter * 32, n0 + c * 32, p.M, lane);
           ++nstore;
         }
       }
       if (++as == kAccStages) { as = 0; aphase ^= 1; }
     }
     if (ew == 0 && lane == 0) B200VQA_STAMP(7);
-    if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the bulk stores reading it
-    if (ew == 0 && lane == 0) B200VQA_STAMP(8);
   }
 
   tc_fence_before_sync();

@@ -32,7 +32,7 @@ def run(M, N, K, epi, bn, iters=200):
     us = e0.elapsed_time(e1) * 1e3 / iters
     print(f"M={M:7d} N={N:5d} K={K:5d} epi={epi} bn={bn:3d}: {us:8.2f} us  {2*M*N*K/us/1e6:8.1f} TFLOP/s")
     if M <= 1024:
-        clk = torch.zeros(16, dtype=torch.int64, device="cuda")
+        clk = torch.zeros(32, dtype=torch.int64, device="cuda")
         a.clk = clk.data_ptr()
         for _ in range(3):
             lib.b200vqa_dbg_gemm(C.byref(a), s)
@@ -41,6 +41,9 @@ def run(M, N, K, epi, bn, iters=200):
         names = ["entry", "setup done", "pdl_wait done", "W landed", "A[0] landed", "A[last] landed", "acc ready (epi)",
                  "epi stores issued", "stores drained", "exit"]
         print("   stage cycles since entry:", ", ".join(f"{n}={c[i] - c[0]}" for i, n in enumerate(names) if c[i]))
+        extra = [f"#{i}={c[i] - c[0]}" for i in range(len(names), 32) if c[i]]
+        if extra:
+            print("   extra stamps:", ", ".join(extra))
 
 if __name__ == "__main__":
     cfgs = [(1024, 256, 256, 2, 256), (1024, 256, 256, 0, 256), (1024, 256, 256, 0, 64), (1024, 768, 256, 0, 64),
