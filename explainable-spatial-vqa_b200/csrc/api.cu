@@ -123,6 +123,7 @@ struct b200vqa_handle {
   int cur_tag = kTagMisc;
   bool use_graphs = true;
   bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
+  bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   int decode_branches = 8;            // concurrent question ranges inside the decode graph
@@ -443,6 +444,11 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
     if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0) bn = 64;
   }
   if (epi == kEpiHead) bn = N;  // N = padded vocabulary (one n-tile); rows >= V of W are zero-filled by TMA
+  // the decode chain's out_proj + LayerNorm (M = questions): a cluster of four CTAs per 128-row tile (64-column slices,
+  // statistics exchanged through distributed shared memory) instead of one SM owning the whole 128 x 256 epilogue.
+  // Chosen per call site, never by M: the two kernels round the statistics differently, and a question's result must
+  // not depend on how many other questions share its batch.
+  if (epi == kEpiBiasResLN && p.ln_cluster && K == 256 && N == 256 && !h->no_ln_cluster) bn = 64;
   const CUtensorMap *ta, *tw, *to;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(K), uint64_t(lda), 128, &ta));
@@ -467,8 +473,9 @@ int gemm_bias(b200vqa_handle* h, bool relu, const __nv_bfloat16* A, int M, int K
 
 int gemm_res_ln(b200vqa_handle* h, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
                 const __nv_bfloat16* residual, const float* gamma, const float* beta, __nv_bfloat16* out,
-                float* out_f32, cudaStream_t s) {
+                float* out_f32, cudaStream_t s, bool decode = false) {
   GemmParams p;
+  p.ln_cluster = decode;
   p.bias = bias;
   p.out = out;
   p.ldc = kD;
@@ -598,7 +605,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       h->cur_tag = kTagDecSelfAttn;
       LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemmLn;
-      RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s));
+      RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s, true));
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
       RowAttnParams cp;
@@ -617,7 +624,8 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       h->cur_tag = kTagDecCrossAttn;
       LAUNCH_OK(h, launch_row_attn(cp, s));
       h->cur_tag = kTagDecGemmLn;
-      RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s));
+      RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s,
+                        true));
       {
         // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
         const CUtensorMap *tx, *tw1, *tw2;
@@ -887,6 +895,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   h->device = device;
   h->num_sms = num_sms;
   if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
+  if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;

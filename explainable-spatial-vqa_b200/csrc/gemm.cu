@@ -607,6 +607,235 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const C
 }
 
 // ------------------------------------------------------------------------------------------
+// Latency-optimised out_proj + residual + LayerNorm for the decode chain (M = questions of one branch, N = K = 256).
+//
+// The persistent kernel above gives a 128-row m-tile to ONE SM, whose epilogue then owns 128 x 256 values: at decode
+// sizes (1..8 m-tiles) that epilogue IS the kernel (12 k of 20 k cycles measured).  Here a cluster of 4 CTAs shares the
+// m-tile, each computing a 128 x 64 column slice (A tile 64 KB + W slice 32 KB per SM instead of 64 + 128 KB).  The
+// LayerNorm statistics are per-warp (mean, M2) pairs over 32 columns, written into every peer's shared memory
+// (st.shared::cluster), combined after one cluster barrier with the parallel-variance formula (exact two-pass
+// statistics per part, no E[x^2] - mean^2 cancellation).
+//   warp 0     : TMA loads + tcgen05.mma issue (one thread), owns the 64 TMEM columns
+//   warps 1..8 : epilogue; warp w reads TMEM lane quarter (w & 3), columns 32 * ((w - 1) >> 2) of the slice
+// ------------------------------------------------------------------------------------------
+constexpr int kLnCl = 4;                      // CTAs per cluster = column slices of the 256-wide row
+constexpr int kLnBN = 256 / kLnCl;            // 64 columns per CTA
+constexpr int kLnKb = 4;                      // K = 256 bf16 = 4 k-blocks of 128 B
+constexpr int kLnThreads = 32 + 8 * 32;
+struct LnClSmem {
+  static constexpr int kOffA = 0;                                   // 4 x [128 rows x 128 B]
+  static constexpr int kOffW = kOffA + kLnKb * kBM * kKBytes;       // 4 x [64 rows x 128 B]
+  static constexpr int kOffStg = kOffW + kLnKb * kLnBN * kKBytes;   // 8 warps x 2 KB
+  static constexpr int kOffPart = kOffStg + 8 * 2048;               // float2 [2 * kLnCl parts][128 rows]
+  static constexpr int kOffTab = kOffPart + 2 * kLnCl * kBM * 8;    // bias | gamma | beta of this slice (3 x 64 fp32)
+  static constexpr int kOffBar = kOffTab + 3 * kLnBN * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+__global__ void __cluster_dims__(kLnCl, 1, 1) __launch_bounds__(kLnThreads, 1)
+gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                       const GemmParams p) {
+  using L = LnClSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [kLnKb] A k-blocks
+  uint64_t* w_full = full_bar + kLnKb;
+  uint64_t* acc_full = w_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* tab = reinterpret_cast<float*>(smem + L::kOffTab);
+  float2* part = reinterpret_cast<float2*>(smem + L::kOffPart);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // == blockIdx.x : column slice
+  const int m0 = blockIdx.y * kBM;
+  const int n0 = int(rank) * kLnBN;
+  const bool dbg = p.dbg_clk != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define B200VQA_STAMP(i) \
+  if (dbg) p.dbg_clk[i] = clock64()
+  if (threadIdx.x == 0) B200VQA_STAMP(0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_w);
+      for (int kb = 0; kb < kLnKb; ++kb) mbar_init(&full_bar[kb], 1);
+      mbar_init(w_full, 1);
+      mbar_init(acc_full, 1);
+      fence_mbar_init();
+      // weights do not depend on the previous kernel
+      mbar_expect_tx(w_full, kLnKb * kLnBN * kKBytes);
+      for (int kb = 0; kb < kLnKb; ++kb)
+        tma_load_2d(&tm_w, w_full, smem + L::kOffW + kb * kLnBN * kKBytes, kb * 64, n0);
+    }
+    __syncwarp();
+    tmem_alloc<kLnBN>(tmem_slot);
+  } else {
+    // this slice's bias | gamma | beta (weights: safe before the dependency wait)
+    const int t = (warp - 1) * 32 + lane;
+    if (t < 3 * kLnBN) {
+      const float* src = t < kLnBN ? p.bias : (t < 2 * kLnBN ? p.gamma : p.beta);
+      tab[t] = src ? __ldg(src + n0 + (t & (kLnBN - 1))) : (t < 2 * kLnBN && t >= kLnBN ? 1.f : 0.f);
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before_sync();
+  // cluster-wide: every peer has started (its shared memory may be written) and this CTA's barriers / TMEM / table are set
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) B200VQA_STAMP(1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();  // A belongs to the previous kernel until here
+      B200VQA_STAMP(2);
+      for (int kb = 0; kb < kLnKb; ++kb) {
+        mbar_expect_tx(&full_bar[kb], kBM * kKBytes);
+        tma_load_2d(&tm_a, &full_bar[kb], smem + L::kOffA + kb * kBM * kKBytes, kb * 64, m0);
+      }
+      constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, kLnBN, 0, 0);
+      mbar_wait(w_full, 0);
+      for (int kb = 0; kb < kLnKb; ++kb) {
+        mbar_wait(&full_bar[kb], 0);
+        tc_fence_after_sync();
+        if (kb == 0) B200VQA_STAMP(4);
+        if (kb == kLnKb - 1) B200VQA_STAMP(5);
+        const uint32_t sa = smem_u32(smem + L::kOffA + kb * kBM * kKBytes);
+        const uint32_t sb = smem_u32(smem + L::kOffW + kb * kLnBN * kKBytes);
+#pragma unroll
+        for (int k = 0; k < kKBytes / kUmmaKBytes; ++k)
+          umma_bf16(tmem_base, make_smem_desc_sw128(sa + k * kUmmaKBytes, 16, 1024),
+                    make_smem_desc_sw128(sb + k * kUmmaKBytes, 16, 1024), idesc, (kb | k) != 0);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+    cluster_arrive_release();  // the statistics exchange barrier counts every thread of the cluster
+    cluster_wait_acquire();
+  } else {
+    const int ew = warp - 1;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const int row = m0 + row_in_tile;
+    const bool valid = row < p.M;
+    const int col0 = n0 + half * 32;
+    uint8_t* buf = smem + L::kOffStg + ew * 2048;
+    pdl_wait();  // the residual is the previous kernel's output
+    // residual chunk (32 rows x 64 B): coalesced 16-byte loads, transposed to a row per lane through shared memory
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rr = (lane >> 2) + 8 * k;
+      const int grow = m0 + quarter * 32 + rr;
+      const uint4 rv = grow < p.M
+                           ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + col0 + (lane & 3) * 8)
+                           : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(buf + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)) = rv;
+    }
+    __syncwarp();
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+      const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 res = unpack_bf16x2(w4[e]);
+        v[q * 8 + e * 2] = res.x + tab[half * 32 + q * 8 + e * 2];
+        v[q * 8 + e * 2 + 1] = res.y + tab[half * 32 + q * 8 + e * 2 + 1];
+      }
+    }
+    __syncwarp();
+    mbar_wait(acc_full, 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    if (ew == 0 && lane == 0) B200VQA_STAMP(6);
+    {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+    }
+    // exact statistics of this thread's 32 values, shared with every CTA of the cluster
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
+    const float mloc = s * (1.f / 32.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = v[j] - mloc;
+      m2 = fmaf(d, d, m2);
+    }
+    const uint32_t slot_addr = smem_u32(part + (int(rank) * 2 + half) * kBM + row_in_tile);
+#pragma unroll
+    for (uint32_t dst = 0; dst < kLnCl; ++dst) st_cluster_f32x2(cluster_map_shared(slot_addr, dst), mloc, m2);
+    if (ew == 0 && lane == 0) B200VQA_STAMP(10);
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (ew == 0 && lane == 0) B200VQA_STAMP(11);
+    float pm[2 * kLnCl], msum = 0.f, m2sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * kLnCl; ++i) {
+      const float2 pr = part[i * kBM + row_in_tile];
+      pm[i] = pr.x;
+      msum += pr.x;
+      m2sum += pr.y;
+    }
+    const float mean = msum * (1.f / (2 * kLnCl));
+    float dev = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * kLnCl; ++i) dev = fmaf(pm[i] - mean, pm[i] - mean, dev);
+    const float rstd = rsqrtf((m2sum + 32.f * dev) * (1.f / 256.f) + p.eps);
+
+    float* frow = (p.out_f32 && valid) ? p.out_f32 + size_t(row) * 256 + col0 : nullptr;
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(tab + kLnBN + half * 32 + j);
+      const float4 t4 = *reinterpret_cast<const float4*>(tab + 2 * kLnBN + half * 32 + j);
+      const float y0 = (v[j] - mean) * rstd * g4.x + t4.x;
+      const float y1 = (v[j + 1] - mean) * rstd * g4.y + t4.y;
+      const float y2 = (v[j + 2] - mean) * rstd * g4.z + t4.z;
+      const float y3 = (v[j + 3] - mean) * rstd * g4.w + t4.w;
+      o[j >> 1] = pack_bf16x2(y0, y1);
+      o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
+      if (frow) *reinterpret_cast<float4*>(frow + j) = make_float4(y0, y1, y2, y3);
+    }
+    store_chunk_bf16(buf, o, p.out, p.ldc, m0 + quarter * 32, col0, p.M, lane);
+    if (ew == 0 && lane == 0) B200VQA_STAMP(7);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<kLnBN>(tmem_base);
+  }
+  if (threadIdx.x == 0) B200VQA_STAMP(9);
+#undef B200VQA_STAMP
+}
+
+cudaError_t launch_ln_cluster(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
+                              cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         LnClSmem::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int tiles_m = (p.M + kBM - 1) / kBM;
+  if (tiles_m <= 0) return cudaSuccess;
+  return launch_kernel(gemm_ln_cluster_kernel, dim3(kLnCl, tiles_m), dim3(kLnThreads), LnClSmem::kBytes, stream, p.pdl,
+                       tm_a, tm_w, p);
+}
+
+// ------------------------------------------------------------------------------------------
 // Test-only CUDA-core check GEMM (fp32 accumulate, one output element per thread).
 // ------------------------------------------------------------------------------------------
 template <typename TA>
@@ -624,9 +853,13 @@ __global__ void gemm_check_kernel(const TA* __restrict__ A, const TA* __restrict
 
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                         const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.N % block_n != 0) return cudaErrorInvalidValue;
+  if (block_n <= 0 || p.N % block_n != 0) return cudaErrorInvalidValue;
   if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N)) return cudaErrorInvalidValue;
   if (epilogue == kEpiLstm && (block_n != 256 || p.N % 256 != 0)) return cudaErrorInvalidValue;
+  if (epilogue == kEpiBiasResLN && block_n == kLnBN) {  // cluster-of-4 variant for the decode-sized launches
+    if (p.N != 256 || p.K != 256 || tf32) return cudaErrorInvalidValue;
+    return launch_ln_cluster(tm_a, tm_w, p, stream);
+  }
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \

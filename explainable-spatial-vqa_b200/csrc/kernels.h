@@ -51,6 +51,7 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M = 0, N = 0, K = 0;
   bool pdl = false;                  // launch with programmatic dependent launch (decode chain)
+  bool ln_cluster = false;           // host-side: kEpiBiasResLN call site of the decode chain -> cluster-of-4 kernel
   long long* dbg_clk = nullptr;      // optional: CTA 0 writes clock64() stamps of its pipeline stages (tools/ only)
   const float* bias = nullptr;       // [N] fp32 (may be null)
   __nv_bfloat16* out = nullptr;      // bf16 output

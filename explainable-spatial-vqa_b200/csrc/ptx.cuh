@@ -134,6 +134,31 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Thread-block clusters: rank, cluster-wide barrier, stores into a peer CTA's shared memory (DSMEM)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster arrives; writes (local and remote) before the arrive are visible after wait
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address) in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_smem_addr), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, MMA, commit, loads
 // ----------------------------------------------------------------------------------------------
 template <uint32_t kCols>

@@ -46,7 +46,7 @@ def run(M, N, K, epi, bn, iters=200):
             print("   extra stamps:", ", ".join(extra))
 
 if __name__ == "__main__":
-    cfgs = [(1024, 256, 256, 2, 256), (1024, 256, 256, 0, 256), (1024, 256, 256, 0, 64), (1024, 768, 256, 0, 64),
+    cfgs = [(1024, 256, 256, 2, 256), (1024, 256, 256, 2, 64), (128, 256, 256, 2, 64), (1024, 256, 256, 0, 256), (1024, 256, 256, 0, 64), (1024, 768, 256, 0, 64),
             (128, 256, 256, 2, 256), (128, 256, 256, 0, 64), (1024, 256, 2048, 2, 256),
             (262144, 2048, 256, 1, 256), (262144, 256, 2048, 2, 256), (262144, 768, 256, 0, 256), (262144, 256, 256, 2, 256)]
     if len(sys.argv) > 1:
