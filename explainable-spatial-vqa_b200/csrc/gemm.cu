@@ -612,9 +612,9 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const C
 // The persistent kernel above gives a 128-row m-tile to ONE SM, whose epilogue then owns 128 x 256 values: at decode
 // sizes (1..8 m-tiles) that epilogue IS the kernel (12 k of 20 k cycles measured).  Here a cluster of 4 CTAs shares the
 // m-tile, each computing a 128 x 64 column slice (A tile 64 KB + W slice 32 KB per SM instead of 64 + 128 KB).  The
-// LayerNorm statistics are per-warp (mean, M2) pairs over 32 columns, written into every peer's shared memory
-// (st.shared::cluster), combined after one cluster barrier with the parallel-variance formula (exact two-pass
-// statistics per part, no E[x^2] - mean^2 cancellation).
+// LayerNorm statistics are per-thread (mean, M2) pairs over 32 columns, sent to every peer's shared memory with
+// st.async (the arriving bytes complete the receiver's mbarrier: no cluster-wide barrier on the critical path) and
+// combined with the parallel-variance formula (exact two-pass statistics per part, no E[x^2] - mean^2 cancellation).
 //   warp 0     : TMA loads + tcgen05.mma issue (one thread), owns the 64 TMEM columns
 //   warps 1..8 : epilogue; warp w reads TMEM lane quarter (w & 3), columns 32 * ((w - 1) >> 2) of the slice
 // ------------------------------------------------------------------------------------------
@@ -641,7 +641,8 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [kLnKb] A k-blocks
   uint64_t* w_full = full_bar + kLnKb;
   uint64_t* acc_full = w_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* stat_full = acc_full + 1;  // completes when all 2 * kLnCl statistic parts of the 128 rows have arrived
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 1);
   float* tab = reinterpret_cast<float*>(smem + L::kOffTab);
   float2* part = reinterpret_cast<float2*>(smem + L::kOffPart);
 
@@ -662,27 +663,31 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       for (int kb = 0; kb < kLnKb; ++kb) mbar_init(&full_bar[kb], 1);
       mbar_init(w_full, 1);
       mbar_init(acc_full, 1);
+      mbar_init(stat_full, 1);
       fence_mbar_init();
+      mbar_expect_tx(stat_full, 2 * kLnCl * kBM * 8);
       // weights do not depend on the previous kernel
       mbar_expect_tx(w_full, kLnKb * kLnBN * kKBytes);
       for (int kb = 0; kb < kLnKb; ++kb)
         tma_load_2d(&tm_w, w_full, smem + L::kOffW + kb * kLnBN * kKBytes, kb * 64, n0);
     }
-    __syncwarp();
+  } else if (warp == 1) {
     tmem_alloc<kLnBN>(tmem_slot);
-  } else {
-    // this slice's bias | gamma | beta (weights: safe before the dependency wait)
-    const int t = (warp - 1) * 32 + lane;
-    if (t < 3 * kLnBN) {
-      const float* src = t < kLnBN ? p.bias : (t < 2 * kLnBN ? p.gamma : p.beta);
-      tab[t] = src ? __ldg(src + n0 + (t & (kLnBN - 1))) : (t < 2 * kLnBN && t >= kLnBN ? 1.f : 0.f);
-    }
+  }
+  // this slice's bias | gamma | beta (weights: safe before the dependency wait).  Only requested here - the value is
+  // parked in shared memory after the residual loads are in flight, so no barrier waits for this L2 round trip
+  float tabv = 0.f;
+  const int tabi = (warp - 1) * 32 + lane;
+  if (warp >= 1 && tabi < 3 * kLnBN) {
+    const float* src = tabi < kLnBN ? p.bias : (tabi < 2 * kLnBN ? p.gamma : p.beta);
+    tabv = src ? __ldg(src + n0 + (tabi & (kLnBN - 1))) : (tabi >= kLnBN && tabi < 2 * kLnBN ? 1.f : 0.f);
   }
   pdl_launch_dependents();
   tc_fence_before_sync();
-  // cluster-wide: every peer has started (its shared memory may be written) and this CTA's barriers / TMEM / table are set
+  __syncthreads();  // this CTA's barriers and TMEM pointer are set
+  // cluster-wide "my barriers are initialised, my shared memory may be written": only arrive here, the wait sits right
+  // before the first store into a peer, where it has long completed
   cluster_arrive_release();
-  cluster_wait_acquire();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) B200VQA_STAMP(1);
@@ -712,7 +717,6 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       umma_commit(acc_full);
     }
     __syncwarp();
-    cluster_arrive_release();  // the statistics exchange barrier counts every thread of the cluster
     cluster_wait_acquire();
   } else {
     const int ew = warp - 1;
@@ -725,16 +729,21 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     uint8_t* buf = smem + L::kOffStg + ew * 2048;
     pdl_wait();  // the residual is the previous kernel's output
     // residual chunk (32 rows x 64 B): coalesced 16-byte loads, transposed to a row per lane through shared memory
+    uint4 rv4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int grow = m0 + quarter * 32 + (lane >> 2) + 8 * k;
+      rv4[k] = grow < p.M
+                   ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + col0 + (lane & 3) * 8)
+                   : make_uint4(0, 0, 0, 0);
+    }
+    if (tabi < 3 * kLnBN) tab[tabi] = tabv;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int rr = (lane >> 2) + 8 * k;
-      const int grow = m0 + quarter * 32 + rr;
-      const uint4 rv = grow < p.M
-                           ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + col0 + (lane & 3) * 8)
-                           : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(buf + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)) = rv;
+      *reinterpret_cast<uint4*>(buf + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)) = rv4[k];
     }
-    __syncwarp();
+    named_bar_sync(1, 8 * 32);  // table complete (all epilogue warps); also orders this warp's staging writes
     float v[32];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -771,12 +780,14 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       m2 = fmaf(d, d, m2);
     }
     const uint32_t slot_addr = smem_u32(part + (int(rank) * 2 + half) * kBM + row_in_tile);
-#pragma unroll
-    for (uint32_t dst = 0; dst < kLnCl; ++dst) st_cluster_f32x2(cluster_map_shared(slot_addr, dst), mloc, m2);
-    if (ew == 0 && lane == 0) B200VQA_STAMP(10);
+    const uint32_t bar_addr = smem_u32(stat_full);
     __syncwarp();
-    cluster_arrive_release();
-    cluster_wait_acquire();
+    cluster_wait_acquire();  // every peer has initialised its barriers (arrived at kernel start)
+#pragma unroll
+    for (uint32_t dst = 0; dst < kLnCl; ++dst)
+      st_async_f32x2(cluster_map_shared(slot_addr, dst), mloc, m2, cluster_map_shared(bar_addr, dst));
+    if (ew == 0 && lane == 0) B200VQA_STAMP(10);
+    mbar_wait(stat_full, 0);
     if (ew == 0 && lane == 0) B200VQA_STAMP(11);
     float pm[2 * kLnCl], msum = 0.f, m2sum = 0.f;
 #pragma unroll
@@ -812,7 +823,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<kLnBN>(tmem_base);
   }

@@ -157,6 +157,14 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_smem_addr,
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float x, float y) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
 }
+// asynchronous 8-byte store into a peer CTA's shared memory; its arrival performs complete_tx(8) on the mbarrier at
+// `cluster_mbar` (same peer), so the receiver needs no cluster-wide barrier: it waits on its own mbarrier
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float x, float y, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                   cluster_addr),
+               "f"(x), "f"(y), "r"(cluster_mbar)
+               : "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, MMA, commit, loads
