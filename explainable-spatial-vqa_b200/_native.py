@@ -87,6 +87,10 @@ SIGNATURES = {
     "b200vqa_profile_end": (C.c_int, [_vp, _vp, _vp]),
     "b200vqa_profile_delay": (C.c_int, [_vp, C.c_double, _vp]),
     "b200vqa_iqap_forward": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200vqa_iqap_forward_indexed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b200vqa_iqap_forward_host_indexed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
+                                                    _vp]),
+    "b200vqa_iqap_tally": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "b200vqa_iqap_forward_host_async": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),

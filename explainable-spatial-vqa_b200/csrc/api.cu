@@ -110,6 +110,8 @@ struct b200vqa_handle {
   uint8_t* wbase = nullptr;
   size_t wbytes = 0;
   float* img_w_f32 = nullptr;           // IQAP: tf32 operand [d, 1024]
+  __nv_bfloat16* img_tok = nullptr;     // IQAP indexed forward: image_proj + PE of the unique images [n_img, 196, d]
+  size_t img_tok_cap = 0;               // images the buffer holds
   __nv_bfloat16* img_w_bf16 = nullptr;  // FA: bf16 operand
   float *img_b = nullptr, *cls = nullptr, *enc_emb = nullptr, *dec_emb = nullptr, *pe_enc = nullptr, *pe_dec = nullptr;
   std::vector<LayerPacked> enc, dec;
@@ -826,14 +828,49 @@ int set_device(const b200vqa_handle* h) {
   return B200VQA_OK;
 }
 
+// image_proj (+bias +PE of rows 1..196) of n_img unique images into h->img_tok [first .. first + n_img)
+int project_unique_images(b200vqa_handle* h, const float* img, size_t first, int n_img, cudaStream_t s) {
+  const auto& d = h->d;
+  h->cur_tag = kTagImgProj;
+  GemmParams p;
+  p.bias = h->img_b;
+  p.out = h->img_tok + first * d.n_img_tokens * kD;
+  p.ldc = kD;
+  p.rows_in = d.n_img_tokens;
+  p.rows_out = d.n_img_tokens;
+  p.row_off = 0;
+  p.pe = h->pe_enc;
+  p.pe_off = 1;
+  return gemm(h, kEpiBiasPeRemap, true, img, n_img * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD, p,
+              s);
+}
+
+int ensure_img_tok(b200vqa_handle* h, size_t n_img) {
+  if (h->img_tok_cap >= n_img) return B200VQA_OK;
+  if (h->img_tok) {
+    B200VQA_CUDA_OK(cudaDeviceSynchronize());
+    B200VQA_CUDA_OK(cudaFree(h->img_tok));
+    h->img_tok = nullptr;
+    h->img_tok_cap = 0;
+    h->tmaps.clear();
+  }
+  B200VQA_CUDA_OK(cudaMalloc(&h->img_tok, n_img * h->d.n_img_tokens * kD * sizeof(__nv_bfloat16)));
+  h->img_tok_cap = n_img;
+  return B200VQA_OK;
+}
+
+// img != null: one feature block per question; otherwise image rows are gathered from h->img_tok by image_idx
 int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int T, float* answer, int64_t* programs,
-               float* step_logits, const int64_t* forced, float* opt_memory, int B_total, int b0, cudaStream_t s) {
+               float* step_logits, const int64_t* forced, float* opt_memory, int B_total, int b0, cudaStream_t s,
+               const int32_t* image_idx = nullptr, int n_img = 0) {
   Workspace& w = h->ws;
   const auto& d = h->d;
   const int S = 1 + d.n_img_tokens + d.max_q_len;
   h->cur_tag = kTagEmbed;
   LAUNCH_OK(h, launch_iqap_embed(q, B, d.max_q_len, h->cls, h->enc_emb, d.enc_vocab, h->pe_enc, d.n_img_tokens, w.x, s));
-  {
+  if (!img) {
+    LAUNCH_OK(h, launch_gather_image_rows(h->img_tok, image_idx, n_img, d.n_img_tokens, B, w.x, s));
+  } else {
     // image_proj straight from the caller's fp32 features (tf32 tensor-core math), +bias +PE, written into
     // rows 1..196 of each question's block (this is the reference's torch.cat, IQAP:164)
     h->cur_tag = kTagImgProj;
@@ -958,6 +995,7 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->wbase) cudaFree(h->wbase);
   if (h->stage) cudaFree(h->stage);
+  if (h->img_tok) cudaFree(h->img_tok);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
@@ -1051,6 +1089,57 @@ B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_featu
                      opt_forced_tokens ? opt_forced_tokens + size_t(b0) * program_len : nullptr, opt_memory, B, b0,
                      s));
   }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_forward_indexed(b200vqa_handle* h, const float* image_features, int n_img,
+                                             const int32_t* image_idx, const int64_t* questions, int B, int program_len,
+                                             float* answer, int64_t* programs, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0 && n_img >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(n_img >= 1, "questions without images");
+  B200VQA_REQUIRE(image_features && image_idx && questions && answer && programs, "a required buffer is NULL");
+  RC_OK(check_decode_len(h, program_len));
+  RC_OK(set_device(h));
+  RC_OK(ensure_workspace(h, B, program_len));
+  RC_OK(ensure_img_tok(h, size_t(n_img)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const auto& d = h->d;
+  RC_OK(project_unique_images(h, image_features, 0, n_img, s));
+  const int cap = h->ws.cap;
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int nb = std::min(cap, B - b0);
+    RC_OK(iqap_chunk(h, nullptr, questions + size_t(b0) * d.max_q_len, nb, program_len,
+                     answer + size_t(b0) * d.num_classes, programs + size_t(b0) * program_len, nullptr, nullptr, nullptr,
+                     B, b0, s, image_idx + b0, n_img));
+  }
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_tally(b200vqa_handle* h, const float* answer_logits, const int64_t* programs,
+                                   const int64_t* gt_answers, const int64_t* gt_programs, int B, int program_len,
+                                   uint64_t* counts, int32_t* opt_pred_answers, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0 && program_len >= 1, "shape out of range (B %d, program length %d)", B, program_len);
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(answer_logits && programs && gt_answers && gt_programs && counts, "a required buffer is NULL");
+  RC_OK(set_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TallyParams p;
+  p.B = B;
+  p.classes = h->d.num_classes;
+  p.T = program_len;
+  p.answer_logits = answer_logits;
+  p.programs = programs;
+  p.gt_answers = gt_answers;
+  p.gt_programs = gt_programs;
+  p.counts = reinterpret_cast<unsigned long long*>(counts);
+  p.pred_answers = opt_pred_answers;
+  h->cur_tag = kTagMisc;
+  LAUNCH_OK(h, launch_tally(p, s));
   return B200VQA_OK;
 }
 
@@ -1155,6 +1244,92 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const float* h_img, const i
   B200VQA_CUDA_OK(cudaMemcpyAsync(h_programs, d_prog, size_t(B) * program_len * sizeof(int64_t),
                                   cudaMemcpyDeviceToHost, s));
   if (sync) B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  return B200VQA_OK;
+}
+
+// Host buffers, several questions per image: the unique images are uploaded (double-buffered) and projected once, then
+// the questions run in chunks whose image rows are gathered on the device.
+B200VQA_API int b200vqa_iqap_forward_host_indexed(b200vqa_handle* h, const float* h_img, int n_img,
+                                                  const int32_t* h_image_idx, const int64_t* h_q, int B,
+                                                  int program_len, float* h_answer, int64_t* h_programs, int chunk,
+                                                  void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
+  B200VQA_REQUIRE(B >= 0 && n_img >= 0, "negative batch");
+  if (B == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(n_img >= 1, "questions without images");
+  B200VQA_REQUIRE(h_img && h_image_idx && h_q && h_answer && h_programs, "a required buffer is NULL");
+  RC_OK(check_decode_len(h, program_len));
+  RC_OK(set_device(h));
+  const auto& d = h->d;
+  if (chunk <= 0) chunk = 512;
+  chunk = std::min({chunk, B, default_cap(h)});
+  const int ichunk = std::min(n_img, 256);  // images per upload: 256 x 803 KB = 205 MB per staging buffer
+  RC_OK(ensure_workspace(h, chunk, program_len));
+  RC_OK(ensure_img_tok(h, size_t(n_img)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->copy_stream) {
+    B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
+  const size_t img_b = up(size_t(ichunk) * d.n_img_tokens * d.img_feat_dim * sizeof(float));
+  const size_t q_b = up(size_t(B) * d.max_q_len * sizeof(int64_t));
+  const size_t idx_b = up(size_t(B) * sizeof(int32_t));
+  const size_t ans_b = up(size_t(B) * d.num_classes * sizeof(float));
+  const size_t prog_b = up(size_t(B) * program_len * sizeof(int64_t));
+  const size_t need = 2 * img_b + q_b + idx_b + ans_b + prog_b;
+  if (h->stage_bytes < need) {
+    if (h->stage) {
+      B200VQA_CUDA_OK(cudaDeviceSynchronize());
+      B200VQA_CUDA_OK(cudaFree(h->stage));
+      h->stage = nullptr;
+      h->stage_bytes = 0;
+      h->tmaps.clear();
+    }
+    B200VQA_CUDA_OK(cudaMalloc(&h->stage, need));
+    h->stage_bytes = need;
+  }
+  uint8_t* p = h->stage;
+  float* d_img[2];
+  for (int i = 0; i < 2; ++i) { d_img[i] = reinterpret_cast<float*>(p); p += img_b; }
+  int64_t* d_q = reinterpret_cast<int64_t*>(p); p += q_b;
+  int32_t* d_idx = reinterpret_cast<int32_t*>(p); p += idx_b;
+  float* d_ans = reinterpret_cast<float*>(p); p += ans_b;
+  int64_t* d_prog = reinterpret_cast<int64_t*>(p);
+
+  // the copy stream must not overwrite staging that earlier work of `s` may still read
+  B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[0], s));
+  B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[0], 0));
+  B200VQA_CUDA_OK(cudaMemcpyAsync(d_q, h_q, size_t(B) * d.max_q_len * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                  h->copy_stream));
+  B200VQA_CUDA_OK(cudaMemcpyAsync(d_idx, h_image_idx, size_t(B) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                  h->copy_stream));
+  int it = 0;
+  const size_t per_img = size_t(d.n_img_tokens) * d.img_feat_dim;
+  for (int i0 = 0; i0 < n_img; i0 += ichunk, ++it) {
+    const int ni = std::min(ichunk, n_img - i0);
+    const int slot = it & 1;
+    if (it >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot], h_img + size_t(i0) * per_img, size_t(ni) * per_img * sizeof(float),
+                                    cudaMemcpyHostToDevice, h->copy_stream));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[slot], h->copy_stream));
+    B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[slot], 0));
+    RC_OK(project_unique_images(h, d_img[slot], size_t(i0), ni, s));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[slot], s));
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    RC_OK(iqap_chunk(h, nullptr, d_q + size_t(b0) * d.max_q_len, nb, program_len, d_ans + size_t(b0) * d.num_classes,
+                     d_prog + size_t(b0) * program_len, nullptr, nullptr, nullptr, B, b0, s, d_idx + b0, n_img));
+  }
+  B200VQA_CUDA_OK(cudaMemcpyAsync(h_answer, d_ans, size_t(B) * d.num_classes * sizeof(float), cudaMemcpyDeviceToHost, s));
+  B200VQA_CUDA_OK(cudaMemcpyAsync(h_programs, d_prog, size_t(B) * program_len * sizeof(int64_t),
+                                  cudaMemcpyDeviceToHost, s));
+  B200VQA_CUDA_OK(cudaStreamSynchronize(s));
   return B200VQA_OK;
 }
 

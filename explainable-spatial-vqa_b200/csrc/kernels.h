@@ -267,6 +267,22 @@ struct ProgToChainParams {
 };
 cudaError_t launch_programs_to_chain(const ProgToChainParams& p, cudaStream_t stream);
 
+// Evaluation tally (inference_transformer_iqap_tally.py:317-344); counts[4] u64 are accumulated, not reset.
+struct TallyParams {
+  int B = 0, classes = 0, T = 0;
+  const float* answer_logits = nullptr;   // [B, classes]
+  const int64_t* programs = nullptr;      // [B, T] generated
+  const int64_t* gt_answers = nullptr;    // [B]
+  const int64_t* gt_programs = nullptr;   // [B, T]
+  unsigned long long* counts = nullptr;   // {both, answer only, program only, neither}
+  int32_t* pred_answers = nullptr;        // optional [B]: argmax of the answer logits
+};
+cudaError_t launch_tally(const TallyParams& p, cudaStream_t stream);
+
+// Image rows of each question's block copied from per-image tokens (several questions per image).
+cudaError_t launch_gather_image_rows(const __nv_bfloat16* img_tok, const int32_t* image_idx, int n_img, int n_img_tokens,
+                                     int B, __nv_bfloat16* x, cudaStream_t stream);
+
 cudaError_t launch_delay(long long cycles, cudaStream_t stream);
 
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.

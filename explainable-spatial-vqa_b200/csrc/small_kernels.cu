@@ -349,6 +349,66 @@ cudaError_t launch_memory_export(const __nv_bfloat16* x, int S, int B, int ldb, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation tally on the device (reference inference_transformer_iqap_tally.py:317-344): per question
+// predicted answer = first maximum of the answer logits (torch.max), program correct = all T tokens equal;
+// counts[0..3] += {both correct, answer only, program only, neither}.  One warp per question.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tally_kernel(const TallyParams p) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = lane; c < p.classes; c += 32) {
+    const float v = p.answer_logits[size_t(b) * p.classes + c];
+    if (v > best || (v == best && c < arg) || arg == 0x7fffffff) { best = v; arg = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    // NaN never wins a comparison in torch.max unless it is present - logits are finite here; lowest index wins ties
+    if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+  }
+  bool same = true;
+  for (int t = lane; t < p.T; t += 32)
+    same &= p.programs[size_t(b) * p.T + t] == p.gt_programs[size_t(b) * p.T + t];
+  const bool prog_ok = __all_sync(0xffffffffu, same);
+  if (lane == 0) {
+    const bool ans_ok = int64_t(arg) == p.gt_answers[b];
+    if (p.pred_answers) p.pred_answers[b] = arg;
+    atomicAdd(p.counts + (ans_ok ? (prog_ok ? 0 : 1) : (prog_ok ? 2 : 3)), 1ull);
+  }
+}
+
+// x[b*kLP + 1 + pos] = img_tok[image_idx[b]*n_img_tokens + pos]  (16 bytes per thread; the image rows of a question's
+// block when several questions share one image: image_proj + PE were applied once per image)
+__global__ void __launch_bounds__(256) gather_image_rows_kernel(const __nv_bfloat16* __restrict__ img_tok,
+                                                                const int32_t* __restrict__ image_idx, int n_img,
+                                                                int n_img_tokens, __nv_bfloat16* __restrict__ x) {
+  const int b = blockIdx.y;
+  int img = image_idx[b];
+  img = img < 0 ? 0 : (img >= n_img ? n_img - 1 : img);
+  const uint4* src = reinterpret_cast<const uint4*>(img_tok + size_t(img) * n_img_tokens * kD);
+  uint4* dst = reinterpret_cast<uint4*>(x + (size_t(b) * kLP + 1) * kD);
+  const int n = n_img_tokens * kD / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+}
+
+cudaError_t launch_tally(const TallyParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  tally_kernel<<<(p.B + 7) / 8, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_image_rows(const __nv_bfloat16* img_tok, const int32_t* image_idx, int n_img, int n_img_tokens,
+                                     int B, __nv_bfloat16* x, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  gather_image_rows_kernel<<<dim3(4, B), 256, 0, stream>>>(img_tok, image_idx, n_img, n_img_tokens, x);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0_t, const float* b0, int hidden,
                                const float* w1, const float* b1, int classes, float* out, cudaStream_t stream) {
   if (hidden > 1024) return cudaErrorInvalidValue;

@@ -231,6 +231,77 @@ class VQAModel(nn.Module):
                       "b200vqa_iqap_forward_host")
         return answer, programs
 
+    # ------------------------------------------------------------------ feature ingest with image de-duplication
+    @torch.no_grad()
+    def forward_indexed(self, image_features, image_idx, questions):
+        """Several questions per image (CLEVR: ~10): image_features (n_img, 196, 1024) f32 holds every image once,
+        image_idx (B,) names each question's image - the `image_idxs` dataset of the question file
+        (VQADatasetSingleSample, IQAP:63-72).  image_proj runs once per image; the results equal
+        `forward(image_features[image_idx], questions)`."""
+        h = self._native()
+        img = self._check_input(image_features, "image_features", torch.float32)
+        q = self._check_input(questions, "questions", torch.int64)
+        idx = self._check_input(image_idx.to(torch.int32), "image_idx", torch.int32)
+        B, n_img, T = q.shape[0], img.shape[0], Config.PROGRAM_SEQ_LEN
+        if tuple(img.shape[1:]) != (self.num_image_tokens, self.image_proj.in_features):
+            raise ValueError(f"image_features must be (n_img, {self.num_image_tokens}, {self.image_proj.in_features})")
+        if idx.shape != (B,):
+            raise ValueError("image_idx must be (B,)")
+        if B and (int(idx.min()) < 0 or int(idx.max()) >= n_img):
+            raise IndexError("image_idx out of range")
+        answer = torch.empty(B, self.answer_classifier[3].out_features, dtype=torch.float32, device=img.device)
+        programs = torch.empty(B, T, dtype=torch.int64, device=img.device)
+        with torch.cuda.device(img.device):
+            nat.check(nat.lib().b200vqa_iqap_forward_indexed(h.raw, nat.ptr(img), n_img, nat.ptr(idx), nat.ptr(q), B, T,
+                                                             nat.ptr(answer), nat.ptr(programs),
+                                                             nat.stream_ptr(img.device)), "b200vqa_iqap_forward_indexed")
+        return answer, programs
+
+    @torch.no_grad()
+    def forward_host_indexed(self, image_features_cpu, image_idx_cpu, questions_cpu, chunk=512):
+        """`forward_indexed` with HOST tensors: each unique image crosses PCIe once."""
+        h = self._native()
+        img = image_features_cpu.to(torch.float32).contiguous()
+        q = questions_cpu.to(torch.int64).contiguous()
+        idx = image_idx_cpu.to(torch.int32).contiguous()
+        if img.is_cuda or q.is_cuda or idx.is_cuda:
+            raise ValueError("forward_host_indexed takes CPU tensors")
+        B, n_img, T = q.shape[0], img.shape[0], Config.PROGRAM_SEQ_LEN
+        if B and (int(idx.min()) < 0 or int(idx.max()) >= n_img):
+            raise IndexError("image_idx out of range")
+        answer = torch.empty(B, self.answer_classifier[3].out_features, dtype=torch.float32).pin_memory()
+        programs = torch.empty(B, T, dtype=torch.int64).pin_memory()
+        dev = self.image_proj.weight.device
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().b200vqa_iqap_forward_host_indexed(h.raw, nat.ptr(img), n_img, nat.ptr(idx), nat.ptr(q),
+                                                                  B, T, nat.ptr(answer), nat.ptr(programs), int(chunk),
+                                                                  nat.stream_ptr(dev)),
+                      "b200vqa_iqap_forward_host_indexed")
+        return answer, programs
+
+    # ------------------------------------------------------------------ evaluation tally on the device
+    @torch.no_grad()
+    def tally(self, answer_output, programs, gt_answers, gt_programs, counts=None):
+        """The four-way tally of inference_transformer_iqap_tally.run_inference (TALLY:317-344) without a host loop:
+        returns `counts` (4,) int64 on the device = {both correct, answer only, program only, neither}, accumulated
+        into the tensor passed in, and the predicted answers (B,) int32."""
+        h = self._native()
+        a = self._check_input(answer_output, "answer_output", torch.float32)
+        p = self._check_input(programs, "programs", torch.int64)
+        ga = self._check_input(gt_answers.to(torch.int64), "gt_answers", torch.int64)
+        gp = self._check_input(gt_programs.to(torch.int64), "gt_programs", torch.int64)
+        B, T = p.shape
+        if a.shape[0] != B or ga.shape != (B,) or tuple(gp.shape) != (B, T):
+            raise ValueError("tally: shapes disagree")
+        if counts is None:
+            counts = torch.zeros(4, dtype=torch.int64, device=a.device)
+        pred = torch.empty(B, dtype=torch.int32, device=a.device)
+        with torch.cuda.device(a.device):
+            nat.check(nat.lib().b200vqa_iqap_tally(h.raw, nat.ptr(a), nat.ptr(p), nat.ptr(ga), nat.ptr(gp), B, T,
+                                                   nat.ptr(counts), nat.ptr(pred), nat.stream_ptr(a.device)),
+                      "b200vqa_iqap_tally")
+        return counts, pred
+
     def native_launch_count(self) -> int:
         return self._pool.launch_count()
 

@@ -168,6 +168,29 @@ B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_featu
                          int program_len, float* answer, int64_t* programs, float* opt_step_logits,
                          const int64_t* opt_forced_tokens, float* opt_memory, void* stream);
 
+/* Feature ingest with image-level de-duplication.  CLEVR has ~10 questions per image and the
+ * question file carries `image_idxs` (reference preprocess_questions/preprocess_questions.py:122, read by
+ * VQADatasetSingleSample, IQAP:63-72): image_features [n_img,196,1024] f32 holds each image ONCE, image_idx [B] i32
+ * names the image of every question.  image_proj (+PE) runs once per image; results are identical to
+ * b200vqa_iqap_forward on the expanded [B,196,1024] features.  Device pointers; asynchronous on `stream`. */
+B200VQA_API int b200vqa_iqap_forward_indexed(b200vqa_handle* h, const float* image_features, int n_img,
+                                             const int32_t* image_idx, const int64_t* questions, int B, int program_len,
+                                             float* answer, int64_t* programs, void* stream);
+/* Same with HOST buffers: unique images are uploaded once (double-buffered against image_proj), then the questions
+ * run in chunks.  Returns once h_answer / h_programs are valid. */
+B200VQA_API int b200vqa_iqap_forward_host_indexed(b200vqa_handle* h, const float* h_image_features, int n_img,
+                                                  const int32_t* h_image_idx, const int64_t* h_questions, int B,
+                                                  int program_len, float* h_answer, int64_t* h_programs, int chunk,
+                                                  void* stream);
+
+/* Evaluation tally on the device (reference inference_transformer_iqap_tally.py:317-344):
+ * predicted answer = first maximum of answer_logits[b] (torch.max), program correct iff all program_len tokens
+ * match.  counts[4] u64 (device) are ACCUMULATED: {both correct, answer correct / program wrong, answer wrong /
+ * program correct, both wrong}.  opt_pred_answers NULL or [B] i32.  Device pointers; asynchronous on `stream`. */
+B200VQA_API int b200vqa_iqap_tally(b200vqa_handle* h, const float* answer_logits, const int64_t* programs,
+                                   const int64_t* gt_answers, const int64_t* gt_programs, int B, int program_len,
+                                   uint64_t* counts, int32_t* opt_pred_answers, void* stream);
+
 /* Replaces VQAModel.autoregressive_program_generation (IQAP:190-241) for a caller-supplied memory
  * [S,B,256] f32 (seq-first, S <= 256). */
 B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int S, int B, int program_len, int64_t* programs,

@@ -302,6 +302,20 @@ def fa_run_chain(sd, image_features, final_chain, rev_vocab, start_token, max_in
 # ------------------------------------------------------------------------------------------------
 # synthetic CLEVR-shaped workloads shared by the tests and bench.py
 # ------------------------------------------------------------------------------------------------
+def iqap_tally(answer_output, generated_programs, gt_answers, gt_programs):
+    """The per-sample tally of inference_transformer_iqap_tally.run_inference (TALLY:317-344) as a plain loop:
+    returns [both correct, answer only, program only, neither] and the predicted answers."""
+    counts, preds = [0, 0, 0, 0], []
+    for i in range(answer_output.shape[0]):
+        _, predicted = torch.max(answer_output[i:i + 1], 1)                      # TALLY:317-318
+        predicted = predicted.item()
+        preds.append(predicted)
+        answer_correct = predicted == int(gt_answers[i])                          # TALLY:327-330
+        program_correct = generated_programs[i].tolist() == gt_programs[i].tolist()  # TALLY:333
+        counts[(0 if program_correct else 1) if answer_correct else (2 if program_correct else 3)] += 1
+    return counts, preds
+
+
 def iqap_inputs(B, seed=1234, relu=True):
     g = torch.Generator().manual_seed(seed)
     img = torch.randn(B, 196, 1024, generator=g)

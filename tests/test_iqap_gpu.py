@@ -175,3 +175,65 @@ def test_pipelined_submit_matches_serial_forward(model):
          for i in range(2)]
     model.drain_host()
     assert torch.equal(torch.cat([o[0] for o in h]), ref_a.cpu()) and torch.equal(torch.cat([o[1] for o in h]), ref_p.cpu())
+
+
+def test_indexed_forward_equals_expanded_features(model):
+    """several questions per image.  image_proj once per image + gather must give bit-identical
+    results to feeding every question its own copy of the features (device and host entry points)."""
+    n_img, B = 7, 45
+    img, q = orc.iqap_inputs(B, seed=77)
+    img = img[:n_img]
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, n_img, (B,), generator=g, dtype=torch.int32)
+    idx[0], idx[1] = n_img - 1, 0
+    ref_a, ref_p = model(img[idx.long()].cuda(), q.cuda())
+    a, p = model.forward_indexed(img.cuda(), idx.cuda(), q.cuda())
+    assert torch.equal(p, ref_p) and torch.equal(a, ref_a)
+    ha, hp = model.forward_host_indexed(img.pin_memory(), idx, q, chunk=16)
+    assert torch.equal(hp, ref_p.cpu()) and torch.equal(ha, ref_a.cpu())
+    with pytest.raises(IndexError):
+        model.forward_indexed(img.cuda(), (idx + n_img).cuda(), q.cuda())
+    a0, p0 = model.forward_indexed(img.cuda(), idx[:0].cuda(), q[:0].cuda())
+    assert a0.shape == (0, 32) and p0.shape == (0, 27)
+
+
+def test_device_tally_matches_reference_loop(model):
+    """the four-way tally (TALLY:317-344) on the device vs the oracle's per-sample loop, with ties in
+    the answer logits (torch.max keeps the first maximum) and near-miss programs."""
+    B, T, C = 1003, 27, 32
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(B, C, generator=g)
+    logits[::7, 5] = logits[::7].max(1).values          # tie between an earlier / later column and column 5
+    logits[3] = 0.0                                     # all equal -> class 0
+    progs = torch.randint(0, 44, (B, T), generator=g)
+    gt_p = progs.clone()
+    wrong = torch.rand(B, generator=g) < 0.5
+    pos = torch.randint(0, T, (B,), generator=g)
+    gt_p[wrong, pos[wrong]] += 1                        # a single differing token, often the last one
+    gt_a = logits.argmax(1)
+    flip = torch.rand(B, generator=g) < 0.4
+    gt_a[flip] = (gt_a[flip] + 1) % C
+    want, want_pred = orc.iqap_tally(logits, progs, gt_a, gt_p)
+    counts, pred = model.tally(logits.cuda(), progs.cuda(), gt_a.cuda(), gt_p.cuda())
+    assert counts.tolist() == want and pred.tolist() == want_pred
+    assert min(want) > 0 and sum(want) == B
+    model.tally(logits.cuda(), progs.cuda(), gt_a.cuda(), gt_p.cuda(), counts)     # accumulates
+    assert counts.tolist() == [2 * w for w in want]
+
+
+def test_tally_dataset_driver(model):
+    """The batched driver (explainable-spatial-vqa_b200/inference_transformer_iqap_tally.py) over array-likes laid out like the
+    reference's H5 files: features (n_images,1024,14,14), image_idxs, questions, answers, programs."""
+    from explainable_spatial_vqa_b200 import inference_transformer_iqap_tally as tl
+    n_img, N = 5, 23
+    img, q = orc.iqap_inputs(N, seed=3)
+    feats = img[:n_img].transpose(1, 2).reshape(n_img, 1024, 14, 14).contiguous().numpy()
+    idx = np.random.RandomState(0).randint(0, n_img, N)
+    a, p = model(img[:n_img][torch.as_tensor(idx)].cuda(), q.cuda())
+    gt_a = a.argmax(1).cpu().numpy().copy()
+    gt_p = p.cpu().numpy().copy()
+    gt_a[:4] = (gt_a[:4] + 1) % 32          # 4 wrong answers
+    gt_p[2:9, 26] += 1                      # 7 wrong programs, two of them with wrong answers
+    t = tl.tally_dataset(model, feats, idx, q.numpy(), gt_a, gt_p, batch_size=10)
+    assert t == (N - 9, 5, 2, 2)
+    assert tl.tally_dataset(model, feats, idx, q.numpy(), gt_a, gt_p, max_samples=4, batch_size=3) == (0, 0, 2, 2)
