@@ -90,6 +90,8 @@ SIGNATURES = {
     "b200vqa_iqap_forward_indexed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host_indexed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                                     _vp]),
+    "b200vqa_iqap_forward_f16": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200vqa_iqap_forward_host_f16": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
     "b200vqa_iqap_tally": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200vqa_iqap_decode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b200vqa_iqap_forward_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),

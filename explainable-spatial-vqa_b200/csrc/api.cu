@@ -110,6 +110,7 @@ struct b200vqa_handle {
   uint8_t* wbase = nullptr;
   size_t wbytes = 0;
   float* img_w_f32 = nullptr;           // IQAP: tf32 operand [d, 1024]
+  __half* img_w_f16 = nullptr;          // IQAP: fp16 operand for the fp16 feature store (same 10-bit mantissa as tf32)
   __nv_bfloat16* img_tok = nullptr;     // IQAP indexed forward: image_proj + PE of the unique images [n_img, 196, d]
   size_t img_tok_cap = 0;               // images the buffer holds
   __nv_bfloat16* img_w_bf16 = nullptr;  // FA: bf16 operand
@@ -161,8 +162,10 @@ void layout_mha(Arena& a, MhaPacked& m, int d) {
 void layout_weights(b200vqa_handle* h, Arena& a) {
   const auto& d = h->d;
   const int D = d.d_model;
-  if (d.kind == B200VQA_MODEL_IQAP) h->img_w_f32 = a.take<float>(size_t(D) * d.img_feat_dim);
-  else h->img_w_bf16 = a.take<__nv_bfloat16>(size_t(D) * d.img_feat_dim);
+  if (d.kind == B200VQA_MODEL_IQAP) {
+    h->img_w_f32 = a.take<float>(size_t(D) * d.img_feat_dim);
+    h->img_w_f16 = a.take<__half>(size_t(D) * d.img_feat_dim);
+  } else h->img_w_bf16 = a.take<__nv_bfloat16>(size_t(D) * d.img_feat_dim);
   h->img_b = a.take<float>(D);
   h->cls = d.cls_token ? a.take<float>(D) : nullptr;
   h->enc_emb = a.take<float>(size_t(d.enc_vocab) * D);
@@ -223,6 +226,7 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
   const auto& d = h->d;
   const int D = d.d_model;
   if (h->img_w_f32) PACK_OK(copy_f32(h->img_w_f32, d.image_proj_weight, size_t(D) * d.img_feat_dim, s));
+  if (h->img_w_f16) PACK_OK(launch_cast_f16(d.image_proj_weight, h->img_w_f16, size_t(D) * d.img_feat_dim, s));
   else PACK_OK(launch_cast_bf16(d.image_proj_weight, h->img_w_bf16, size_t(D) * d.img_feat_dim, s));
   PACK_OK(copy_f32(h->img_b, d.image_proj_bias, D, s));
   if (h->cls) PACK_OK(copy_f32(h->cls, d.cls_token, D, s));
@@ -862,7 +866,7 @@ int ensure_img_tok(b200vqa_handle* h, size_t n_img) {
 // img != null: one feature block per question; otherwise image rows are gathered from h->img_tok by image_idx
 int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int T, float* answer, int64_t* programs,
                float* step_logits, const int64_t* forced, float* opt_memory, int B_total, int b0, cudaStream_t s,
-               const int32_t* image_idx = nullptr, int n_img = 0) {
+               const int32_t* image_idx = nullptr, int n_img = 0, bool f16 = false) {
   Workspace& w = h->ws;
   const auto& d = h->d;
   const int S = 1 + d.n_img_tokens + d.max_q_len;
@@ -883,8 +887,14 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
     p.row_off = 1;
     p.pe = h->pe_enc;
     p.pe_off = 1;
-    RC_OK(gemm(h, kEpiBiasPeRemap, true, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD, p,
-               s));
+    if (f16) {  // `img` holds fp16 features: kind::f16 MMA against the fp16 copy of the weight
+      p.f16 = true;
+      RC_OK(gemm(h, kEpiBiasPeRemap, false, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f16, kD,
+                 p, s));
+    } else {
+      RC_OK(gemm(h, kEpiBiasPeRemap, true, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD,
+                 p, s));
+    }
   }
   __nv_bfloat16* memory = nullptr;
   RC_OK(run_encoder(h, B, nullptr, S, &memory, s));
@@ -1066,9 +1076,9 @@ B200VQA_API int b200vqa_profile_end(b200vqa_handle* h, float* ms_per_tag, int32_
 }
 
 // ------------------------------------------------------------------------------------------------ IQAP
-B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_features, const int64_t* questions, int B,
-                         int program_len, float* answer, int64_t* programs, float* opt_step_logits,
-                         const int64_t* opt_forced_tokens, float* opt_memory, void* stream) {
+static int iqap_forward_impl(b200vqa_handle* h, const void* image_features, bool f16, const int64_t* questions, int B,
+                             int program_len, float* answer, int64_t* programs, float* opt_step_logits,
+                             const int64_t* opt_forced_tokens, float* opt_memory, void* stream) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
   B200VQA_REQUIRE(B >= 0, "negative batch");
@@ -1082,14 +1092,30 @@ B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_featu
   const int cap = h->ws.cap;
   for (int b0 = 0; b0 < B; b0 += cap) {
     const int nb = std::min(cap, B - b0);
-    RC_OK(iqap_chunk(h, image_features + size_t(b0) * d.n_img_tokens * d.img_feat_dim,
+    const size_t off = size_t(b0) * d.n_img_tokens * d.img_feat_dim * (f16 ? 2 : 4);
+    RC_OK(iqap_chunk(h, reinterpret_cast<const float*>(static_cast<const uint8_t*>(image_features) + off),
                      questions + size_t(b0) * d.max_q_len, nb, program_len, answer + size_t(b0) * d.num_classes,
                      programs + size_t(b0) * program_len,
                      opt_step_logits ? opt_step_logits + size_t(b0) * program_len * d.dec_vocab : nullptr,
                      opt_forced_tokens ? opt_forced_tokens + size_t(b0) * program_len : nullptr, opt_memory, B, b0,
-                     s));
+                     s, nullptr, 0, f16));
   }
   return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_iqap_forward(b200vqa_handle* h, const float* image_features, const int64_t* questions, int B,
+                         int program_len, float* answer, int64_t* programs, float* opt_step_logits,
+                         const int64_t* opt_forced_tokens, float* opt_memory, void* stream) {
+  return iqap_forward_impl(h, image_features, false, questions, B, program_len, answer, programs, opt_step_logits,
+                           opt_forced_tokens, opt_memory, stream);
+}
+
+B200VQA_API int b200vqa_iqap_forward_f16(b200vqa_handle* h, const void* image_features_f16, const int64_t* questions,
+                                         int B, int program_len, float* answer, int64_t* programs,
+                                         float* opt_step_logits, const int64_t* opt_forced_tokens, float* opt_memory,
+                                         void* stream) {
+  return iqap_forward_impl(h, image_features_f16, true, questions, B, program_len, answer, programs, opt_step_logits,
+                           opt_forced_tokens, opt_memory, stream);
 }
 
 B200VQA_API int b200vqa_iqap_forward_indexed(b200vqa_handle* h, const float* image_features, int n_img,
@@ -1175,8 +1201,10 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
   return B200VQA_OK;
 }
 
-static int iqap_forward_host_impl(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
-                                  float* h_answer, int64_t* h_programs, int chunk, void* stream, bool sync) {
+static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16, const int64_t* h_q, int B,
+                                  int program_len, float* h_answer, int64_t* h_programs, int chunk, void* stream,
+                                  bool sync) {
+  const size_t esz = f16 ? 2 : 4;  // bytes per feature element
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
   B200VQA_REQUIRE(B >= 0, "negative batch");
@@ -1197,7 +1225,7 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const float* h_img, const i
     }
   }
   // staging: 2 x (features + questions) for the double-buffered upload, + results for the whole batch
-  const size_t img_b = size_t(chunk) * d.n_img_tokens * d.img_feat_dim * sizeof(float);
+  const size_t img_b = (size_t(chunk) * d.n_img_tokens * d.img_feat_dim * esz + 255) & ~size_t(255);
   const size_t q_b = (size_t(chunk) * d.max_q_len * sizeof(int64_t) + 255) & ~size_t(255);
   const size_t ans_b = (size_t(B) * d.num_classes * sizeof(float) + 255) & ~size_t(255);
   const size_t prog_b = (size_t(B) * program_len * sizeof(int64_t) + 255) & ~size_t(255);
@@ -1228,16 +1256,17 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const float* h_img, const i
     const int nb = std::min(chunk, B - b0);
     const int slot = it & 1;
     if (it >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot], h_img + size_t(b0) * d.n_img_tokens * d.img_feat_dim,
-                                    size_t(nb) * d.n_img_tokens * d.img_feat_dim * sizeof(float),
-                                    cudaMemcpyHostToDevice, h->copy_stream));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot],
+                                    static_cast<const uint8_t*>(h_img) + size_t(b0) * d.n_img_tokens * d.img_feat_dim * esz,
+                                    size_t(nb) * d.n_img_tokens * d.img_feat_dim * esz, cudaMemcpyHostToDevice,
+                                    h->copy_stream));
     B200VQA_CUDA_OK(cudaMemcpyAsync(d_q[slot], h_q + size_t(b0) * d.max_q_len,
                                     size_t(nb) * d.max_q_len * sizeof(int64_t), cudaMemcpyHostToDevice,
                                     h->copy_stream));
     B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[slot], h->copy_stream));
     B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[slot], 0));
     RC_OK(iqap_chunk(h, d_img[slot], d_q[slot], nb, program_len, d_ans + size_t(b0) * d.num_classes,
-                     d_prog + size_t(b0) * program_len, nullptr, nullptr, nullptr, B, b0, s));
+                     d_prog + size_t(b0) * program_len, nullptr, nullptr, nullptr, B, b0, s, nullptr, 0, f16));
     B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[slot], s));
   }
   B200VQA_CUDA_OK(cudaMemcpyAsync(h_answer, d_ans, size_t(B) * d.num_classes * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1335,13 +1364,19 @@ B200VQA_API int b200vqa_iqap_forward_host_indexed(b200vqa_handle* h, const float
 
 B200VQA_API int b200vqa_iqap_forward_host(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B, int program_len,
                               float* h_answer, int64_t* h_programs, int chunk, void* stream) {
-  return iqap_forward_host_impl(h, h_img, h_q, B, program_len, h_answer, h_programs, chunk, stream, true);
+  return iqap_forward_host_impl(h, h_img, false, h_q, B, program_len, h_answer, h_programs, chunk, stream, true);
+}
+
+B200VQA_API int b200vqa_iqap_forward_host_f16(b200vqa_handle* h, const void* h_img_f16, const int64_t* h_q, int B,
+                                              int program_len, float* h_answer, int64_t* h_programs, int chunk,
+                                              void* stream) {
+  return iqap_forward_host_impl(h, h_img_f16, true, h_q, B, program_len, h_answer, h_programs, chunk, stream, true);
 }
 
 B200VQA_API int b200vqa_iqap_forward_host_async(b200vqa_handle* h, const float* h_img, const int64_t* h_q, int B,
                                                 int program_len, float* h_answer, int64_t* h_programs, int chunk,
                                                 void* stream) {
-  return iqap_forward_host_impl(h, h_img, h_q, B, program_len, h_answer, h_programs, chunk, stream, false);
+  return iqap_forward_host_impl(h, h_img, false, h_q, B, program_len, h_answer, h_programs, chunk, stream, false);
 }
 
 // ------------------------------------------------------------------------------------------------ FA

@@ -201,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, kBM, BN, 0, 0);
+      const uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : (p.f16 ? kFmtF16 : kFmtBF16), kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;

@@ -51,6 +51,7 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M = 0, N = 0, K = 0;
   bool pdl = false;                  // launch with programmatic dependent launch (decode chain)
+  bool f16 = false;                  // 2-byte operands are IEEE fp16 instead of bf16 (fp16 feature store -> image_proj)
   bool ln_cluster = false;           // host-side: kEpiBiasResLN call site of the decode chain -> cluster-of-4 kernel
   long long* dbg_clk = nullptr;      // optional: CTA 0 writes clock64() stamps of its pipeline stages (tools/ only)
   const float* bias = nullptr;       // [N] fp32 (may be null)
@@ -287,6 +288,7 @@ cudaError_t launch_delay(long long cycles, cudaStream_t stream);
 
 // Weight packing (run once per b200vqa_create / refresh): fp32 -> bf16 cast, fp32 [R,C] -> [C,R] transpose.
 cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t stream);
+cudaError_t launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
 cudaError_t launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t stream);
 
 }  // namespace b200vqa

@@ -232,6 +232,11 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
     out[i] = __float2bfloat16(in[i]);
 }
 
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
+
 __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -431,6 +436,13 @@ cudaError_t launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cuda
   if (n == 0) return cudaSuccess;
   const int grid = int(std::min<size_t>((n + 255) / 256, 4096));
   cast_bf16_kernel<<<grid, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int grid = int(std::min<size_t>((n + 255) / 256, 4096));
+  cast_f16_kernel<<<grid, 256, 0, stream>>>(in, out, n);
   return cudaGetLastError();
 }
 

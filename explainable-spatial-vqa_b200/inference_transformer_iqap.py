@@ -173,7 +173,9 @@ class VQAModel(nn.Module):
         `forced_programs` (B, 27) and returns the per-position program logits (B, 27, Vp) and the encoder
         memory (S, B, d) next to the reference's two outputs."""
         h = self._native(slot)
-        img = self._check_input(image_features, "image_features", torch.float32)
+        # fp16 features (the half-size feature store) are consumed as they are; everything else is the reference's fp32
+        f16 = image_features.dtype == torch.float16
+        img = self._check_input(image_features, "image_features", torch.float16 if f16 else torch.float32)
         q = self._check_input(questions, "questions", torch.int64)
         B = img.shape[0]
         T = Config.PROGRAM_SEQ_LEN
@@ -195,9 +197,9 @@ class VQAModel(nn.Module):
             if tuple(forced.shape) != (B, T):
                 raise ValueError(f"forced_programs must be (B, {T})")
         with torch.cuda.device(dev):
-            nat.check(nat.lib().b200vqa_iqap_forward(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
-                                                     nat.ptr(programs), nat.ptr(logits), nat.ptr(forced),
-                                                     nat.ptr(memory), nat.stream_ptr(dev)), "b200vqa_iqap_forward")
+            fn = nat.lib().b200vqa_iqap_forward_f16 if f16 else nat.lib().b200vqa_iqap_forward
+            nat.check(fn(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer), nat.ptr(programs), nat.ptr(logits),
+                         nat.ptr(forced), nat.ptr(memory), nat.stream_ptr(dev)), "b200vqa_iqap_forward")
         return answer, programs, logits, memory
 
     @torch.no_grad()
@@ -217,7 +219,8 @@ class VQAModel(nn.Module):
         """End-to-end call with HOST tensors (pinned for full PCIe speed): upload, compute and download are
         pipelined inside the library; returns CPU tensors.  This is what bench.py times as `e2e`."""
         h = self._native()
-        img = image_features_cpu.to(torch.float32).contiguous()
+        f16 = image_features_cpu.dtype == torch.float16   # fp16 feature store: half the PCIe bytes
+        img = image_features_cpu.to(torch.float16 if f16 else torch.float32).contiguous()
         q = questions_cpu.to(torch.int64).contiguous()
         if img.is_cuda or q.is_cuda:
             raise ValueError("forward_host takes CPU tensors; use forward() for device tensors")
@@ -226,9 +229,9 @@ class VQAModel(nn.Module):
         programs = torch.empty(B, T, dtype=torch.int64).pin_memory()
         dev = self.image_proj.weight.device
         with torch.cuda.device(dev):
-            nat.check(nat.lib().b200vqa_iqap_forward_host(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
-                                                          nat.ptr(programs), int(chunk), nat.stream_ptr(dev)),
-                      "b200vqa_iqap_forward_host")
+            fn = nat.lib().b200vqa_iqap_forward_host_f16 if f16 else nat.lib().b200vqa_iqap_forward_host
+            nat.check(fn(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer), nat.ptr(programs), int(chunk),
+                         nat.stream_ptr(dev)), "b200vqa_iqap_forward_host")
         return answer, programs
 
     # ------------------------------------------------------------------ feature ingest with image de-duplication

@@ -183,6 +183,18 @@ B200VQA_API int b200vqa_iqap_forward_host_indexed(b200vqa_handle* h, const float
                                                   int program_len, float* h_answer, int64_t* h_programs, int chunk,
                                                   void* stream);
 
+/* fp16 feature store: the same calls with image features held as IEEE fp16 - half the HBM / PCIe
+ * bytes of the reference's float32 HDF5 layout (preprocess_images/extract_features.py:124).  image_proj then runs as
+ * an fp16 x fp16 tensor-core GEMM with fp32 accumulation: fp16 carries the same 10-bit mantissa as the tf32 operands
+ * of the fp32 path, so the results agree to rounding (conv4 features are post-ReLU, far inside fp16's range). */
+B200VQA_API int b200vqa_iqap_forward_f16(b200vqa_handle* h, const void* image_features_f16, const int64_t* questions,
+                                         int B, int program_len, float* answer, int64_t* programs,
+                                         float* opt_step_logits, const int64_t* opt_forced_tokens, float* opt_memory,
+                                         void* stream);
+B200VQA_API int b200vqa_iqap_forward_host_f16(b200vqa_handle* h, const void* h_image_features_f16,
+                                              const int64_t* h_questions, int B, int program_len, float* h_answer,
+                                              int64_t* h_programs, int chunk, void* stream);
+
 /* Evaluation tally on the device (reference inference_transformer_iqap_tally.py:317-344):
  * predicted answer = first maximum of answer_logits[b] (torch.max), program correct iff all program_len tokens
  * match.  counts[4] u64 (device) are ACCUMULATED: {both correct, answer correct / program wrong, answer wrong /

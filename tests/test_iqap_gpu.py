@@ -237,3 +237,25 @@ def test_tally_dataset_driver(model):
     t = tl.tally_dataset(model, feats, idx, q.numpy(), gt_a, gt_p, batch_size=10)
     assert t == (N - 9, 5, 2, 2)
     assert tl.tally_dataset(model, feats, idx, q.numpy(), gt_a, gt_p, max_samples=4, batch_size=3) == (0, 0, 2, 2)
+
+
+def test_fp16_feature_store_matches_oracle(model):
+    """features held as fp16 (half the bytes).  Against the oracle fed the same fp16-rounded features
+    the gate is the usual 1e-2 (H1); against our own fp32/tf32 path on those features the two agree much closer,
+    because fp16 and tf32 carry the same mantissa width."""
+    B = 24
+    img, q = orc.iqap_inputs(B, seed=21)
+    img16 = img.half()
+    sd = cpu_sd(model)
+    ref = orc.iqap_forward(sd, img16.float(), q)
+    forced = ref["programs"]
+    a, p, logits, _ = model.forward_detailed(img16.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    want = orc.iqap_forward(sd, img16.float(), q, forced=forced)
+    assert common.rel_err(logits.cpu(), want["logits"]) < 1e-2
+    assert common.rel_err(a.cpu(), want["answer"]) < 1e-2
+    a32, p32, logits32, _ = model.forward_detailed(img16.float().cuda(), q.cuda(), forced_programs=forced.cuda(),
+                                                   want_logits=True)
+    assert common.rel_err(logits, logits32) < 6e-3   # both are bf16 pipelines after the projection: rounding-level
+    ha, hp = model.forward_host(img16.pin_memory(), q)
+    fa_, fp_ = model(img16.cuda(), q.cuda())
+    assert torch.equal(ha, fa_.cpu()) and torch.equal(hp, fp_.cpu())
