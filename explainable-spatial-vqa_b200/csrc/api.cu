@@ -126,6 +126,8 @@ struct b200vqa_handle {
   int cur_tag = kTagMisc;
   bool use_graphs = true;
   bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
+  int stagger_us = 0;          // start delay of every other decode branch (B200VQA_BRANCH_STAGGER_US)
+  int stagger_mod = 2;
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
@@ -436,6 +438,12 @@ int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, 
     ++(h)->launches;                                                                              \
   } while (0)
 
+#define LAUNCH_OK_S(h, expr, stream_) \
+  do {                               \
+    cudaStream_t s = (stream_);      \
+    LAUNCH_OK(h, expr);              \
+  } while (0)
+
 // out = epilogue(A[M,K] . W[N,K]^T + bias), A/W bf16 (or fp32 for tf32) row-major
 int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int lda, const void* W, int N,
          GemmParams p, cudaStream_t s) {
@@ -742,6 +750,14 @@ int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memo
     if (lo >= hi) break;
     cudaStream_t bs = i == 0 ? s : h->br_stream[i - 1];
     if (i > 0) B200VQA_CUDA_OK(cudaStreamWaitEvent(bs, h->br_fork, 0));
+    if (h->stagger_us > 0 && (i % h->stagger_mod) != 0) {
+      // identical branches run in lock step: all of them hit the HBM-bound cross-attention together and the
+      // latency-bound small kernels together.  A start offset de-phases them so the two kinds of work overlap.
+      int khz = 0;
+      B200VQA_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+      h->cur_tag = kTagMisc;
+      LAUNCH_OK_S(h, launch_delay((long long)(h->stagger_us) * (i % h->stagger_mod) * khz / 1000, bs), bs);
+    }
     rc = enqueue_decode_rows(h, lo, hi - lo, lens, const_len, io, bs);
     if (i > 0) {
       B200VQA_CUDA_OK(cudaEventRecord(h->br_done[i - 1], bs));
@@ -942,6 +958,8 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   h->device = device;
   h->num_sms = num_sms;
   if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
+  if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
+  if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));

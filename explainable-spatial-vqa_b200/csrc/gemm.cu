@@ -457,22 +457,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (other.x > best || (other.x == best && oi < besti)) { best = other.x; besti = oi; }
         named_bar_sync(1 + quarter, 64);  // xch is reused by the next tile
         if (besti >= p.head_V) besti = 0;  // all-NaN row: keep the index in range
-        if (valid) {
-          if (half == 0) p.tok[size_t(row) * p.tok_ld + p.head_t + 1] = besti;
-          if (p.pe_next) {
-            long long nxt = p.forced ? p.forced[size_t(row) * p.forced_ld + p.head_t] : (long long)besti;
-            nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
-            // next decoder input: this thread writes columns [128*half, 128*half + 128) of its row
-            const float* erow = p.emb + size_t(nxt) * kD + half * 128;
-            const float* prow = p.pe_next + half * 128;
-            __nv_bfloat16* xrow = p.x_next + size_t(row) * kD + half * 128;
-#pragma unroll 4
-            for (int j = 0; j < 128; j += 8) {
-              const float4 e0 = ldg4(erow + j), e1 = ldg4(erow + j + 4);
-              const float4 p0 = ldg4(prow + j), p1 = ldg4(prow + j + 4);
-              *reinterpret_cast<uint4*>(xrow + j) =
-                  make_uint4(pack_bf16x2(e0.x + p0.x, e0.y + p0.y), pack_bf16x2(e0.z + p0.z, e0.w + p0.w),
-                             pack_bf16x2(e1.x + p1.x, e1.y + p1.y), pack_bf16x2(e1.z + p1.z, e1.w + p1.w));
+        if (valid && half == 0) p.tok[size_t(row) * p.tok_ld + p.head_t + 1] = besti;
+        if (p.pe_next) {
+          // next decoder input x_next[row] = emb[next token] + pe[t+1].  The warp walks its 32 rows together: one
+          // row per iteration, 4 columns per lane of this warp's half [128*half, 128*half + 128) - coalesced 512-byte
+          // embedding reads and 256-byte stores (a row per lane would touch 32 different lines per instruction)
+          long long nxt = (valid && p.forced) ? p.forced[size_t(row) * p.forced_ld + p.head_t] : (long long)besti;
+          nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
+          const int nx = int(nxt);
+          const int colx = half * 128 + lane * 4;
+          const float4 pe4 = ldg4(p.pe_next + colx);
+          const int row0 = m0 + quarter * 32;
+          const int rows_here = p.M - row0;  // rows of this warp inside the matrix (may be <= 0 or > 32)
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int tr = __shfl_sync(0xffffffffu, nx, r);
+            if (r < rows_here) {
+              const float4 e = ldg4(p.emb + size_t(tr) * kD + colx);
+              *reinterpret_cast<uint2*>(p.x_next + size_t(row0 + r) * kD + colx) =
+                  make_uint2(pack_bf16x2(e.x + pe4.x, e.y + pe4.y), pack_bf16x2(e.z + pe4.z, e.w + pe4.w));
             }
           }
         }
