@@ -68,8 +68,9 @@ def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
         "dec_proj_gemm": ("tensor", n_dec * T * (2 * d * 3 * d + 2 * d * d)),     # self in_proj + cross q-proj
         "dec_outproj_ln_gemm": ("tensor", n_dec * T * 2 * 2 * d * d),            # two out-proj + LayerNorm
         "dec_ffn_split": ("tensor", n_dec * T * 4 * d * ff),
-        # HBM-bound: every step re-reads the projected K and V of the memory (bf16), SURVEY H2
-        "dec_cross_attention": ("hbm", n_dec * T * S * 2 * d * 2),
+        # HBM-bound: every decode position re-reads the encoder memory rows (bf16, 512 B per row) - the absorbed
+        # form of SURVEY H2; with B200VQA_NO_ABSORB=1 it reads a projected K and a V row instead (twice the bytes)
+        "dec_cross_attention": ("hbm", n_dec * T * S * d * 2 * (1 if ABSORB else 2)),
         "dec_self_attention": ("hbm", n_dec * sum((t + 1) * 2 * d * 2 for t in range(T))),
         "dec_head_argmax": ("tensor", T * 2 * d * Vp),
         "answer_head": ("hbm", d * 2 + C * 4),
@@ -79,6 +80,7 @@ def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
 
 
 IQAP_FLOPS_PER_QUESTION = 1.0983e9
+ABSORB = os.environ.get("B200VQA_NO_ABSORB", "0") in ("", "0")  # library default: absorbed cross-attention
 
 
 class ClockSampler:
@@ -479,8 +481,8 @@ def run_ours(args):
                 "dec_ffn_split": ("tensor", nstep * T_ * 4 * d_ * ff_),
                 "dec_head_argmax": ("tensor", nstep * T_ * 2 * d_ * V_),
                 "dec_self_attention": ("hbm", nstep * sum((t + 1) * 2 * d_ * 2 for t in range(T_))),
-                # HBM-bound: every decode position re-reads the projected K|V of the memory (1 KB per key row)
-                "dec_cross_attention": ("hbm", Lsum * 1024 * T_),
+                # HBM-bound: every decode position re-reads the memory rows (512 B each; K|V rows = 1 KB without absorption)
+                "dec_cross_attention": ("hbm", Lsum * (512 if ABSORB else 1024) * T_),
             }
 
         def roof(name):

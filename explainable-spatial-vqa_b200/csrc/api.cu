@@ -44,6 +44,9 @@ struct LayerPacked {
   __nv_bfloat16* w2 = nullptr;  // [d, ff]
   float* b2 = nullptr;
   float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr;
+  // decoder layers: absorbed cross-attention query weights, row h*d + i = W_k,h^T W_q,h (kernels.h: MemAttnParams)
+  __nv_bfloat16* w_qk = nullptr;  // [nhead*d, d]
+  float* b_qk = nullptr;          // [nhead*d]
 };
 
 // Bump allocator over one cudaMalloc'ed arena (first pass measures, second pass assigns).
@@ -67,6 +70,7 @@ struct Workspace {
   __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *x1 = nullptr, *hid = nullptr, *mem = nullptr;
   int32_t* lens = nullptr;
   std::vector<__nv_bfloat16*> ckv, kc, vc;
+  __nv_bfloat16* du = nullptr;     // absorbed cross-attention output [drows, nhead*256]
   __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dx1 = nullptr, *dq = nullptr, *dx2 = nullptr,
                 *dhid = nullptr, *dxo[2] = {nullptr, nullptr};
   float* dout = nullptr;
@@ -126,6 +130,7 @@ struct b200vqa_handle {
   int cur_tag = kTagMisc;
   bool use_graphs = true;
   bool pdl_chain = false;  // set while the decode loop is being enqueued: its kernels form a PDL chain
+  bool absorb = true;          // cross-attention reads the encoder memory directly (B200VQA_NO_ABSORB=1: K|V rows)
   int stagger_us = 0;          // start delay of every other decode branch (B200VQA_BRANCH_STAGGER_US)
   int stagger_mod = 2;
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
@@ -187,6 +192,8 @@ void layout_weights(b200vqa_handle* h, Arena& a) {
   for (auto& L : h->dec) {
     layout_mha(a, L.self_attn, D);
     layout_mha(a, L.cross_attn, D);
+    L.w_qk = a.take<__nv_bfloat16>(size_t(d.nhead) * D * D);
+    L.b_qk = a.take<float>(size_t(d.nhead) * D);
     L.w1 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
     L.b1 = a.take<float>(d.dim_ff);
     L.w2 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
@@ -229,7 +236,7 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
   const int D = d.d_model;
   if (h->img_w_f32) PACK_OK(copy_f32(h->img_w_f32, d.image_proj_weight, size_t(D) * d.img_feat_dim, s));
   if (h->img_w_f16) PACK_OK(launch_cast_f16(d.image_proj_weight, h->img_w_f16, size_t(D) * d.img_feat_dim, s));
-  else PACK_OK(launch_cast_bf16(d.image_proj_weight, h->img_w_bf16, size_t(D) * d.img_feat_dim, s));
+  if (h->img_w_bf16) PACK_OK(launch_cast_bf16(d.image_proj_weight, h->img_w_bf16, size_t(D) * d.img_feat_dim, s));
   PACK_OK(copy_f32(h->img_b, d.image_proj_bias, D, s));
   if (h->cls) PACK_OK(copy_f32(h->cls, d.cls_token, D, s));
   PACK_OK(copy_f32(h->enc_emb, d.enc_embedding, size_t(d.enc_vocab) * D, s));
@@ -252,6 +259,8 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
     auto& L = h->dec[l];
     PACK_OK(pack_mha(w.self_attn, L.self_attn, D, s));
     PACK_OK(pack_mha(w.multihead_attn, L.cross_attn, D, s));
+    PACK_OK(launch_absorb_qk(w.multihead_attn.in_proj_weight, w.multihead_attn.in_proj_bias, d.nhead, L.w_qk, L.b_qk,
+                             s));
     PACK_OK(launch_cast_bf16(w.linear1_weight, L.w1, size_t(d.dim_ff) * D, s));
     PACK_OK(copy_f32(L.b1, w.linear1_bias, d.dim_ff, s));
     PACK_OK(launch_cast_bf16(w.linear2_weight, L.w2, size_t(d.dim_ff) * D, s));
@@ -343,7 +352,7 @@ void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, 
   w.kc.resize(d.n_dec_layers);
   w.vc.resize(d.n_dec_layers);
   for (int l = 0; l < d.n_dec_layers; ++l) {
-    w.ckv[l] = a.take<__nv_bfloat16>(rows * 2 * kD);
+    w.ckv[l] = h->absorb ? nullptr : a.take<__nv_bfloat16>(rows * 2 * kD);
     w.kc[l] = a.take<__nv_bfloat16>(size_t(cap) * t_max * kD);
     w.vc[l] = a.take<__nv_bfloat16>(size_t(cap) * t_max * kD);
   }
@@ -353,7 +362,8 @@ void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, 
   w.dqkv = a.take<__nv_bfloat16>(drows * 3 * kD);
   w.dattn = a.take<__nv_bfloat16>(drows * kD);
   w.dx1 = a.take<__nv_bfloat16>(drows * kD);
-  w.dq = a.take<__nv_bfloat16>(drows * kD);
+  w.dq = a.take<__nv_bfloat16>(drows * d.nhead * kD);  // absorbed queries: nhead x 256 per row
+  w.du = a.take<__nv_bfloat16>(drows * d.nhead * kD);
   w.dx2 = a.take<__nv_bfloat16>(drows * kD);
   w.dhid = a.take<__nv_bfloat16>(drows * d.dim_ff);
   w.dxo[0] = a.take<__nv_bfloat16>(drows * kD);
@@ -446,7 +456,7 @@ int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, 
 
 // out = epilogue(A[M,K] . W[N,K]^T + bias), A/W bf16 (or fp32 for tf32) row-major
 int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int lda, const void* W, int N,
-         GemmParams p, cudaStream_t s) {
+         GemmParams p, cudaStream_t s, int a_cols = 0) {
   if (M <= 0) return B200VQA_OK;
   p.pdl = h->pdl_chain;
   const TmapType ty = tf32 ? TmapType::kF32 : TmapType::kBF16;
@@ -457,6 +467,7 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
     if (tiles_m * (N / 256) < h->num_sms / 2 && N % 128 == 0) bn = 128;
     if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0) bn = 64;
   }
+  if (p.a_group_cols > 0) bn = 64;  // grouped GEMM: an n-tile must not straddle two heads
   if (epi == kEpiHead) bn = N;  // N = padded vocabulary (one n-tile); rows >= V of W are zero-filled by TMA
   // the decode chain's out_proj + LayerNorm (M = questions): a cluster of four CTAs per 128-row tile (64-column slices,
   // statistics exchanged through distributed shared memory) instead of one SM owning the whole 128 x 256 epilogue.
@@ -465,7 +476,7 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
   if (epi == kEpiBiasResLN && p.ln_cluster && K == 256 && N == 256 && !h->no_ln_cluster) bn = 64;
   const CUtensorMap *ta, *tw, *to;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
-  RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(K), uint64_t(lda), 128, &ta));
+  RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(a_cols > 0 ? a_cols : K), uint64_t(lda), 128, &ta));
   RC_OK(get_tmap(h, W, ty, uint64_t(epi == kEpiHead ? p.head_V : N), uint64_t(K), uint64_t(K), bn, &tw));
   if (epi == kEpiBiasPeRemap || epi == kEpiHead) to = ta;  // unused by those epilogues
   else RC_OK(get_tmap(h, p.out, TmapType::kBF16, uint64_t(M), uint64_t(N), uint64_t(p.ldc), 32, &to, 32));
@@ -564,8 +575,8 @@ struct DecodeIO {
 // sequence can be captured once and replayed (run_decoder).
 // Decode positions 0..steps-1 for the questions [b_lo, b_lo + B) of the current chunk on stream `s`: a chain of
 // small kernels per position (PDL-linked).  `br` selects this branch's slice of the partial-sum buffer.
-int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens, int const_len, const DecodeIO& io,
-                        cudaStream_t s) {
+int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16* memory, const int32_t* lens,
+                        int const_len, const DecodeIO& io, cudaStream_t s) {
   Workspace& w = h->ws;
   const auto& d = h->d;
   const size_t r0 = size_t(b_lo);
@@ -573,7 +584,9 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
   __nv_bfloat16* dqkv = w.dqkv + r0 * 3 * kD;
   __nv_bfloat16* dattn = w.dattn + r0 * kD;
   __nv_bfloat16* dx1 = w.dx1 + r0 * kD;
-  __nv_bfloat16* dq = w.dq + r0 * kD;
+  __nv_bfloat16* dq = w.dq + r0 * d.nhead * kD;
+  __nv_bfloat16* du = w.du + r0 * d.nhead * kD;
+  const __nv_bfloat16* mem_b = memory + r0 * kLP * kD;
   __nv_bfloat16* dx2 = w.dx2 + r0 * kD;
   __nv_bfloat16* dxo[2] = {w.dxo[0] + r0 * kD, w.dxo[1] + r0 * kD};
   float* dout = w.dout + r0 * kD;
@@ -595,7 +608,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       __nv_bfloat16* out = dxo[l & 1];
       __nv_bfloat16* kc = w.kc[l] + r0 * w.t_max * kD;
       __nv_bfloat16* vc = w.vc[l] + r0 * w.t_max * kD;
-      const __nv_bfloat16* ckv = w.ckv[l] + r0 * kLP * 2 * kD;
+      const __nv_bfloat16* ckv = h->absorb ? nullptr : w.ckv[l] + r0 * kLP * 2 * kD;
       h->cur_tag = kTagDecGemm;
       RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, dqkv, s));
       RowAttnParams sp;
@@ -620,23 +633,50 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const int32_t* lens,
       LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s, true));
-      h->cur_tag = kTagDecGemm;
-      RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
-      RowAttnParams cp;
-      cp.B = B;
-      cp.nhead = d.nhead;
-      cp.q = dq;
-      cp.ldq = kD;
-      cp.k = ckv;
-      cp.v = ckv + kD;
-      cp.rows_per_q = kLP;
-      cp.ld = 2 * kD;
-      cp.lens = lens_b;
-      cp.const_len = const_len;
-      cp.out = dattn;
-      cp.pdl = true;
-      h->cur_tag = kTagDecCrossAttn;
-      LAUNCH_OK(h, launch_row_attn(cp, s));
+      if (h->absorb) {
+        // cross-attention on the encoder memory itself: absorbed queries (N = nhead*256), one pass over the memory
+        // rows for all heads, then the per-head value projection as a grouped GEMM
+        const int NHD = d.nhead * kD;
+        h->cur_tag = kTagDecGemm;
+        RC_OK(gemm_bias(h, false, dx1, B, kD, L.w_qk, NHD, L.b_qk, dq, s));
+        MemAttnParams mp;
+        mp.B = B;
+        mp.nhead = d.nhead;
+        mp.qp = dq;
+        mp.mem = mem_b;
+        mp.rows_per_q = kLP;
+        mp.lens = lens_b;
+        mp.const_len = const_len;
+        mp.out = du;
+        mp.pdl = true;
+        h->cur_tag = kTagDecCrossAttn;
+        LAUNCH_OK(h, launch_mem_attn(mp, s));
+        GemmParams vp;
+        vp.bias = L.cross_attn.b_in + 2 * kD;
+        vp.out = dattn;
+        vp.ldc = kD;
+        vp.a_group_cols = kD / d.nhead;
+        h->cur_tag = kTagDecGemm;
+        RC_OK(gemm(h, kEpiBias, false, du, B, kD, NHD, L.cross_attn.w_in + size_t(2) * kD * kD, kD, vp, s, NHD));
+      } else {
+        h->cur_tag = kTagDecGemm;
+        RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
+        RowAttnParams cp;
+        cp.B = B;
+        cp.nhead = d.nhead;
+        cp.q = dq;
+        cp.ldq = kD;
+        cp.k = ckv;
+        cp.v = ckv + kD;
+        cp.rows_per_q = kLP;
+        cp.ld = 2 * kD;
+        cp.lens = lens_b;
+        cp.const_len = const_len;
+        cp.out = dattn;
+        cp.pdl = true;
+        h->cur_tag = kTagDecCrossAttn;
+        LAUNCH_OK(h, launch_row_attn(cp, s));
+      }
       h->cur_tag = kTagDecGemmLn;
       RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s,
                         true));
@@ -699,7 +739,7 @@ int enqueue_decode_prologue(b200vqa_handle* h, int B, const __nv_bfloat16* memor
   const auto& d = h->d;
   const int M = B * kLP;
   h->cur_tag = kTagDecCrossKv;
-  for (int l = 0; l < d.n_dec_layers; ++l) {
+  for (int l = 0; l < d.n_dec_layers && !h->absorb; ++l) {
     const MhaPacked& ca = h->dec[l].cross_attn;
     RC_OK(gemm_bias(h, false, memory, M, kD, ca.w_in + size_t(kD) * kD, 2 * kD, ca.b_in + kD, w.ckv[l], s));
   }
@@ -722,7 +762,7 @@ int enqueue_decode_prologue(b200vqa_handle* h, int B, const __nv_bfloat16* memor
 int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
                     const DecodeIO& io, cudaStream_t s) {
   RC_OK(enqueue_decode_prologue(h, B, memory, io, s));
-  return enqueue_decode_rows(h, 0, B, lens, const_len, io, s);
+  return enqueue_decode_rows(h, 0, B, memory, lens, const_len, io, s);
 }
 
 // Graph-capture form: the batch is split into independent branches (questions never interact) that the GPU runs
@@ -733,7 +773,7 @@ int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memo
   RC_OK(enqueue_decode_prologue(h, B, memory, io, s));
   int nbr = h->decode_branches;
   while (nbr > 1 && B / nbr < 128) --nbr;
-  if (nbr <= 1) return enqueue_decode_rows(h, 0, B, lens, const_len, io, s);
+  if (nbr <= 1) return enqueue_decode_rows(h, 0, B, memory, lens, const_len, io, s);
   for (int i = 0; i < nbr - 1; ++i) {
     if (!h->br_stream[i]) {
       B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking));
@@ -758,7 +798,7 @@ int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memo
       h->cur_tag = kTagMisc;
       LAUNCH_OK_S(h, launch_delay((long long)(h->stagger_us) * (i % h->stagger_mod) * khz / 1000, bs), bs);
     }
-    rc = enqueue_decode_rows(h, lo, hi - lo, lens, const_len, io, bs);
+    rc = enqueue_decode_rows(h, lo, hi - lo, memory, lens, const_len, io, bs);
     if (i > 0) {
       B200VQA_CUDA_OK(cudaEventRecord(h->br_done[i - 1], bs));
       B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->br_done[i - 1], 0));
@@ -958,6 +998,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   h->device = device;
   h->num_sms = num_sms;
   if (const char* g = getenv("B200VQA_NO_GRAPH")) h->use_graphs = !(g[0] && g[0] != '0');
+  if (const char* g = getenv("B200VQA_NO_ABSORB")) h->absorb = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';

@@ -170,6 +170,185 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Absorbed cross-attention (MemAttnParams, kernels.h): one CTA (8 warps) per question, ONE pass over the memory.
+//
+// The memory rows m_j (256 bf16 = 512 B) stream through a 3-stage shared-memory ring of 64-row tiles (cp.async, rows
+// past the length zero-filled); every tile is consumed once with an online softmax, so HBM traffic per question is
+// len * 512 B - half of reading a projected K row and a V row - and nothing is re-read.  With NH query vectors per
+// row a CUDA-core form needs 8*NH FMAs per 16 loaded bytes and is issue-bound (measured 66 us per 1024 questions vs
+// 47 us for the K|V kernel), so both contractions run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate):
+//   scores  S[j, h] = sum_d M[j, d] q'[h, d]   A = memory tile (ldmatrix), B = absorbed queries (registers, heads padded
+//                                              to the 8 MMA columns); warp w takes rows 16 (w & 3), half (w >> 2) of d
+//   values  U[h, d] += sum_j P[h, j] M[j, d]   A = exp2(S - running max) (heads padded to the 16 MMA rows), B = the same
+//                                              tile through ldmatrix.trans; warp w owns output columns [32 w, 32 w + 32)
+// Every warp tracks the running max / sum of "its" head redundantly, so no cross-warp merge is needed at the end.
+// Shared rows are padded to 528 B so the eight row addresses of an ldmatrix hit different banks.  (A 128-row tcgen05
+// atom would be 97% padding here: 2-4 query rows per question.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMemTileRows = 64;
+constexpr int kMemRowBytes = kD * 2 + 16;
+constexpr int kMemStages = 3;
+constexpr int kMemStageBytes = kMemTileRows * kMemRowBytes;
+constexpr int kMemAttnSmem = kMemStages * kMemStageBytes;
+constexpr int kScPad = kMemTileRows + 8;  // row pitch of the score exchange: heads land in different banks
+
+template <int NH>
+__global__ void __launch_bounds__(kAttnWarps * 32, 2) mem_attn_kernel(const MemAttnParams p) {
+  static_assert(NH == 2 || NH == 4, "heads");
+  extern __shared__ __align__(16) uint8_t ring[];
+  __shared__ float s_part[2][NH][kScPad];  // partial scores of the current tile (two halves of d)
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int kh = warp >> 2;  // half of the 256 channels this warp contracts in the score MMA
+  constexpr uint32_t kHeadLanes = (1u << (4 * NH)) - 1u;  // lanes whose fragment row g is a real head
+  pdl_launch_dependents();
+  pdl_wait();
+  int len = p.lens ? p.lens[b] : p.const_len;
+  len = len > kLP ? kLP : len;
+  const int n_tiles = (len + kMemTileRows - 1) / kMemTileRows;
+  const uint8_t* mbase = reinterpret_cast<const uint8_t*>(p.mem + size_t(b) * p.rows_per_q * kD);
+  const uint32_t ring_u32 = smem_u32(ring);
+
+  auto issue = [&](int i) {  // tile i -> stage i % kMemStages
+    if (i < n_tiles) {
+      const uint32_t dst = ring_u32 + (i % kMemStages) * kMemStageBytes;
+#pragma unroll
+      for (int c = 0; c < kMemTileRows * 32 / (kAttnWarps * 32); ++c) {
+        const int chunk = c * (kAttnWarps * 32) + threadIdx.x;  // 32 16-byte chunks per row
+        const int r = chunk >> 5, col = chunk & 31;
+        const int j = i * kMemTileRows + r;
+        cp_async_16(dst + r * kMemRowBytes + col * 16, mbase + size_t(j < len ? j : 0) * (kD * 2) + col * 16,
+                    j < len ? 16u : 0u);
+      }
+    }
+    cp_async_commit();  // (possibly empty) group: keeps the group count in step with the tile number
+  };
+  for (int i = 0; i < kMemStages - 1; ++i) issue(i);
+
+  // absorbed queries as B fragments of this warp's channel half: bq[k] = q'[head g][16 ks + 2 q4 + {0,1}],
+  // [.. + 8 + {0,1}] with ks = 8 kh + k; heads >= NH are zero columns
+  uint32_t bq[8][2];
+  {
+    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(p.qp + (size_t(b) * NH + (g < NH ? g : 0)) * kD) + kh * 64;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      bq[k][0] = g < NH ? __ldg(qrow + k * 8 + q4) : 0u;
+      bq[k][1] = g < NH ? __ldg(qrow + k * 8 + q4 + 4) : 0u;
+    }
+  }
+  const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
+
+  float m_run = -INFINITY, l_run = 0.f;  // running max / (per-lane partial) sum of head g
+  float acc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+
+  for (int i = 0; i < n_tiles; ++i) {
+    cp_async_wait<kMemStages - 2>();
+    __syncthreads();  // tile i has landed for every thread; stage (i-1) % S and s_part are free again
+    issue(i + kMemStages - 1);
+    const uint32_t tile_u32 = ring_u32 + (i % kMemStages) * kMemStageBytes;
+    {
+      // partial scores of rows [16 (w & 3), +16) over channels [128 kh, +128)
+      const uint32_t a_addr =
+          tile_u32 + ((warp & 3) * 16 + (lane & 15)) * kMemRowBytes + (lane >> 4) * 16 + kh * 256;
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        uint32_t a0[4], a1[4];
+        ldmatrix_x4(a_addr + k * 32, a0);
+        ldmatrix_x4(a_addr + k * 32 + 32, a1);
+        mma_bf16_16816(c0, a0, bq[k][0], bq[k][1]);
+        mma_bf16_16816(c1, a1, bq[k + 1][0], bq[k + 1][1]);
+      }
+      // c[0,1] = S[row g][heads 2 q4, 2 q4 + 1], c[2,3] = the same heads of row g + 8
+      if (2 * q4 < NH) {
+        const int r = (warp & 3) * 16 + g;
+        s_part[kh][2 * q4][r] = (c0[0] + c1[0]) * sl2;
+        s_part[kh][2 * q4 + 1][r] = (c0[1] + c1[1]) * sl2;
+        s_part[kh][2 * q4][r + 8] = (c0[2] + c1[2]) * sl2;
+        s_part[kh][2 * q4 + 1][r + 8] = (c0[3] + c1[3]) * sl2;
+      }
+    }
+    __syncthreads();
+    // softmax weights of head g for the 64 rows, in A-fragment order: pa[ks][0] = rows 16 ks + 2 q4 + {0,1},
+    // pa[ks][2] = rows 16 ks + 8 + 2 q4 + {0,1}; fragment rows >= NH (registers 1 and 3) stay zero
+    uint32_t pa[kMemTileRows / 16][4];
+    if (g < NH) {
+      float sv[kMemTileRows / 16][4];
+      float mt = -INFINITY;
+      const int jbase = i * kMemTileRows;
+#pragma unroll
+      for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = ks * 16 + 2 * q4 + (e & 1) + (e >> 1) * 8;
+          const float s = s_part[0][g][j] + s_part[1][g][j];
+          sv[ks][e] = (jbase + j < len) ? s : -INFINITY;
+          mt = fmaxf(mt, sv[ks][e]);
+        }
+      }
+      mt = fmaxf(mt, __shfl_xor_sync(kHeadLanes, mt, 1));
+      mt = fmaxf(mt, __shfl_xor_sync(kHeadLanes, mt, 2));
+      const float m_new = fmaxf(m_run, mt);  // finite: every tile holds at least one valid row
+      const float alpha = exp2f(m_run - m_new);
+      m_run = m_new;
+      float ls = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
+        float pe[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pe[e] = exp2f(sv[ks][e] - m_new);
+          ls += pe[e];
+        }
+        pa[ks][0] = pack_bf16x2(pe[0], pe[1]);
+        pa[ks][1] = 0u;
+        pa[ks][2] = pack_bf16x2(pe[2], pe[3]);
+        pa[ks][3] = 0u;
+      }
+      l_run = l_run * alpha + ls;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] *= alpha;
+        acc[nt][1] *= alpha;
+      }
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < kMemTileRows / 16; ++ks) pa[ks][0] = pa[ks][1] = pa[ks][2] = pa[ks][3] = 0u;
+    }
+    __syncwarp();
+    // ldmatrix.trans addresses: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, columns 32 w + pair * 16 + (m >> 1) * 8
+    const uint32_t b_addr =
+        tile_u32 + (((lane >> 3) & 1) * 8 + (lane & 7)) * kMemRowBytes + (warp * 32 + (lane >> 4) * 8) * 2;
+#pragma unroll
+    for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
+#pragma unroll
+      for (int pair = 0; pair < 2; ++pair) {
+        uint32_t bm[4];
+        ldmatrix_x4_trans(b_addr + ks * 16 * kMemRowBytes + pair * 32, bm);
+        mma_bf16_16816(acc[2 * pair], pa[ks], bm[0], bm[1]);
+        mma_bf16_16816(acc[2 * pair + 1], pa[ks], bm[2], bm[3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  // acc[nt][0,1] = U[head g][32 w + 8 nt + 2 q4 + {0,1}] (un-normalised); the sum is spread over the quad
+  if (g < NH) {
+    l_run += __shfl_xor_sync(kHeadLanes, l_run, 1);
+    l_run += __shfl_xor_sync(kHeadLanes, l_run, 2);
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* orow = p.out + (size_t(b) * NH + g) * kD + warp * 32 + 2 * q4;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+  }
+}
+
 __global__ void publish_tokens_kernel(const PublishParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * p.n_cols) return;
@@ -196,6 +375,23 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
   const int dh = kD / p.nhead;
   if (dh == 64) return launch_kernel(row_attn_kernel<64>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
   if (dh == 128) return launch_kernel(row_attn_kernel<128>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_mem_attn(const MemAttnParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(mem_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMemAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mem_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMemAttnSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (p.nhead == 4)
+    return launch_kernel(mem_attn_kernel<4>, dim3(p.B), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, p);
+  if (p.nhead == 2)
+    return launch_kernel(mem_attn_kernel<2>, dim3(p.B), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, p);
   return cudaErrorInvalidValue;
 }
 

@@ -176,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int nt = tile / tiles_m;
         const int m0 = (tile - nt * tiles_m) * kBM;
         const int n0 = nt * BN;
+        const int a_koff = p.a_group_cols > 0 ? (n0 / p.a_group_cols) * p.K : 0;  // grouped GEMM: A columns of this head
         if (wstat && nt != cur_n) {
           mbar_wait(w_empty, wphase ^ 1);  // every MMA that read the previous W has retired
           mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
@@ -187,11 +188,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (wstat) {
             mbar_expect_tx(&full_bar[stage], L::kStageA);
-            tma_load_2d(&tm_a, &full_bar[stage], sAring + stage * L::kStageA, kb * bk, m0);
+            tma_load_2d(&tm_a, &full_bar[stage], sAring + stage * L::kStageA, kb * bk + a_koff, m0);
           } else {
             uint8_t* sa = smem + stage * (L::kStageA + L::kStageB);
             mbar_expect_tx(&full_bar[stage], L::kStageA + L::kStageB);
-            tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk, m0);
+            tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk + a_koff, m0);
             tma_load_2d(&tm_w, &full_bar[stage], sa + L::kStageA, kb * bk, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }

@@ -51,6 +51,8 @@ enum GemmEpilogue : int {
 struct GemmParams {
   int M = 0, N = 0, K = 0;
   bool pdl = false;                  // launch with programmatic dependent launch (decode chain)
+  int a_group_cols = 0;              // > 0: grouped GEMM - the n-tile at column n0 reads A columns
+                                     // [(n0 / a_group_cols) * K, +K) (per-head value projection of absorbed attention)
   bool f16 = false;                  // 2-byte operands are IEEE fp16 instead of bf16 (fp16 feature store -> image_proj)
   bool ln_cluster = false;           // host-side: kEpiBiasResLN call site of the decode chain -> cluster-of-4 kernel
   long long* dbg_clk = nullptr;      // optional: CTA 0 writes clock64() stamps of its pipeline stages (tools/ only)
@@ -216,6 +218,29 @@ struct RowAttnParams {
   __nv_bfloat16* out = nullptr;      // [B, kD]
 };
 cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream);
+
+// Cross-attention of one decode position straight from the encoder memory ("absorbed" projections):
+//   scores_h[j] = (W_k,h^T q_h) . m_j / sqrt(dh)      (the key bias adds a per-head constant: softmax-invariant)
+//   u_h        = sum_j softmax(scores_h)[j] m_j       (the value projection W_v,h u_h + b_v,h follows as a GEMM)
+// so a decode position reads the memory rows (512 B each) once from HBM instead of a K row and a V row, and the
+// per-question K|V projection of the memory disappears.  qp [B, nhead*256] bf16 = absorbed queries W_k,h^T q_h,
+// mem [B*rows_per_q, 256] bf16, out u [B, nhead*256] bf16.
+struct MemAttnParams {
+  int B = 0, nhead = 4;
+  bool pdl = false;
+  const __nv_bfloat16* qp = nullptr;
+  const __nv_bfloat16* mem = nullptr;
+  long long rows_per_q = 0;
+  const int32_t* lens = nullptr;     // [B] or null -> const_len
+  int const_len = 0;
+  __nv_bfloat16* out = nullptr;
+};
+cudaError_t launch_mem_attn(const MemAttnParams& p, cudaStream_t stream);
+
+// Weight packing for the absorbed cross-attention: in_proj_weight [3d, d] / in_proj_bias [3d] fp32 ->
+//   w_qk [nhead*d, d] bf16, row h*d + i = sum_e W_k[h*dh+e][i] * W_q[h*dh+e][:]     b_qk [nhead*d] likewise with b_q
+cudaError_t launch_absorb_qk(const float* in_proj_weight, const float* in_proj_bias, int nhead, __nv_bfloat16* w_qk,
+                             float* b_qk, cudaStream_t stream);
 
 // tok[B, tok_ld] -> caller layout.
 //   out_i64 : out[b*out_ld + j] = tok[b, src_col0 + j], j < n_cols                       (IQAP programs, FA `ys`)

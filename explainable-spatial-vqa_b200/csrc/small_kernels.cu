@@ -401,6 +401,31 @@ __global__ void __launch_bounds__(256) gather_image_rows_kernel(const __nv_bfloa
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
 }
 
+// Absorbed query-key weights of one cross-attention block (kernels.h: launch_absorb_qk).  Block = one output row
+// (head h, memory channel i), thread = input channel d; fp32 accumulation over the head dimension.
+__global__ void __launch_bounds__(kD) absorb_qk_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                                       int nhead, __nv_bfloat16* __restrict__ w_qk,
+                                                       float* __restrict__ b_qk) {
+  const int dh = kD / nhead;
+  const int h = blockIdx.x / kD, i = blockIdx.x % kD, d = threadIdx.x;
+  const float* wq = w_in;                    // rows 0 .. d-1
+  const float* wk = w_in + size_t(kD) * kD;  // rows d .. 2d-1
+  float acc = 0.f, accb = 0.f;
+  for (int e = 0; e < dh; ++e) {
+    const float k = wk[size_t(h * dh + e) * kD + i];
+    acc = fmaf(k, wq[size_t(h * dh + e) * kD + d], acc);
+    accb = fmaf(k, b_in[h * dh + e], accb);
+  }
+  w_qk[size_t(blockIdx.x) * kD + d] = __float2bfloat16(acc);
+  if (d == 0) b_qk[blockIdx.x] = accb;
+}
+
+cudaError_t launch_absorb_qk(const float* in_proj_weight, const float* in_proj_bias, int nhead, __nv_bfloat16* w_qk,
+                             float* b_qk, cudaStream_t stream) {
+  absorb_qk_kernel<<<nhead * kD, kD, 0, stream>>>(in_proj_weight, in_proj_bias, nhead, w_qk, b_qk);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tally(const TallyParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
   tally_kernel<<<(p.B + 7) / 8, 256, 0, stream>>>(p);
