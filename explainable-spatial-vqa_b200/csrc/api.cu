@@ -643,14 +643,15 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.B = B;
         mp.nhead = d.nhead;
         mp.qp = dq;
-        mp.mem = mem_b;
         mp.rows_per_q = kLP;
         mp.lens = lens_b;
         mp.const_len = const_len;
         mp.out = du;
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
-        LAUNCH_OK(h, launch_mem_attn(mp, s));
+        const CUtensorMap* tmem_map;
+        RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 32, &tmem_map));
+        LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
         GemmParams vp;
         vp.bias = L.cross_attn.b_in + 2 * kD;
         vp.out = dattn;

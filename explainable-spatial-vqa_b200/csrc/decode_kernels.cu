@@ -171,181 +171,201 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
 }
 
 // ------------------------------------------------------------------------------------------------
-// Absorbed cross-attention (MemAttnParams, kernels.h): one CTA (8 warps) per question, ONE pass over the memory.
+// Absorbed cross-attention (MemAttnParams, kernels.h): persistent CTAs (8 warps, three per SM), ONE pass over the memory.
 //
-// The memory rows m_j (256 bf16 = 512 B) stream through a 3-stage shared-memory ring of 64-row tiles (cp.async, rows
-// past the length zero-filled); every tile is consumed once with an online softmax, so HBM traffic per question is
-// len * 512 B - half of reading a projected K row and a V row - and nothing is re-read.  With NH query vectors per
-// row a CUDA-core form needs 8*NH FMAs per 16 loaded bytes and is issue-bound (measured 66 us per 1024 questions vs
-// 47 us for the K|V kernel), so both contractions run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate):
+// The memory rows m_j (256 bf16 = 512 B) stream through a 4-stage shared-memory ring of 32-row tiles, filled by TMA
+// (one elected thread, 128-byte swizzle, mbarrier completion) and running ahead ACROSS question boundaries so the HBM
+// stream never drains.  Every tile is consumed once with an online softmax: HBM traffic per question is len * 512 B -
+// half of reading a projected K row and a V row - and nothing is re-read.  With NH query vectors per row a CUDA-core
+// form needs 8*NH FMAs per 16 loaded bytes and is issue-bound (measured 66 us per 1024 questions vs 47 us for the K|V
+// kernel), so both contractions run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate):
 //   scores  S[j, h] = sum_d M[j, d] q'[h, d]   A = memory tile (ldmatrix), B = absorbed queries (registers, heads padded
-//                                              to the 8 MMA columns); warp w takes rows 16 (w & 3), half (w >> 2) of d
-//   values  U[h, d] += sum_j P[h, j] M[j, d]   A = exp2(S - running max) (heads padded to the 16 MMA rows), B = the same
-//                                              tile through ldmatrix.trans; warp w owns output columns [32 w, 32 w + 32)
-// Every warp tracks the running max / sum of "its" head redundantly, so no cross-warp merge is needed at the end.
-// Shared rows are padded to 528 B so the eight row addresses of an ldmatrix hit different banks.  (A 128-row tcgen05
-// atom would be 97% padding here: 2-4 query rows per question.)
+//                                              to the 8 MMA columns); warp w takes 16 rows and a quarter of the channels
+//   softmax warp h (< NH) owns head h: sums the partial scores of the tile's 32 rows (one per lane), keeps the running
+//           max / sum, publishes exp2(S - max) as bf16 and the rescale factor of the accumulators
+//   values  U[h, d] += sum_j P[h, j] M[j, d]   A = published weights (heads padded to the 16 MMA rows), B = the same tile
+//                                              through ldmatrix.trans; warp w owns output columns [32 w, 32 w + 32)
+// (A 128-row tcgen05 atom would be 97% padding here: 2-4 query rows per question.)  Rows past the sequence length
+// are read as they lie in the memory buffer (finite: the encoder writes all 256 rows) and get weight exactly 0.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMemTileRows = 64;
-constexpr int kMemRowBytes = kD * 2 + 16;
-constexpr int kMemStages = 3;
-constexpr int kMemStageBytes = kMemTileRows * kMemRowBytes;
-constexpr int kMemAttnSmem = kMemStages * kMemStageBytes;
+constexpr int kMemTileRows = 32;
+constexpr int kMemRowGroups = kMemTileRows / 16;            // 16-row MMA groups per tile
+constexpr int kMemKSplit = kAttnWarps / kMemRowGroups;      // warps sharing a row group split the 256 channels
+constexpr int kMemKSteps = 16 / kMemKSplit;                 // 16-channel MMA steps per warp in the score phase
+constexpr int kMemCtasPerSm = 3;
+constexpr int kMemStages = 4;
+constexpr int kMemBlockBytes = kMemTileRows * 128;          // one 64-channel column block of a tile (TMA box)
+constexpr int kMemStageBytes = 4 * kMemBlockBytes;          // 16 KB
+constexpr int kMemAttnSmem = kMemStages * kMemStageBytes + 1024;  // + slack to align the ring to the swizzle atom
 constexpr int kScPad = kMemTileRows + 8;  // row pitch of the score exchange: heads land in different banks
 
+// byte offset of the 16-byte chunk holding channels [c, c + 8) of row r inside a swizzled tile
+__device__ __forceinline__ uint32_t mem_tile_off(int r, int c) {
+  return uint32_t((c >> 6) * kMemBlockBytes + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4));
+}
+
 template <int NH>
-__global__ void __launch_bounds__(kAttnWarps * 32, 2) mem_attn_kernel(const MemAttnParams p) {
+__global__ void __launch_bounds__(kAttnWarps * 32, kMemCtasPerSm)
+mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams p) {
   static_assert(NH == 2 || NH == 4, "heads");
-  extern __shared__ __align__(16) uint8_t ring[];
-  __shared__ float s_part[2][NH][kScPad];  // partial scores of the current tile (two halves of d)
-  const int b = blockIdx.x;
+  extern __shared__ uint8_t ring_raw[];
+  __shared__ float s_part[kMemKSplit][NH][kScPad];   // partial scores of the current tile (channel slices)
+  __shared__ __align__(16) __nv_bfloat16 s_p[NH][kMemTileRows];  // softmax weights of the current tile
+  __shared__ float s_alpha[NH], s_inv[NH];
+  __shared__ __align__(8) uint64_t full_bar[kMemStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q4 = lane & 3;
-  const int kh = warp >> 2;  // half of the 256 channels this warp contracts in the score MMA
-  constexpr uint32_t kHeadLanes = (1u << (4 * NH)) - 1u;  // lanes whose fragment row g is a real head
+  const int rg = warp % kMemRowGroups;  // 16-row group of the tile this warp scores ...
+  const int kh = warp / kMemRowGroups;  // ... over channels [kh * 16 * kMemKSteps, +16 * kMemKSteps)
+  const uint32_t ring_u32 = (smem_u32(ring_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_mem);
+    for (int s = 0; s < kMemStages; ++s) mbar_init(&full_bar[s], 1);
+    fence_mbar_init();
+  }
   pdl_launch_dependents();
+  __syncthreads();
   pdl_wait();
-  int len = p.lens ? p.lens[b] : p.const_len;
-  len = len > kLP ? kLP : len;
-  const int n_tiles = (len + kMemTileRows - 1) / kMemTileRows;
-  const uint8_t* mbase = reinterpret_cast<const uint8_t*>(p.mem + size_t(b) * p.rows_per_q * kD);
-  const uint32_t ring_u32 = smem_u32(ring);
-
-  auto issue = [&](int i) {  // tile i -> stage i % kMemStages
-    if (i < n_tiles) {
-      const uint32_t dst = ring_u32 + (i % kMemStages) * kMemStageBytes;
-#pragma unroll
-      for (int c = 0; c < kMemTileRows * 32 / (kAttnWarps * 32); ++c) {
-        const int chunk = c * (kAttnWarps * 32) + threadIdx.x;  // 32 16-byte chunks per row
-        const int r = chunk >> 5, col = chunk & 31;
-        const int j = i * kMemTileRows + r;
-        cp_async_16(dst + r * kMemRowBytes + col * 16, mbase + size_t(j < len ? j : 0) * (kD * 2) + col * 16,
-                    j < len ? 16u : 0u);
-      }
-    }
-    cp_async_commit();  // (possibly empty) group: keeps the group count in step with the tile number
+  auto len_of = [&](int q) {
+    const int l = p.lens ? p.lens[q] : p.const_len;
+    return l > kLP ? kLP : (l < 1 ? 1 : l);  // producer and consumer must agree on >= 1 tile per question
   };
-  for (int i = 0; i < kMemStages - 1; ++i) issue(i);
 
-  // absorbed queries as B fragments of this warp's channel half: bq[k] = q'[head g][16 ks + 2 q4 + {0,1}],
-  // [.. + 8 + {0,1}] with ks = 8 kh + k; heads >= NH are zero columns
-  uint32_t bq[8][2];
-  {
-    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(p.qp + (size_t(b) * NH + (g < NH ? g : 0)) * kD) + kh * 64;
+  // Producer cursor (thread 0): the CTA walks questions blockIdx.x, + gridDim.x, ... and the tiles inside each; loads
+  // run kMemStages - 1 tiles ahead of the consumers across question boundaries.
+  int pq = blockIdx.x, pt = 0, p_len = 0, issued = 0;
+  auto issue_next = [&]() {
+    if (pq < p.B) {
+      if (pt == 0) p_len = len_of(pq);
+      const int st = issued % kMemStages;
+      const uint32_t dst = ring_u32 + st * kMemStageBytes;
+      const int row = pq * int(p.rows_per_q) + pt * kMemTileRows;
+      mbar_expect_tx(&full_bar[st], kMemStageBytes);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      bq[k][0] = g < NH ? __ldg(qrow + k * 8 + q4) : 0u;
-      bq[k][1] = g < NH ? __ldg(qrow + k * 8 + q4 + 4) : 0u;
+      for (int cb = 0; cb < 4; ++cb) tma_load_2d_u32(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row);
+      if ((++pt) * kMemTileRows >= p_len) {
+        pt = 0;
+        pq += gridDim.x;
+      }
     }
-  }
+    ++issued;
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kMemStages - 1; ++i) issue_next();
   const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
+  int consumed = 0;
 
-  float m_run = -INFINITY, l_run = 0.f;  // running max / (per-lane partial) sum of head g
-  float acc[4][4];
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-
-  for (int i = 0; i < n_tiles; ++i) {
-    cp_async_wait<kMemStages - 2>();
-    __syncthreads();  // tile i has landed for every thread; stage (i-1) % S and s_part are free again
-    issue(i + kMemStages - 1);
-    const uint32_t tile_u32 = ring_u32 + (i % kMemStages) * kMemStageBytes;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const int len = len_of(b);
+    const int n_tiles = (len + kMemTileRows - 1) / kMemTileRows;
+    // absorbed queries as B fragments of this warp's channel slice: bq[k] = q'[head g][16 ks + 2 q4 + {0,1}],
+    // [.. + 8 + {0,1}] with ks = kMemKSteps kh + k; heads >= NH are zero columns
+    uint32_t bq[kMemKSteps][2];
     {
-      // partial scores of rows [16 (w & 3), +16) over channels [128 kh, +128)
-      const uint32_t a_addr =
-          tile_u32 + ((warp & 3) * 16 + (lane & 15)) * kMemRowBytes + (lane >> 4) * 16 + kh * 256;
-      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t* qrow =
+          reinterpret_cast<const uint32_t*>(p.qp + (size_t(b) * NH + (g < NH ? g : 0)) * kD) + kh * kMemKSteps * 8;
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        uint32_t a0[4], a1[4];
-        ldmatrix_x4(a_addr + k * 32, a0);
-        ldmatrix_x4(a_addr + k * 32 + 32, a1);
-        mma_bf16_16816(c0, a0, bq[k][0], bq[k][1]);
-        mma_bf16_16816(c1, a1, bq[k + 1][0], bq[k + 1][1]);
-      }
-      // c[0,1] = S[row g][heads 2 q4, 2 q4 + 1], c[2,3] = the same heads of row g + 8
-      if (2 * q4 < NH) {
-        const int r = (warp & 3) * 16 + g;
-        s_part[kh][2 * q4][r] = (c0[0] + c1[0]) * sl2;
-        s_part[kh][2 * q4 + 1][r] = (c0[1] + c1[1]) * sl2;
-        s_part[kh][2 * q4][r + 8] = (c0[2] + c1[2]) * sl2;
-        s_part[kh][2 * q4 + 1][r + 8] = (c0[3] + c1[3]) * sl2;
+      for (int k = 0; k < kMemKSteps; ++k) {
+        bq[k][0] = g < NH ? __ldg(qrow + k * 8 + q4) : 0u;
+        bq[k][1] = g < NH ? __ldg(qrow + k * 8 + q4 + 4) : 0u;
       }
     }
-    __syncthreads();
-    // softmax weights of head g for the 64 rows, in A-fragment order: pa[ks][0] = rows 16 ks + 2 q4 + {0,1},
-    // pa[ks][2] = rows 16 ks + 8 + 2 q4 + {0,1}; fragment rows >= NH (registers 1 and 3) stay zero
-    uint32_t pa[kMemTileRows / 16][4];
-    if (g < NH) {
-      float sv[kMemTileRows / 16][4];
-      float mt = -INFINITY;
-      const int jbase = i * kMemTileRows;
-#pragma unroll
-      for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = ks * 16 + 2 * q4 + (e & 1) + (e >> 1) * 8;
-          const float s = s_part[0][g][j] + s_part[1][g][j];
-          sv[ks][e] = (jbase + j < len) ? s : -INFINITY;
-          mt = fmaxf(mt, sv[ks][e]);
-        }
-      }
-      mt = fmaxf(mt, __shfl_xor_sync(kHeadLanes, mt, 1));
-      mt = fmaxf(mt, __shfl_xor_sync(kHeadLanes, mt, 2));
-      const float m_new = fmaxf(m_run, mt);  // finite: every tile holds at least one valid row
-      const float alpha = exp2f(m_run - m_new);
-      m_run = m_new;
-      float ls = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
-        float pe[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          pe[e] = exp2f(sv[ks][e] - m_new);
-          ls += pe[e];
-        }
-        pa[ks][0] = pack_bf16x2(pe[0], pe[1]);
-        pa[ks][1] = 0u;
-        pa[ks][2] = pack_bf16x2(pe[2], pe[3]);
-        pa[ks][3] = 0u;
-      }
-      l_run = l_run * alpha + ls;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        acc[nt][0] *= alpha;
-        acc[nt][1] *= alpha;
-      }
-    } else {
-#pragma unroll
-      for (int ks = 0; ks < kMemTileRows / 16; ++ks) pa[ks][0] = pa[ks][1] = pa[ks][2] = pa[ks][3] = 0u;
-    }
-    __syncwarp();
-    // ldmatrix.trans addresses: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, columns 32 w + pair * 16 + (m >> 1) * 8
-    const uint32_t b_addr =
-        tile_u32 + (((lane >> 3) & 1) * 8 + (lane & 7)) * kMemRowBytes + (warp * 32 + (lane >> 4) * 8) * 2;
-#pragma unroll
-    for (int ks = 0; ks < kMemTileRows / 16; ++ks) {
-#pragma unroll
-      for (int pair = 0; pair < 2; ++pair) {
-        uint32_t bm[4];
-        ldmatrix_x4_trans(b_addr + ks * 16 * kMemRowBytes + pair * 32, bm);
-        mma_bf16_16816(acc[2 * pair], pa[ks], bm[0], bm[1]);
-        mma_bf16_16816(acc[2 * pair + 1], pa[ks], bm[2], bm[3]);
-      }
-    }
-  }
-  cp_async_wait<0>();
-  // acc[nt][0,1] = U[head g][32 w + 8 nt + 2 q4 + {0,1}] (un-normalised); the sum is spread over the quad
-  if (g < NH) {
-    l_run += __shfl_xor_sync(kHeadLanes, l_run, 1);
-    l_run += __shfl_xor_sync(kHeadLanes, l_run, 2);
-    const float inv = 1.f / l_run;
-    __nv_bfloat16* orow = p.out + (size_t(b) * NH + g) * kD + warp * 32 + 2 * q4;
+    float m_run = -INFINITY, l_run = 0.f;  // softmax warps: running max (warp-uniform) and this lane's share of the sum
+    float acc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
-      *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+
+    for (int i = 0; i < n_tiles; ++i) {
+      __syncthreads();  // everyone is done with the previous tile: its stage, s_part, s_p and s_alpha are free
+      if (threadIdx.x == 0) issue_next();
+      const int st = consumed % kMemStages;
+      mbar_wait(&full_bar[st], uint32_t(consumed / kMemStages) & 1u);
+      const uint32_t tile_u32 = ring_u32 + st * kMemStageBytes;
+      ++consumed;
+      {
+        // partial scores of this warp's 16 rows over its channel slice
+        const int ar = rg * 16 + (lane & 15);
+        const int ac = kh * kMemKSteps * 16 + (lane >> 4) * 8;
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < kMemKSteps; k += 2) {
+          uint32_t a0[4], a1[4];
+          ldmatrix_x4(tile_u32 + mem_tile_off(ar, ac + k * 16), a0);
+          ldmatrix_x4(tile_u32 + mem_tile_off(ar, ac + k * 16 + 16), a1);
+          mma_bf16_16816(c0, a0, bq[k][0], bq[k][1]);
+          mma_bf16_16816(c1, a1, bq[k + 1][0], bq[k + 1][1]);
+        }
+        // c[0,1] = S[row g][heads 2 q4, 2 q4 + 1], c[2,3] = the same heads of row g + 8
+        if (2 * q4 < NH) {
+          const int r = rg * 16 + g;
+          s_part[kh][2 * q4][r] = c0[0] + c1[0];
+          s_part[kh][2 * q4 + 1][r] = c0[1] + c1[1];
+          s_part[kh][2 * q4][r + 8] = c0[2] + c1[2];
+          s_part[kh][2 * q4 + 1][r + 8] = c0[3] + c1[3];
+        }
+      }
+      __syncthreads();
+      if (warp < NH) {  // online softmax of head `warp`: lane = row of the tile
+        float sv = s_part[0][warp][lane];
+#pragma unroll
+        for (int kp = 1; kp < kMemKSplit; ++kp) sv += s_part[kp][warp][lane];
+        sv = (i * kMemTileRows + lane < len) ? sv * sl2 : -INFINITY;
+        const float m_new = fmaxf(m_run, warp_max(sv));  // finite: every tile holds at least one valid row
+        const float alpha = exp2f(m_run - m_new);
+        const float pe = exp2f(sv - m_new);
+        m_run = m_new;
+        l_run = l_run * alpha + pe;
+        s_p[warp][lane] = __float2bfloat16(pe);
+        if (lane == 0) s_alpha[warp] = alpha;
+      }
+      __syncthreads();
+      // A fragments: pa[ks][0] = P[head g][16 ks + 2 q4 + {0,1}], pa[ks][2] = the same + 8; fragment rows >= NH are zero
+      uint32_t pa[kMemRowGroups][4];
+#pragma unroll
+      for (int ks = 0; ks < kMemRowGroups; ++ks) {
+        const uint32_t* pr = reinterpret_cast<const uint32_t*>(&s_p[g < NH ? g : 0][ks * 16 + 2 * q4]);
+        pa[ks][0] = g < NH ? pr[0] : 0u;
+        pa[ks][1] = 0u;
+        pa[ks][2] = g < NH ? pr[4] : 0u;
+        pa[ks][3] = 0u;
+      }
+      {
+        const float alpha = s_alpha[g < NH ? g : 0];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[nt][0] *= alpha;
+          acc[nt][1] *= alpha;
+        }
+      }
+      // ldmatrix.trans: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, channels 32 w + pair * 16 + (m >> 1) * 8
+      const int br = ((lane >> 3) & 1) * 8 + (lane & 7);
+      const int bc = warp * 32 + (lane >> 4) * 8;
+#pragma unroll
+      for (int ks = 0; ks < kMemRowGroups; ++ks) {
+#pragma unroll
+        for (int pair = 0; pair < 2; ++pair) {
+          uint32_t bm[4];
+          ldmatrix_x4_trans(tile_u32 + mem_tile_off(ks * 16 + br, bc + pair * 16), bm);
+          mma_bf16_16816(acc[2 * pair], pa[ks], bm[0], bm[1]);
+          mma_bf16_16816(acc[2 * pair + 1], pa[ks], bm[2], bm[3]);
+        }
+      }
+    }
+    // normalise: acc[nt][0,1] = U[head g][32 w + 8 nt + 2 q4 + {0,1}]
+    if (warp < NH) {
+      const float l = warp_sum(l_run);
+      if (lane == 0) s_inv[warp] = 1.f / l;
+    }
+    __syncthreads();
+    if (g < NH) {
+      const float inv = s_inv[g];
+      __nv_bfloat16* orow = p.out + (size_t(b) * NH + g) * kD + warp * 32 + 2 * q4;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+    }
   }
 }
 
@@ -378,8 +398,17 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_mem_attn(const MemAttnParams& p, cudaStream_t stream) {
+cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  // persistent: kMemCtasPerSm CTAs per SM, each streaming its questions back to back
+  const int grid = p.B < kMemCtasPerSm * num_sms ? p.B : kMemCtasPerSm * num_sms;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(mem_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMemAttnSmem);
@@ -389,9 +418,9 @@ cudaError_t launch_mem_attn(const MemAttnParams& p, cudaStream_t stream) {
     attr_done = true;
   }
   if (p.nhead == 4)
-    return launch_kernel(mem_attn_kernel<4>, dim3(p.B), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, p);
+    return launch_kernel(mem_attn_kernel<4>, dim3(grid), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   if (p.nhead == 2)
-    return launch_kernel(mem_attn_kernel<2>, dim3(p.B), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, p);
+    return launch_kernel(mem_attn_kernel<2>, dim3(grid), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   return cudaErrorInvalidValue;
 }
 

@@ -224,18 +224,18 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream);
 //   u_h        = sum_j softmax(scores_h)[j] m_j       (the value projection W_v,h u_h + b_v,h follows as a GEMM)
 // so a decode position reads the memory rows (512 B each) once from HBM instead of a K row and a V row, and the
 // per-question K|V projection of the memory disappears.  qp [B, nhead*256] bf16 = absorbed queries W_k,h^T q_h,
-// mem [B*rows_per_q, 256] bf16, out u [B, nhead*256] bf16.
+// memory [B*rows_per_q, 256] bf16 (through the tensor map), out u [B, nhead*256] bf16.
 struct MemAttnParams {
   int B = 0, nhead = 4;
   bool pdl = false;
   const __nv_bfloat16* qp = nullptr;
-  const __nv_bfloat16* mem = nullptr;
   long long rows_per_q = 0;
   const int32_t* lens = nullptr;     // [B] or null -> const_len
   int const_len = 0;
   __nv_bfloat16* out = nullptr;
 };
-cudaError_t launch_mem_attn(const MemAttnParams& p, cudaStream_t stream);
+// tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, 32 rows}
+cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream);
 
 // Weight packing for the absorbed cross-attention: in_proj_weight [3d, d] / in_proj_bias [3d] fp32 ->
 //   w_qk [nhead*d, d] bf16, row h*d + i = sum_e W_k[h*dh+e][i] * W_q[h*dh+e][:]     b_qk [nhead*d] likewise with b_q

@@ -96,6 +96,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// same with the destination given as a shared-memory address
+__device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -135,17 +143,8 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 
 // ----------------------------------------------------------------------------------------------
 // Warp-level pieces for the bandwidth-bound decode attention (a handful of query rows per question: far below the
-// 128-row tcgen05 atom): 16-byte async copies global -> shared, ldmatrix fragment loads, m16n8k16 bf16 MMA.
+// 128-row tcgen05 atom): ldmatrix fragment loads and the m16n8k16 bf16 MMA.
 // ----------------------------------------------------------------------------------------------
-// copies 16 bytes; src_bytes = 0 zero-fills the destination instead (rows past the sequence length)
-__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 // four 8x8 b16 matrices; lanes 8i..8i+7 give the row addresses of matrix i
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
