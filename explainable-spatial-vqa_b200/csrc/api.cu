@@ -650,7 +650,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
         const CUtensorMap* tmem_map;
-        RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 32, &tmem_map));
+        RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
         LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
         GemmParams vp;
         vp.bias = L.cross_attn.b_in + 2 * kD;

@@ -173,29 +173,28 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
 // ------------------------------------------------------------------------------------------------
 // Absorbed cross-attention (MemAttnParams, kernels.h): persistent CTAs (8 warps, three per SM), ONE pass over the memory.
 //
-// The memory rows m_j (256 bf16 = 512 B) stream through a 4-stage shared-memory ring of 32-row tiles, filled by TMA
-// (one elected thread, 128-byte swizzle, mbarrier completion) and running ahead ACROSS question boundaries so the HBM
-// stream never drains.  Every tile is consumed once with an online softmax: HBM traffic per question is len * 512 B -
+// The memory rows m_j (256 bf16 = 512 B) stream through a double-buffered shared-memory ring of 64-row tiles, filled
+// by TMA (one elected thread, 128-byte swizzle, mbarrier completion) and running ahead ACROSS question boundaries.  Every tile is consumed once with an online softmax: HBM traffic per question is len * 512 B -
 // half of reading a projected K row and a V row - and nothing is re-read.  With NH query vectors per row a CUDA-core
 // form needs 8*NH FMAs per 16 loaded bytes and is issue-bound (measured 66 us per 1024 questions vs 47 us for the K|V
 // kernel), so both contractions run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate):
 //   scores  S[j, h] = sum_d M[j, d] q'[h, d]   A = memory tile (ldmatrix), B = absorbed queries (registers, heads padded
-//                                              to the 8 MMA columns); warp w takes 16 rows and a quarter of the channels
-//   softmax warp h (< NH) owns head h: sums the partial scores of the tile's 32 rows (one per lane), keeps the running
+//                                              to the 8 MMA columns); warp w takes 16 rows and half of the channels
+//   softmax warp h (< NH) owns head h: sums the partial scores of the tile's rows (two per lane), keeps the running
 //           max / sum, publishes exp2(S - max) as bf16 and the rescale factor of the accumulators
 //   values  U[h, d] += sum_j P[h, j] M[j, d]   A = published weights (heads padded to the 16 MMA rows), B = the same tile
 //                                              through ldmatrix.trans; warp w owns output columns [32 w, 32 w + 32)
 // (A 128-row tcgen05 atom would be 97% padding here: 2-4 query rows per question.)  Rows past the sequence length
 // are read as they lie in the memory buffer (finite: the encoder writes all 256 rows) and get weight exactly 0.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMemTileRows = 32;
+constexpr int kMemTileRows = kMemAttnTileRows;
 constexpr int kMemRowGroups = kMemTileRows / 16;            // 16-row MMA groups per tile
 constexpr int kMemKSplit = kAttnWarps / kMemRowGroups;      // warps sharing a row group split the 256 channels
 constexpr int kMemKSteps = 16 / kMemKSplit;                 // 16-channel MMA steps per warp in the score phase
 constexpr int kMemCtasPerSm = 3;
-constexpr int kMemStages = 4;
+constexpr int kMemStages = 2;
 constexpr int kMemBlockBytes = kMemTileRows * 128;          // one 64-channel column block of a tile (TMA box)
-constexpr int kMemStageBytes = 4 * kMemBlockBytes;          // 16 KB
+constexpr int kMemStageBytes = 4 * kMemBlockBytes;
 constexpr int kMemAttnSmem = kMemStages * kMemStageBytes + 1024;  // + slack to align the ring to the swizzle atom
 constexpr int kScPad = kMemTileRows + 8;  // row pitch of the score exchange: heads land in different banks
 
@@ -307,17 +306,28 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
         }
       }
       __syncthreads();
-      if (warp < NH) {  // online softmax of head `warp`: lane = row of the tile
-        float sv = s_part[0][warp][lane];
+      if (warp < NH) {  // online softmax of head `warp`: lane = rows lane, lane + 32, ... of the tile
+        float sv[kMemTileRows / 32];
+        float mt = -INFINITY;
 #pragma unroll
-        for (int kp = 1; kp < kMemKSplit; ++kp) sv += s_part[kp][warp][lane];
-        sv = (i * kMemTileRows + lane < len) ? sv * sl2 : -INFINITY;
-        const float m_new = fmaxf(m_run, warp_max(sv));  // finite: every tile holds at least one valid row
+        for (int rr = 0; rr < kMemTileRows / 32; ++rr) {
+          const int r = rr * 32 + lane;
+          float v = s_part[0][warp][r];
+#pragma unroll
+          for (int kp = 1; kp < kMemKSplit; ++kp) v += s_part[kp][warp][r];
+          sv[rr] = (i * kMemTileRows + r < len) ? v * sl2 : -INFINITY;
+          mt = fmaxf(mt, sv[rr]);
+        }
+        const float m_new = fmaxf(m_run, warp_max(mt));  // finite: every tile holds at least one valid row
         const float alpha = exp2f(m_run - m_new);
-        const float pe = exp2f(sv - m_new);
         m_run = m_new;
-        l_run = l_run * alpha + pe;
-        s_p[warp][lane] = __float2bfloat16(pe);
+        l_run *= alpha;
+#pragma unroll
+        for (int rr = 0; rr < kMemTileRows / 32; ++rr) {
+          const float pe = exp2f(sv[rr] - m_new);
+          l_run += pe;
+          s_p[warp][rr * 32 + lane] = __float2bfloat16(pe);
+        }
         if (lane == 0) s_alpha[warp] = alpha;
       }
       __syncthreads();

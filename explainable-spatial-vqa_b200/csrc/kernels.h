@@ -234,7 +234,8 @@ struct MemAttnParams {
   int const_len = 0;
   __nv_bfloat16* out = nullptr;
 };
-// tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, 32 rows}
+constexpr int kMemAttnTileRows = 64;  // memory rows per shared-memory tile of the absorbed cross-attention
+// tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, kMemAttnTileRows}
 cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream);
 
 // Weight packing for the absorbed cross-attention: in_proj_weight [3d, d] / in_proj_bias [3d] fp32 ->
