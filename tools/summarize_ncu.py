@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-  python tools/summarize_ncu.py launches gpurun_out/launches.csv profiles/r1_launches_iqap_b1024.md [skip_steps]
+  python tools/summarize_ncu.py launches gpurun_out/launches.csv profiles/r1_launches_iqap_b1024.md [first last]
   python tools/summarize_ncu.py full gpurun_out/prof.ncu-rep profiles/r1_full_<name>.md
 
 `launches`: per-kernel totals / averages / shares of one bench step from the
@@ -33,15 +33,18 @@ def short(name):
     return name.replace("b200vqa::", "").replace("<unnamed>::", "").replace("void ", "").replace("unnamed>::", "")[-64:]
 
 
-def launches(path, out):
+def launches(path, out, first=None, last=None):
+    """first / last: launch index range [first, last) of ONE bench step inside the list (steps start at the
+    embedding kernel); default = the whole list."""
     rows = list(csv.reader(open(path)))
     start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[start]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = collections.OrderedDict()
-    for r in rows[start + 1:]:
-        if len(r) <= vi:
-            continue
+    body = [r for r in rows[start + 1:] if len(r) > vi]
+    if first is not None:
+        body = body[first:last]
+    for r in body:
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
         a = agg.setdefault(short(r[ki]), [0, 0.0])
@@ -75,14 +78,25 @@ def to_bytes(val, unit):
 
 
 def full(path, out, tag=None):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    """path: an .ncu-rep, or the `ncu -i rep --page raw --csv` text already exported on the GPU box (reports with many
+    launches exceed what gpurun copies back)."""
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True,
+                             check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     traffic = {}
     with open(out, "w") as f:
         f.write(f"# ncu --set full summary ({os.path.basename(path)})\n\n")
+        seen = set()
         for r in rows[2:]:
             name = short(r[hdr.index("Kernel Name")])
+            key = (name, r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "")
+            if key in seen:
+                continue
+            seen.add(key)
             f.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
             rd = wr = None
             for m in WANT:
@@ -109,6 +123,6 @@ def full(path, out, tag=None):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], sys.argv[3])
+        launches(sys.argv[2], sys.argv[3], *(int(a) for a in sys.argv[4:6]))
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
