@@ -548,6 +548,20 @@ def run_ours(args):
                     "value": 3 * units_per_step / (e0.elapsed_time(e1) * 1e-3), "unit": "program-steps/s",
                     "h2d_bytes_per_step": img_u.numel() * 4 + q_host.numel() * 8 + idx_host.numel() * 4,
                     "what": "forward_host_indexed: host buffers, unique images uploaded and projected once"}
+                # the same questions with the features held as fp16 on the host (the half-size feature store)
+                img16 = img_host.half().pin_memory()
+                model.forward_host(img16, q_host, chunk=args.e2e_chunk)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    model.forward_host(img16, q_host, chunk=args.e2e_chunk)
+                e1.record()
+                torch.cuda.synchronize()
+                extra["e2e_fp16_feature_store"] = {
+                    "value": 3 * units_per_step / (e0.elapsed_time(e1) * 1e-3), "unit": "program-steps/s",
+                    "h2d_bytes_per_step": img16.numel() * 2 + q_host.numel() * 8,
+                    "what": "forward_host on fp16 features (same mantissa width as the tf32 path); serial calls"}
+                del img16
         except Exception as e:  # pragma: no cover - context numbers must never break the bench line
             extra["context_error"] = repr(e)
 

@@ -259,3 +259,21 @@ def test_fp16_feature_store_matches_oracle(model):
     ha, hp = model.forward_host(img16.pin_memory(), q)
     fa_, fp_ = model(img16.cuda(), q.cuda())
     assert torch.equal(ha, fa_.cpu()) and torch.equal(hp, fp_.cpu())
+
+
+def test_absorbed_cross_attention_equals_projected_kv_path(monkeypatch):
+    """The decode cross-attention runs on the encoder memory with W_k^T W_q folded into the query projection
+    (MemAttnParams, csrc/kernels.h).  B200VQA_NO_ABSORB=1 keeps the textbook form (K|V of the memory projected once,
+    one K row and one V row read per key): both must give the same teacher-forced logits to bf16 rounding, and the
+    same answers (the encoder is untouched)."""
+    img, q = orc.iqap_inputs(16, seed=99)
+    g = torch.Generator().manual_seed(3)
+    forced = torch.randint(0, 44, (16, 27), generator=g)
+    absorbed = common.seeded_iqap().cuda()
+    a1, _, l1, _ = absorbed.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    monkeypatch.setenv("B200VQA_NO_ABSORB", "1")
+    plain = common.seeded_iqap().cuda()          # the switch is read when the native handle is created
+    a2, _, l2, _ = plain.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    assert torch.equal(a1, a2)
+    assert common.rel_err(l1, l2) < 4e-3
+    assert plain.native_launch_count() != absorbed.native_launch_count()   # really two different kernel sequences
