@@ -1571,9 +1571,10 @@ B200VQA_API int b200vqa_fa_forward(b200vqa_handle* h, const void* img_tokens_bf1
   return B200VQA_OK;
 }
 
-B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_bf16, const int32_t* func, const int32_t* deps,
-                         const int32_t* n_steps, int B, int S, int start_token, int max_len, int32_t* cache,
-                         const int32_t* h_active, float* opt_logits, const int64_t* opt_forced, void* stream) {
+static int fa_run_chain_impl(b200vqa_handle* h, const void* img_tokens_bf16, const int32_t* image_idx, int n_images,
+                             const int32_t* func, const int32_t* deps, const int32_t* n_steps, int B, int S,
+                             int start_token, int max_len, int32_t* cache, const int32_t* h_active, float* opt_logits,
+                             const int64_t* opt_forced, void* stream) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
   B200VQA_REQUIRE(B >= 0 && S >= 0, "negative batch or step count");
@@ -1604,6 +1605,8 @@ B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_b
       bp.deps = deps + size_t(b0) * S * 2;
       bp.n_steps = n_steps + b0;
       bp.cache = cache + size_t(b0) * S * max_len;
+      bp.image_idx = image_idx ? image_idx + b0 : nullptr;
+      bp.n_images = n_images;
       DecodeIO io;
       io.start_token = start_token;
       io.steps = T;
@@ -1611,8 +1614,8 @@ B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_b
       io.logits_T = S * T;  // row (b, i, t) = b*S*T + i*T + t
       io.forced = opt_forced ? opt_forced + (size_t(b0) * S + i) * T : nullptr;
       io.forced_ld = S * T;
-      RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) + size_t(b0) * d.n_img_tokens * kD, bp,
-                        nb, io, s));
+      RC_OK(fa_one_step(h, static_cast<const __nv_bfloat16*>(img_tokens_bf16) +
+                               (image_idx ? size_t(0) : size_t(b0) * d.n_img_tokens * kD), bp, nb, io, s));
       // step i's 20 tokens (start token included, FA:120-121) into the HBM cache; with teacher forcing the
       // cache receives the forced tokens so that later steps consume exactly what the caller dictated
       RC_OK(publish(h, nb, max_len, 0, nullptr, cache + (size_t(b0) * S + i) * max_len, (long long)S * max_len, io.forced,
@@ -1620,6 +1623,23 @@ B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_b
     }
   }
   return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_fa_run_chain(b200vqa_handle* h, const void* img_tokens_bf16, const int32_t* func, const int32_t* deps,
+                         const int32_t* n_steps, int B, int S, int start_token, int max_len, int32_t* cache,
+                         const int32_t* h_active, float* opt_logits, const int64_t* opt_forced, void* stream) {
+  return fa_run_chain_impl(h, img_tokens_bf16, nullptr, 0, func, deps, n_steps, B, S, start_token, max_len, cache,
+                           h_active, opt_logits, opt_forced, stream);
+}
+
+B200VQA_API int b200vqa_fa_run_chain_indexed(b200vqa_handle* h, const void* img_tokens_bf16, int n_images,
+                                             const int32_t* image_idx, const int32_t* func, const int32_t* deps,
+                                             const int32_t* n_steps, int B, int S, int start_token, int max_len,
+                                             int32_t* cache, const int32_t* h_active, float* opt_logits,
+                                             const int64_t* opt_forced, void* stream) {
+  B200VQA_REQUIRE(image_idx != nullptr && n_images >= 1, "image_idx is NULL or there are no images");
+  return fa_run_chain_impl(h, img_tokens_bf16, image_idx, n_images, func, deps, n_steps, B, S, start_token, max_len,
+                           cache, h_active, opt_logits, opt_forced, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks

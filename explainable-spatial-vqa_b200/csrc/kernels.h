@@ -143,7 +143,9 @@ struct FaBuildSrcParams {
   const int64_t* src_direct = nullptr;  // alternative: explicit src tokens [B, src_ld] with src_len[b]
   const int32_t* src_len_in = nullptr;
   int src_ld = 0;
-  const __nv_bfloat16* img_tokens = nullptr;  // [B,196,kD]
+  const __nv_bfloat16* img_tokens = nullptr;  // [B,196,kD], or [n_images,196,kD] with image_idx
+  const int32_t* image_idx = nullptr;         // optional [B]: image of question b (several questions per image)
+  int n_images = 0;
   const float* emb = nullptr;
   int vocab = 0;
   const float* pe = nullptr;

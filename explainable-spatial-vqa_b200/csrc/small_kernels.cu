@@ -100,7 +100,12 @@ __global__ void __launch_bounds__(256) fa_build_src_kernel(const FaBuildSrcParam
   const int n = s_len;
 
   // image tokens: straight 16-byte copy (PE rows 0..195 were folded in by fa_project_images)
-  const uint4* src = reinterpret_cast<const uint4*>(p.img_tokens + size_t(b) * p.n_img * kD);
+  int img = b;
+  if (p.image_idx) {
+    img = p.image_idx[b];
+    img = img < 0 ? 0 : (img >= p.n_images ? p.n_images - 1 : img);
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(p.img_tokens + size_t(img) * p.n_img * kD);
   uint4* dst = reinterpret_cast<uint4*>(p.x + size_t(b) * kLP * kD);
   const int n16 = p.n_img * kD / 8;
   for (int i = threadIdx.x; i < n16; i += 256) dst[i] = src[i];

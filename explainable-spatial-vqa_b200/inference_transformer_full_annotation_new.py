@@ -238,13 +238,17 @@ def chain_to_arrays(final_chain, rev_vocab, max_steps=None):
 
 @torch.no_grad()
 def run_inference_chain_batched(model, image_features, func, deps, n_steps, start_token=0, max_infer_len=20,
-                                forced=None, want_logits=False, img_tokens=None, sort_by_steps=True, slot=0):
+                                forced=None, want_logits=False, img_tokens=None, sort_by_steps=True, slot=0,
+                                image_idx=None):
     """Executes B programs at once with the inference cache in HBM.
 
     func (B,S) i32, deps (B,S,2) i32 (-1 = none), n_steps (B,) i32  ->  cache (B,S,max_infer_len) i32 where
     cache[b,i] holds the max_infer_len tokens of step i (start token included, FA:120-121) and rows with
     i >= n_steps[b] stay -1.  Questions are processed longest-program-first so that finished questions drop
     out of later steps (`sort_by_steps`); results are returned in the caller's order.
+
+    image_idx (B,) optional: several questions per image (CLEVR ~10) - `image_features` / `img_tokens` then hold every
+    image ONCE (n_images rows) and question b uses image image_idx[b]; the projection runs once per image.
     """
     if slot > 0:
         # pipelined submission: the whole call runs on the slot's own handle + stream; results are valid after
@@ -253,13 +257,13 @@ def run_inference_chain_batched(model, image_features, func, deps, n_steps, star
         st.wait_stream(torch.cuda.current_stream(st.device))
         with torch.cuda.stream(st):
             return _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced,
-                                  want_logits, img_tokens, sort_by_steps, slot)
+                                  want_logits, img_tokens, sort_by_steps, slot, image_idx)
     return _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced, want_logits,
-                          img_tokens, sort_by_steps, 0)
+                          img_tokens, sort_by_steps, 0, image_idx)
 
 
 def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_infer_len, forced, want_logits,
-                   img_tokens, sort_by_steps, slot):
+                   img_tokens, sort_by_steps, slot, image_idx=None):
     h = model._native(slot)
     dev = model.image_proj.weight.device
     func = _dev(func.to(dev), "func", torch.int32)
@@ -270,13 +274,24 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
         raise ValueError("deps must be (B,S,2) and n_steps (B,)")
     if img_tokens is None:
         img_tokens = project_images(model, image_features.to(dev), slot)
+    if image_idx is not None:
+        image_idx = _dev(image_idx.to(dev), "image_idx", torch.int32)
+        if tuple(image_idx.shape) != (B,):
+            raise ValueError("image_idx must be (B,)")
+        if B and (int(image_idx.min()) < 0 or int(image_idx.max()) >= img_tokens.shape[0]):
+            raise IndexError("image_idx out of range")
+    elif img_tokens.shape[0] != B:
+        raise ValueError("one image per question expected (or pass image_idx)")
     T = max_infer_len - 1
     order = None
     active = None
     if sort_by_steps and B > 1:
         order = torch.argsort(n_steps, descending=True, stable=True)
-        func, deps, n_steps, img_tokens = func[order].contiguous(), deps[order].contiguous(), n_steps[order].contiguous(), \
-            img_tokens[order].contiguous()
+        func, deps, n_steps = func[order].contiguous(), deps[order].contiguous(), n_steps[order].contiguous()
+        if image_idx is not None:
+            image_idx = image_idx[order].contiguous()     # the tokens themselves stay where they are
+        else:
+            img_tokens = img_tokens[order].contiguous()
         if forced is not None:
             forced = forced.to(dev)[order]
         ns_host = n_steps.cpu().numpy()
@@ -286,10 +301,18 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
     logits = torch.zeros(B, S, T, model.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
     active_ptr = None if active is None else active.ctypes.data
     with torch.cuda.device(dev):
-        nat.check(nat.lib().b200vqa_fa_run_chain(h.raw, nat.ptr(img_tokens), nat.ptr(func), nat.ptr(deps), nat.ptr(n_steps),
-                                                 B, S, int(start_token), int(max_infer_len), nat.ptr(cache), active_ptr,
-                                                 nat.ptr(logits), nat.ptr(fz), nat.stream_ptr(dev)),
-                  "b200vqa_fa_run_chain")
+        if image_idx is None:
+            rc = nat.lib().b200vqa_fa_run_chain(h.raw, nat.ptr(img_tokens), nat.ptr(func), nat.ptr(deps),
+                                                nat.ptr(n_steps), B, S, int(start_token), int(max_infer_len),
+                                                nat.ptr(cache), active_ptr, nat.ptr(logits), nat.ptr(fz),
+                                                nat.stream_ptr(dev))
+        else:
+            rc = nat.lib().b200vqa_fa_run_chain_indexed(h.raw, nat.ptr(img_tokens), int(img_tokens.shape[0]),
+                                                        nat.ptr(image_idx), nat.ptr(func), nat.ptr(deps),
+                                                        nat.ptr(n_steps), B, S, int(start_token), int(max_infer_len),
+                                                        nat.ptr(cache), active_ptr, nat.ptr(logits), nat.ptr(fz),
+                                                        nat.stream_ptr(dev))
+        nat.check(rc, "b200vqa_fa_run_chain")
     if order is not None:
         inv = torch.empty_like(order)
         inv[order] = torch.arange(B, device=dev)

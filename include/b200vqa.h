@@ -303,6 +303,15 @@ B200VQA_API int b200vqa_programs_to_chain(const int64_t* programs, int B, int T,
                                           const int32_t* func_map, int prog_vocab, int S, int32_t* func,
                                           int32_t* deps, int32_t* n_steps, void* stream);
 
+/* b200vqa_fa_run_chain with image-level de-duplication ("dedup of img_tokens (image_idxs)"):
+ * img_tokens_bf16 [n_images,196,256] holds every image once, image_idx [B] i32 (device) names the image of each
+ * question (reference preprocess_questions/preprocess_questions.py:122).  Everything else as above. */
+B200VQA_API int b200vqa_fa_run_chain_indexed(b200vqa_handle* h, const void* img_tokens_bf16, int n_images,
+                                             const int32_t* image_idx, const int32_t* func, const int32_t* deps,
+                                             const int32_t* n_steps, int B, int S, int start_token, int max_len,
+                                             int32_t* cache, const int32_t* h_active, float* opt_logits,
+                                             const int64_t* opt_forced, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* Kernel-level entry points used by the test-suite only (not part of the drop-in surface)               */
 /* ---------------------------------------------------------------------------------------------------- */

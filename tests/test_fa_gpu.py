@@ -237,3 +237,24 @@ def test_pipelined_chain_slots_match_serial(model):
     b = fa.run_inference_chain_batched(model, img[24:], func[24:], deps[24:], n_steps[24:], 0, 20, slot=2)
     model.drain()
     assert torch.equal(torch.cat([a, b]), ref)
+
+
+def test_chain_with_shared_images_equals_expanded(model):
+    """SURVEY 8f next-2 for the FA path: several questions per image.  The chain over `img_tokens` of the unique images
+    + image_idx must fill the same cache, bit for bit, as the chain over one (repeated) image per question."""
+    B, n_img = 40, 6
+    func, deps, n_steps = orc.fa_programs(B, seed=17, max_steps=6)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    img = torch.randn(n_img, 1024, 14, 14, device="cuda", generator=g).relu_()
+    idx = torch.randint(0, n_img, (B,), generator=torch.Generator().manual_seed(1), dtype=torch.int32)
+    ref = fa.run_inference_chain_batched(model, img[idx.long().cuda()], func, deps, n_steps, 0, 20)
+    got = fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20, image_idx=idx)
+    assert torch.equal(got, ref)
+    toks = fa.project_images(model, img)
+    got2 = fa.run_inference_chain_batched(model, None, func, deps, n_steps, 0, 20, img_tokens=toks, image_idx=idx,
+                                          sort_by_steps=False)
+    assert torch.equal(got2, ref)
+    with pytest.raises(IndexError):
+        fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20, image_idx=idx + n_img)
+    with pytest.raises(ValueError):
+        fa.run_inference_chain_batched(model, img, func, deps, n_steps, 0, 20)      # 6 images, 40 questions, no index
