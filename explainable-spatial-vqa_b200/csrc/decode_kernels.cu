@@ -182,16 +182,19 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
 //                                              to the 8 MMA columns); warp w takes 16 rows and half of the channels
 //   softmax warp h (< NH) owns head h: sums the partial scores of the tile's rows (two per lane), keeps the running
 //           max / sum, publishes exp2(S - max) as bf16 and the rescale factor of the accumulators
-//   values  U[h, d] += sum_j P[h, j] M[j, d]   A = published weights (heads padded to the 16 MMA rows), B = the same tile
-//                                              through ldmatrix.trans; warp w owns output columns [32 w, 32 w + 32)
+//   values  U^T[d, h] += sum_j M[j, d] P[h, j]  A = the same tile through ldmatrix.trans (channels on the MMA rows),
+//                                              B = published weights (heads on the 8 columns); warp w owns channels
+//                                              [32 w, 32 w + 32)
 // (A 128-row tcgen05 atom would be 97% padding here: 2-4 query rows per question.)  Rows past the sequence length
 // are read as they lie in the memory buffer (finite: the encoder writes all 256 rows) and get weight exactly 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMemTileRows = kMemAttnTileRows;
 constexpr int kMemRowGroups = kMemTileRows / 16;            // 16-row MMA groups per tile
-constexpr int kMemKSplit = kAttnWarps / kMemRowGroups;      // warps sharing a row group split the 256 channels
+constexpr int kMemWarps = 4;                                // small CTAs: six fit an SM (registers and 33 KB of ring each)
+constexpr int kMemKSplit = kMemWarps / kMemRowGroups;       // warps sharing a row group split the 256 channels
+constexpr int kMemMTiles = kD / kMemWarps / 16;             // 16-channel output tiles per warp in the value product
 constexpr int kMemKSteps = 16 / kMemKSplit;                 // 16-channel MMA steps per warp in the score phase
-constexpr int kMemCtasPerSm = 3;
+constexpr int kMemCtasPerSm = 6;
 constexpr int kMemStages = 2;
 constexpr int kMemBlockBytes = kMemTileRows * 128;          // one 64-channel column block of a tile (TMA box)
 constexpr int kMemStageBytes = 4 * kMemBlockBytes;
@@ -204,7 +207,7 @@ __device__ __forceinline__ uint32_t mem_tile_off(int r, int c) {
 }
 
 template <int NH>
-__global__ void __launch_bounds__(kAttnWarps * 32, kMemCtasPerSm)
+__global__ void __launch_bounds__(kMemWarps * 32, kMemCtasPerSm)
 mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams p) {
   static_assert(NH == 2 || NH == 4, "heads");
   extern __shared__ uint8_t ring_raw[];
@@ -270,11 +273,13 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
       }
     }
     float m_run = -INFINITY, l_run = 0.f;  // softmax warps: running max (warp-uniform) and this lane's share of the sum
-    float acc[4][4];
+    // acc[mt] = U^T[channels 32 w + 16 mt + g (+8)][heads 2 q4, 2 q4 + 1]: the value product is computed transposed
+    // (channels on the 16 MMA rows, heads on the 8 columns) - half the MMAs of heads-on-rows
+    float acc[kMemMTiles][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int mt = 0; mt < kMemMTiles; ++mt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
 
     for (int i = 0; i < n_tiles; ++i) {
       __syncthreads();  // everyone is done with the previous tile: its stage, s_part, s_p and s_alpha are free
@@ -331,50 +336,55 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
         if (lane == 0) s_alpha[warp] = alpha;
       }
       __syncthreads();
-      // A fragments: pa[ks][0] = P[head g][16 ks + 2 q4 + {0,1}], pa[ks][2] = the same + 8; fragment rows >= NH are zero
-      uint32_t pa[kMemRowGroups][4];
+      // B fragments of P^T: pb[ks][0] = P[head g][16 ks + 2 q4 + {0,1}], pb[ks][1] = the same + 8; heads >= NH are zero
+      uint32_t pb[kMemRowGroups][2];
 #pragma unroll
       for (int ks = 0; ks < kMemRowGroups; ++ks) {
         const uint32_t* pr = reinterpret_cast<const uint32_t*>(&s_p[g < NH ? g : 0][ks * 16 + 2 * q4]);
-        pa[ks][0] = g < NH ? pr[0] : 0u;
-        pa[ks][1] = 0u;
-        pa[ks][2] = g < NH ? pr[4] : 0u;
-        pa[ks][3] = 0u;
+        pb[ks][0] = g < NH ? pr[0] : 0u;
+        pb[ks][1] = g < NH ? pr[4] : 0u;
       }
       {
-        const float alpha = s_alpha[g < NH ? g : 0];
+        const float al0 = s_alpha[2 * q4 < NH ? 2 * q4 : 0], al1 = s_alpha[2 * q4 + 1 < NH ? 2 * q4 + 1 : 0];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          acc[nt][0] *= alpha;
-          acc[nt][1] *= alpha;
+        for (int mt = 0; mt < kMemMTiles; ++mt) {
+          acc[mt][0] *= al0;
+          acc[mt][1] *= al1;
+          acc[mt][2] *= al0;
+          acc[mt][3] *= al1;
         }
       }
-      // ldmatrix.trans: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, channels 32 w + pair * 16 + (m >> 1) * 8
-      const int br = ((lane >> 3) & 1) * 8 + (lane & 7);
-      const int bc = warp * 32 + (lane >> 4) * 8;
+      // A = M^T through ldmatrix.trans: matrix m = lane / 8 -> memory rows (m >> 1) * 8 + lane % 8,
+      // channels 32 w + 16 mt + (m & 1) * 8
+      const int tr = ((lane >> 4) & 1) * 8 + (lane & 7);
+      const int tc = warp * (kD / kMemWarps) + ((lane >> 3) & 1) * 8;
 #pragma unroll
       for (int ks = 0; ks < kMemRowGroups; ++ks) {
 #pragma unroll
-        for (int pair = 0; pair < 2; ++pair) {
-          uint32_t bm[4];
-          ldmatrix_x4_trans(tile_u32 + mem_tile_off(ks * 16 + br, bc + pair * 16), bm);
-          mma_bf16_16816(acc[2 * pair], pa[ks], bm[0], bm[1]);
-          mma_bf16_16816(acc[2 * pair + 1], pa[ks], bm[2], bm[3]);
+        for (int mt = 0; mt < kMemMTiles; ++mt) {
+          uint32_t am[4];
+          ldmatrix_x4_trans(tile_u32 + mem_tile_off(ks * 16 + tr, tc + mt * 16), am);
+          mma_bf16_16816(acc[mt], am, pb[ks][0], pb[ks][1]);
         }
       }
     }
-    // normalise: acc[nt][0,1] = U[head g][32 w + 8 nt + 2 q4 + {0,1}]
+    // normalise and store: this lane holds heads 2 q4, 2 q4 + 1 of channels 32 w + 16 mt + g and + 8
     if (warp < NH) {
       const float l = warp_sum(l_run);
       if (lane == 0) s_inv[warp] = 1.f / l;
     }
     __syncthreads();
-    if (g < NH) {
-      const float inv = s_inv[g];
-      __nv_bfloat16* orow = p.out + (size_t(b) * NH + g) * kD + warp * 32 + 2 * q4;
+    if (2 * q4 < NH) {
+      const float inv0 = s_inv[2 * q4], inv1 = s_inv[2 * q4 + 1];
+      __nv_bfloat16* o0 = p.out + (size_t(b) * NH + 2 * q4) * kD + warp * (kD / kMemWarps) + g;
+      __nv_bfloat16* o1 = o0 + kD;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        *reinterpret_cast<uint32_t*>(orow + nt * 8) = pack_bf16x2(acc[nt][0] * inv, acc[nt][1] * inv);
+      for (int mt = 0; mt < kMemMTiles; ++mt) {
+        o0[mt * 16] = __float2bfloat16(acc[mt][0] * inv0);
+        o1[mt * 16] = __float2bfloat16(acc[mt][1] * inv1);
+        o0[mt * 16 + 8] = __float2bfloat16(acc[mt][2] * inv0);
+        o1[mt * 16 + 8] = __float2bfloat16(acc[mt][3] * inv1);
+      }
     }
   }
 }
@@ -428,9 +438,9 @@ cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, c
     attr_done = true;
   }
   if (p.nhead == 4)
-    return launch_kernel(mem_attn_kernel<4>, dim3(grid), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
+    return launch_kernel(mem_attn_kernel<4>, dim3(grid), dim3(kMemWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   if (p.nhead == 2)
-    return launch_kernel(mem_attn_kernel<2>, dim3(grid), dim3(kAttnWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
+    return launch_kernel(mem_attn_kernel<2>, dim3(grid), dim3(kMemWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   return cudaErrorInvalidValue;
 }
 

@@ -236,7 +236,7 @@ struct MemAttnParams {
   int const_len = 0;
   __nv_bfloat16* out = nullptr;
 };
-constexpr int kMemAttnTileRows = 64;  // memory rows per shared-memory tile of the absorbed cross-attention
+constexpr int kMemAttnTileRows = 32;  // memory rows per shared-memory tile of the absorbed cross-attention
 // tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, kMemAttnTileRows}
 cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream);
 
