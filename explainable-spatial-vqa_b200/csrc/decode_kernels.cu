@@ -214,6 +214,9 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
   __shared__ float s_part[kMemKSplit][NH][kScPad];   // partial scores of the current tile (channel slices)
   __shared__ __align__(16) __nv_bfloat16 s_p[NH][kMemTileRows];  // softmax weights of the current tile
   __shared__ float s_alpha[NH], s_inv[NH];
+  // absorbed queries of the current / next question (row pitch 132 words: heads land in different banks); they arrive
+  // with the question's first tile, so no global-load latency sits between two questions
+  __shared__ __align__(16) uint32_t s_q[2][NH][132];
   __shared__ __align__(8) uint64_t full_bar[kMemStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q4 = lane & 3;
@@ -235,14 +238,21 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
 
   // Producer cursor (thread 0): the CTA walks questions blockIdx.x, + gridDim.x, ... and the tiles inside each; loads
   // run kMemStages - 1 tiles ahead of the consumers across question boundaries.
-  int pq = blockIdx.x, pt = 0, p_len = 0, issued = 0;
+  int pq = blockIdx.x, pt = 0, p_len = 0, issued = 0, p_questions = 0;
   auto issue_next = [&]() {
     if (pq < p.B) {
       if (pt == 0) p_len = len_of(pq);
       const int st = issued % kMemStages;
       const uint32_t dst = ring_u32 + st * kMemStageBytes;
       const int row = pq * int(p.rows_per_q) + pt * kMemTileRows;
-      mbar_expect_tx(&full_bar[st], kMemStageBytes);
+      mbar_expect_tx(&full_bar[st], kMemStageBytes + (pt == 0 ? NH * kD * 2 : 0));
+      if (pt == 0) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          bulk_load_u32(smem_u32(&s_q[p_questions & 1][h][0]), p.qp + (size_t(pq) * NH + h) * kD, kD * 2,
+                        &full_bar[st]);
+        ++p_questions;
+      }
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) tma_load_2d_u32(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row);
       if ((++pt) * kMemTileRows >= p_len) {
@@ -255,23 +265,14 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
   if (threadIdx.x == 0)
     for (int i = 0; i < kMemStages - 1; ++i) issue_next();
   const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
-  int consumed = 0;
+  int consumed = 0, questions = 0;
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const int len = len_of(b);
     const int n_tiles = (len + kMemTileRows - 1) / kMemTileRows;
     // absorbed queries as B fragments of this warp's channel slice: bq[k] = q'[head g][16 ks + 2 q4 + {0,1}],
-    // [.. + 8 + {0,1}] with ks = kMemKSteps kh + k; heads >= NH are zero columns
+    // [.. + 8 + {0,1}] with ks = kMemKSteps kh + k; heads >= NH are zero columns.  Filled from s_q at the first tile.
     uint32_t bq[kMemKSteps][2];
-    {
-      const uint32_t* qrow =
-          reinterpret_cast<const uint32_t*>(p.qp + (size_t(b) * NH + (g < NH ? g : 0)) * kD) + kh * kMemKSteps * 8;
-#pragma unroll
-      for (int k = 0; k < kMemKSteps; ++k) {
-        bq[k][0] = g < NH ? __ldg(qrow + k * 8 + q4) : 0u;
-        bq[k][1] = g < NH ? __ldg(qrow + k * 8 + q4 + 4) : 0u;
-      }
-    }
     float m_run = -INFINITY, l_run = 0.f;  // softmax warps: running max (warp-uniform) and this lane's share of the sum
     // acc[mt] = U^T[channels 32 w + 16 mt + g (+8)][heads 2 q4, 2 q4 + 1]: the value product is computed transposed
     // (channels on the 16 MMA rows, heads on the 8 columns) - half the MMAs of heads-on-rows
@@ -288,6 +289,15 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
       mbar_wait(&full_bar[st], uint32_t(consumed / kMemStages) & 1u);
       const uint32_t tile_u32 = ring_u32 + st * kMemStageBytes;
       ++consumed;
+      if (i == 0) {
+        const uint32_t* qrow = &s_q[questions & 1][g < NH ? g : 0][kh * kMemKSteps * 8];
+#pragma unroll
+        for (int k = 0; k < kMemKSteps; ++k) {
+          bq[k][0] = g < NH ? qrow[k * 8 + q4] : 0u;
+          bq[k][1] = g < NH ? qrow[k * 8 + q4 + 4] : 0u;
+        }
+        ++questions;
+      }
       {
         // partial scores of this warp's 16 rows over its channel slice
         const int ar = rg * 16 + (lane & 15);
