@@ -405,16 +405,15 @@ int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
 // ---------------------------------------------------------------------------------------------
 // GEMM helpers
 // ---------------------------------------------------------------------------------------------
-// box_cols == 0: 128-byte swizzled operand box; otherwise the un-swizzled {box_cols, box_rows} store box
+// cached 2D operand tensor map: 128-byte swizzle, box = {128 bytes of the inner dimension, box_rows}
 int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
-             uint32_t box_rows, const CUtensorMap** out, uint32_t box_cols = 0) {
-  TmapKey key{base, int(type), rows, cols, ld, box_rows, box_cols};
+             uint32_t box_rows, const CUtensorMap** out) {
+  TmapKey key{base, int(type), rows, cols, ld, box_rows, 0u};
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
     if (h->tmaps.size() > 4096) h->tmaps.clear();
     CUtensorMap m;
-    int rc = box_cols ? make_tmap_2d_store(&m, base, type, rows, cols, ld, box_cols, box_rows)
-                      : make_tmap_2d(&m, base, type, rows, cols, ld, box_rows);
+    int rc = make_tmap_2d(&m, base, type, rows, cols, ld, box_rows);
     if (rc != B200VQA_OK) return rc;
     it = h->tmaps.emplace(key, m).first;
   }
@@ -474,16 +473,14 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
   // Chosen per call site, never by M: the two kernels round the statistics differently, and a question's result must
   // not depend on how many other questions share its batch.
   if (epi == kEpiBiasResLN && p.ln_cluster && K == 256 && N == 256 && !h->no_ln_cluster) bn = 64;
-  const CUtensorMap *ta, *tw, *to;
+  const CUtensorMap *ta, *tw;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(a_cols > 0 ? a_cols : K), uint64_t(lda), 128, &ta));
   RC_OK(get_tmap(h, W, ty, uint64_t(epi == kEpiHead ? p.head_V : N), uint64_t(K), uint64_t(K), bn, &tw));
-  if (epi == kEpiBiasPeRemap || epi == kEpiHead) to = ta;  // unused by those epilogues
-  else RC_OK(get_tmap(h, p.out, TmapType::kBF16, uint64_t(M), uint64_t(N), uint64_t(p.ldc), 32, &to, 32));
   p.M = M;
   p.N = N;
   p.K = K;
-  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, *to, p, h->num_sms, s));
+  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, p, h->num_sms, s));
   return B200VQA_OK;
 }
 
@@ -1649,11 +1646,9 @@ B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   B200VQA_CUDA_OK(cudaGetDevice(&dev));
   RC_OK(require_sm100(dev, &num_sms));
   const TmapType ty = a->tf32 ? TmapType::kF32 : TmapType::kBF16;
-  CUtensorMap ta, tw, to;
+  CUtensorMap ta, tw;
   RC_OK(make_tmap_2d(&ta, a->A, ty, uint64_t(a->M), uint64_t(a->K), uint64_t(a->K), 128));
   RC_OK(make_tmap_2d(&tw, a->W, ty, uint64_t(a->N), uint64_t(a->K), uint64_t(a->K), uint32_t(a->block_n)));
-  if (a->epilogue == kEpiBiasPeRemap) to = ta;
-  else RC_OK(make_tmap_2d_store(&to, a->out, TmapType::kBF16, uint64_t(a->M), uint64_t(a->N), uint64_t(a->ldc), 32, 32));
   GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.bias = a->bias;
@@ -1670,7 +1665,7 @@ B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   p.pe = a->pe;
   p.pe_off = a->pe_off;
   p.dbg_clk = a->clk;
-  B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, to, p, num_sms,
+  B200VQA_CUDA_OK(launch_gemm(a->epilogue, a->tf32 != 0, a->block_n, ta, tw, p, num_sms,
                               static_cast<cudaStream_t>(stream)));
   return B200VQA_OK;
 }

@@ -12,9 +12,9 @@
 // Structure (one CTA per SM, 320 threads):
 //   warp 0      : TMA producer   - operand tiles into shared memory (128-byte swizzle)
 //   warp 1      : MMA issuer     - tcgen05.mma (M=128, N=BN, K=32 B) accumulating into TMEM; owns the TMEM allocation
-//   warps 2..9  : epilogue       - two warps per TMEM lane quarter, each taking every other 32-column chunk:
-//                                  tcgen05.ld -> fused bias / ReLU / residual+LayerNorm -> bf16 tile staged in
-//                                  shared memory -> TMA store (coalesced; rows >= M are clipped by the tensor map)
+//   warps 2..9  : epilogue       - two warps per TMEM lane quarter (four for LayerNorm), each taking every other
+//                                  32-column chunk: tcgen05.ld -> fused bias / ReLU / residual+LayerNorm -> bf16 chunk
+//                                  transposed through a swizzled shared-memory tile -> coalesced 16-byte stores
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop
 // of tile i+1.
 //
@@ -82,8 +82,7 @@ __device__ __forceinline__ void store_chunk_bf16(uint8_t* buf, const uint32_t (&
 
 template <int BN, int EPI, bool TF32>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const GemmParams p) {
   using L = GemmSmem<BN>;
   constexpr uint32_t kTmemCols = kAccStages * BN;
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
@@ -134,7 +133,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
-    (void)tm_out;  // outputs leave through coalesced plain stores (store_chunk_bf16); kept for ABI stability
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -594,8 +592,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 template <int BN, int EPI, bool TF32>
-cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const CUtensorMap& tm_out,
-                       const GemmParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p, int num_sms,
+                       cudaStream_t stream) {
   using L = GemmSmem<BN>;
   auto kfn = gemm_tc_kernel<BN, EPI, TF32>;
   static bool attr_done = false;
@@ -607,7 +605,7 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const C
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  return launch_kernel(kfn, dim3(grid), dim3(gemm_threads(EPI)), L::kBytes, stream, p.pdl, tm_a, tm_w, tm_out, p);
+  return launch_kernel(kfn, dim3(grid), dim3(gemm_threads(EPI)), L::kBytes, stream, p.pdl, tm_a, tm_w, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -867,7 +865,7 @@ __global__ void gemm_check_kernel(const TA* __restrict__ A, const TA* __restrict
 }  // namespace
 
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
-                        const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream) {
+                        const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (block_n <= 0 || p.N % block_n != 0) return cudaErrorInvalidValue;
   if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N)) return cudaErrorInvalidValue;
   if (epilogue == kEpiLstm && (block_n != 256 || p.N % 256 != 0)) return cudaErrorInvalidValue;
@@ -878,7 +876,7 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \
-    return launch_one<BN_, EPI_, TF_>(tm_a, tm_w, tm_out, p, num_sms, stream);
+    return launch_one<BN_, EPI_, TF_>(tm_a, tm_w, p, num_sms, stream);
   B200VQA_GEMM_CASE(256, kEpiBias, false)
   B200VQA_GEMM_CASE(128, kEpiBias, false)
   B200VQA_GEMM_CASE(64, kEpiBias, false)

@@ -51,11 +51,6 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t row
   return encode_2d(out, base, type, rows, cols, ld, 128 / esz, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int make_tmap_2d_store(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
-                       uint32_t box_cols, uint32_t box_rows) {
-  return encode_2d(out, base, type, rows, cols, ld, box_cols, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
-}
-
 static int encode_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = resolve_encode();

@@ -39,10 +39,6 @@ enum class TmapType { kBF16, kF32 };
 // 128-byte swizzle; out-of-bounds elements read as zero.
 int make_tmap_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows);
-// Same tensor, un-swizzled box of {box_cols elements, box_rows}: the shared->global store path of the epilogues.
-int make_tmap_2d_store(CUtensorMap* out, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
-                       uint32_t box_cols, uint32_t box_rows);
-
 // Verifies the device is compute capability 10.x (B200) - there is no other code path.
 int require_sm100(int device, int* num_sms);
 

@@ -97,10 +97,9 @@ struct GemmParams {
 };
 
 // A/W tensor maps: 2D, 128-byte swizzle, box = {128 B of K, 128 rows (A) | BN rows (W)}.
-// tm_out: the bf16 output [M, N] (leading dimension ldc), un-swizzled box {32 columns, 32 rows} for the epilogue's
-// TMA stores (ignored by kEpiBiasPeRemap, which scatters rows).
+// The output leaves through plain coalesced stores (p.out, leading dimension p.ldc).
 cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
-                        const CUtensorMap& tm_out, const GemmParams& p, int num_sms, cudaStream_t stream);
+                        const GemmParams& p, int num_sms, cudaStream_t stream);
 
 // Plain CUDA-core GEMM used ONLY by the test suite to cross-check the tensor-core kernel on the GPU
 // at sizes where a host check is too slow. fp32 accumulate over the same bf16 (or fp32) inputs.

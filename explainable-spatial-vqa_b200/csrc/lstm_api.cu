@@ -94,7 +94,7 @@ int lstm_step(b200vqa_lstm* h, int B, int src, const __nv_bfloat16* whh, const f
   p.lstm_c = h->c;
   p.lstm_h = h->h[src ^ 1];
   p.lstm_h_f32 = want_f32 ? h->hf : nullptr;
-  B200VQA_CUDA_OK(launch_gemm(kEpiLstm, false, 256, ta, tw, ta, p, h->num_sms, s));
+  B200VQA_CUDA_OK(launch_gemm(kEpiLstm, false, 256, ta, tw, p, h->num_sms, s));
   ++h->launches;
   return B200VQA_OK;
 }
@@ -135,7 +135,7 @@ int enqueue_generate(b200vqa_lstm* h, int B, int q_len, int T, int start_token, 
     p.tok_ld = kLstmTokLd;
     p.logits = logits;
     p.logits_T = T;
-    B200VQA_CUDA_OK(launch_gemm(kEpiHead, true, bn, ta, tw, ta, p, h->num_sms, s));
+    B200VQA_CUDA_OK(launch_gemm(kEpiHead, true, bn, ta, tw, p, h->num_sms, s));
     ++h->launches;
   }
   return B200VQA_OK;

@@ -111,33 +111,6 @@ __device__ __forceinline__ void bulk_load_u32(uint32_t dst_smem, const void* src
                : "memory");
 }
 
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-// 2D tile store shared -> global (bulk async-group completion). Rows/columns outside the tensor map are clipped.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// wait until at most N of this thread's bulk groups still READ their shared-memory source
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all() {
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor still runs; pdl_wait() blocks until the predecessor grid has completed and its memory is
 // visible (no-op for a normal launch), pdl_launch_dependents() lets the successor's prologue begin early.
@@ -193,9 +166,6 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_smem_addr,
   uint32_t a;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_smem_addr), "r"(rank));
   return a;
-}
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float x, float y) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
 }
 // asynchronous 8-byte store into a peer CTA's shared memory; its arrival performs complete_tx(8) on the mbarrier at
 // `cluster_mbar` (same peer), so the receiver needs no cluster-wide barrier: it waits on its own mbarrier
