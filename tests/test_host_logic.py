@@ -174,3 +174,19 @@ def test_modules_survive_deepcopy_and_pickle():
     m2.load_state_dict(torch.load(buf))
     f2 = copy.deepcopy(common.seeded_fa())
     assert f2._pool._module is f2
+
+
+def test_oracle_tally_follows_reference_loop():
+    """oracle.iqap_tally restates inference_transformer_iqap_tally.py:317-344: torch.max keeps the FIRST maximum, a
+    program is correct only if all 27 tokens match, and the four cases partition the samples."""
+    import torch
+    from oracle import executor_oracle as orc
+    logits = torch.tensor([[0.0, 2.0, 2.0], [1.0, 0.0, 0.0], [0.0, 0.0, 3.0], [5.0, 5.0, 5.0]])
+    progs = torch.arange(4 * 27).view(4, 27)
+    gt_p = progs.clone()
+    gt_p[1, 26] += 1          # last token differs
+    gt_p[3, 0] += 1
+    gt_a = torch.tensor([1, 0, 0, 1])   # sample 0: tie -> class 1 (first max) correct; 2: wrong; 3: tie -> class 0, wrong
+    counts, preds = orc.iqap_tally(logits, progs, gt_a, gt_p)
+    assert preds == [1, 0, 2, 0]
+    assert counts == [1, 1, 1, 1]
