@@ -111,6 +111,7 @@ SIGNATURES = {
     "b200vqa_dbg_gemm": (C.c_int, [C.POINTER(DbgGemmArgs), _vp]),
     "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "b200vqa_dbg_mem_attn": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -133,6 +133,8 @@ struct b200vqa_handle {
   bool absorb = true;          // cross-attention reads the encoder memory directly (B200VQA_NO_ABSORB=1: K|V rows)
   int stagger_us = 0;          // start delay of every other decode branch (B200VQA_BRANCH_STAGGER_US)
   int stagger_mod = 2;
+  bool mem_attn_tc = false;    // B200VQA_MEM_ATTN=tc|mma: absorbed cross-attention on tcgen05 (cluster of two CTAs per
+                               // question) or on warp-level MMAs (persistent ring kernel)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
@@ -647,8 +649,15 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
         const CUtensorMap* tmem_map;
-        RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
-        LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
+        if (h->mem_attn_tc) {
+          const CUtensorMap* tq_map;
+          RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128, &tmem_map));
+          RC_OK(get_tmap(h, dq, TmapType::kBF16, uint64_t(B) * d.nhead, kD, kD, uint32_t(d.nhead), &tq_map));
+          LAUNCH_OK(h, launch_mem_attn_tc(*tmem_map, *tq_map, mp, s));
+        } else {
+          RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
+          LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
+        }
         GemmParams vp;
         vp.bias = L.cross_attn.b_in + 2 * kD;
         vp.out = dattn;
@@ -999,6 +1008,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_ABSORB")) h->absorb = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
+  if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_tc = g[0] == 't';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
@@ -1695,6 +1705,34 @@ B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, 
   ap.v_mode = v_mode;
   B200VQA_CUDA_OK(launch_enc_attention(tq, tkv, static_cast<const __nv_bfloat16*>(qkv), ap,
                                        static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const int32_t* lens, int const_len, int B, int nhead,
+                                     int impl, void* out, long long* stamps, void* stream) {
+  B200VQA_REQUIRE(qp && memory && out && B > 0 && (nhead == 2 || nhead == 4), "bad arguments");
+  int dev = 0;
+  B200VQA_CUDA_OK(cudaGetDevice(&dev));
+  RC_OK(require_sm100(dev, nullptr));
+  MemAttnParams mp;
+  mp.B = B;
+  mp.nhead = nhead;
+  mp.qp = static_cast<const __nv_bfloat16*>(qp);
+  mp.rows_per_q = kLP;
+  mp.lens = lens;
+  mp.const_len = const_len;
+  mp.out = static_cast<__nv_bfloat16*>(out);
+  CUtensorMap tm, tq;
+  mp.tc_persistent = impl == 1;
+  mp.dbg = stamps;
+  if (impl >= 1) {
+    RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128));
+    RC_OK(make_tmap_2d(&tq, qp, TmapType::kBF16, uint64_t(B) * nhead, kD, kD, uint32_t(nhead)));
+    B200VQA_CUDA_OK(launch_mem_attn_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
+  } else {
+    RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows));
+    B200VQA_CUDA_OK(launch_mem_attn(tm, mp, static_cast<cudaStream_t>(stream)));
+  }
   return B200VQA_OK;
 }
 

@@ -167,6 +167,14 @@ __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t local_smem_addr,
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_smem_addr), "r"(rank));
   return a;
 }
+// plain stores into a peer CTA's shared memory (made visible by the cluster barrier that follows)
+__device__ __forceinline__ void st_cluster_f32x4(uint32_t cluster_addr, float x, float y, float z, float w) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float x) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(x) : "memory");
+}
 // asynchronous 8-byte store into a peer CTA's shared memory; its arrival performs complete_tx(8) on the mbarrier at
 // `cluster_mbar` (same peer), so the receiver needs no cluster-wide barrier: it waits on its own mbarrier
 __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float x, float y, uint32_t cluster_mbar) {
@@ -245,6 +253,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 4 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -159,3 +159,56 @@ def test_encoder_attention_constant_len_matches_lens_array():
     nat.check(nat.lib().b200vqa_dbg_enc_attention(qkv.data_ptr(), lens.data_ptr(), 0, B, 4, 0, o2.data_ptr(), nat.stream_ptr()), "b")
     torch.cuda.synchronize()
     assert torch.equal(o1, o2)
+
+
+def ref_mem_attn(qp, mem, lens, nhead):
+    """u[b, h] = softmax_j(q'[b, h] . m[b, j] / sqrt(dh)) applied to the memory rows themselves (MemAttnParams)."""
+    B = qp.shape[0]
+    q = qp.float().view(B, nhead, 256)
+    m = mem.float().view(B, 256, 256)
+    s = torch.einsum("bhd,bjd->bhj", q, m) / (256 // nhead) ** 0.5
+    dead = torch.arange(256, device=qp.device)[None] >= lens[:, None]
+    s = s.masked_fill(dead[:, None, :], float("-inf"))
+    return torch.einsum("bhj,bjd->bhd", torch.softmax(s, -1), m).reshape(B, nhead * 256)
+
+
+def dbg_mem_attn(qp, mem, lens, const_len, nhead, impl):
+    B = qp.shape[0]
+    out = torch.full((B, nhead * 256), 7.0, dtype=torch.bfloat16, device="cuda")
+    nat.check(nat.lib().b200vqa_dbg_mem_attn(qp.data_ptr(), mem.data_ptr(), None if lens is None else lens.data_ptr(),
+                                             const_len, B, nhead, impl, out.data_ptr(), None, nat.stream_ptr()), "dbg_mem_attn")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("nhead", [4, 2])
+@pytest.mark.parametrize("impl", [1, 2, 0])
+def test_memory_attention_kernels(nhead, impl):
+    """Absorbed decode cross-attention, tcgen05 cluster kernel (impl 1) and warp-MMA ring kernel (impl 0), against fp32
+    torch math on the same bf16 operands: ragged lengths incl. a single row, exactly / just over one 128-row half,
+    the IQAP length and the maximum."""
+    g = torch.Generator(device="cuda").manual_seed(100 + nhead)
+    lens = torch.tensor([243, 1, 128, 129, 256, 197, 64, 200, 17, 255, 130, 243, 243], dtype=torch.int32, device="cuda")
+    B = len(lens)
+    mem = torch.randn(B * 256, 256, device="cuda", generator=g).bfloat16()
+    qp = (torch.randn(B, nhead * 256, device="cuda", generator=g) * 0.5).bfloat16()  # logits of a few units: peaked rows
+    out = dbg_mem_attn(qp, mem, lens, 0, nhead, impl)
+    ref = ref_mem_attn(qp, mem, lens, nhead)
+    assert torch.isfinite(out.float()).all()
+    for b in range(B):
+        assert common.rel_err(out[b].float(), ref[b]) < 1.5e-2, (b, int(lens[b]))  # P rounded to bf16 before the product
+
+
+def test_memory_attention_tc_full_batch_and_constant_len():
+    """1024 questions at the IQAP length: every cluster lands on its own question; const_len == lens array."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B = 1024
+    mem = torch.randn(B * 256, 256, device="cuda", generator=g).bfloat16()
+    qp = (torch.randn(B, 4 * 256, device="cuda", generator=g) * 0.25).bfloat16()
+    lens = torch.full((B,), 243, dtype=torch.int32, device="cuda")
+    o1 = dbg_mem_attn(qp, mem, None, 243, 4, 1)
+    o2 = dbg_mem_attn(qp, mem, lens, 0, 4, 1)
+    assert torch.equal(o1, o2)
+    ref = ref_mem_attn(qp, mem, lens, 4)
+    err = (o1.float() - ref).abs().amax(1) / ref.abs().amax(1)
+    assert float(err.max()) < 1.5e-2, int(err.argmax())
