@@ -133,8 +133,9 @@ struct b200vqa_handle {
   bool absorb = true;          // cross-attention reads the encoder memory directly (B200VQA_NO_ABSORB=1: K|V rows)
   int stagger_us = 0;          // start delay of every other decode branch (B200VQA_BRANCH_STAGGER_US)
   int stagger_mod = 2;
-  bool mem_attn_tc = false;    // B200VQA_MEM_ATTN=tc|mma: absorbed cross-attention on tcgen05 (cluster of two CTAs per
-                               // question) or on warp-level MMAs (persistent ring kernel)
+  int mem_attn_impl = 0;       // B200VQA_MEM_ATTN=mma|tc|ring: absorbed cross-attention on warp-level MMAs (persistent ring
+                               // kernel, 0), on tcgen05 with a cluster of two CTAs per question (1) or on tcgen05 with
+                               // one persistent CTA per SM and a three-stage tile ring (3)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
@@ -649,11 +650,14 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
         const CUtensorMap* tmem_map;
-        if (h->mem_attn_tc) {
+        if (h->mem_attn_impl != 0) {
           const CUtensorMap* tq_map;
           RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128, &tmem_map));
           RC_OK(get_tmap(h, dq, TmapType::kBF16, uint64_t(B) * d.nhead, kD, kD, uint32_t(d.nhead), &tq_map));
-          LAUNCH_OK(h, launch_mem_attn_tc(*tmem_map, *tq_map, mp, s));
+          if (h->mem_attn_impl == 3)
+            LAUNCH_OK(h, launch_mem_attn_ring_tc(*tmem_map, *tq_map, mp, s));
+          else
+            LAUNCH_OK(h, launch_mem_attn_tc(*tmem_map, *tq_map, mp, s));
         } else {
           RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
           LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
@@ -1008,7 +1012,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_ABSORB")) h->absorb = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
-  if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_tc = g[0] == 't';
+  if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_impl = g[0] == 't' ? 1 : (g[0] == 'r' ? 3 : 0);
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
@@ -1728,7 +1732,10 @@ B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const i
   if (impl >= 1) {
     RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128));
     RC_OK(make_tmap_2d(&tq, qp, TmapType::kBF16, uint64_t(B) * nhead, kD, kD, uint32_t(nhead)));
-    B200VQA_CUDA_OK(launch_mem_attn_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
+    if (impl == 3)
+      B200VQA_CUDA_OK(launch_mem_attn_ring_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
+    else
+      B200VQA_CUDA_OK(launch_mem_attn_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
   } else {
     RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows));
     B200VQA_CUDA_OK(launch_mem_attn(tm, mp, static_cast<cudaStream_t>(stream)));

@@ -657,6 +657,239 @@ mem_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_mem, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same tcgen05 arithmetic as mem_attn_tc_kernel with ONE persistent CTA per SM that owns whole questions: the
+// 128-row halves stream through a ring of three 64 KB stages filled by a producer thread that runs ahead across
+// question boundaries (two stages are always loading while the third is being consumed), the MMA thread issues the
+// score MMAs of tile t + 1 before the value MMAs of tile t (score accumulators and P double-buffered by tile parity),
+// and the halves of a question are combined inside the CTA (value accumulators per (question parity, half of the
+// memory, half of the channels) in TMEM) - no cluster, no distributed shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMrStages = 3;
+constexpr int kMrThreads = 192;  // warps 0-3 softmax / combine, warp 4 TMA producer, warp 5 MMA issue
+constexpr int kMrOffQ = kMrStages * kMtTileBytes;  // [2 question parities] 4 x 1 KB query blocks (heads 8..15 alias + 4 KB)
+constexpr int kMrOffP = kMrOffQ + 2 * 4096;        // [2 tile parities] 2 x 1 KB P blocks (heads 8..15 alias + 2 KB)
+constexpr int kMrOffMisc = kMrOffP + 2 * 2048;     // statistics, mbarriers, TMEM slot
+constexpr int kMrSmem = kMrOffMisc + 3072;         // the aliased rows of the last P buffer end at kMrOffP + 2048 + 4096
+static_assert(kMrOffQ + 4096 + 3 * 1024 + kMtQSbo + 1024 <= kMrSmem && kMrOffP + 2048 + 1024 + kMtPSbo + 1024 <= kMrSmem,
+              "aliases");
+
+struct MrTileIter {  // the tiles of this CTA in processing order; every role walks the same sequence
+  int q, i, n, g, qi, stride, B;
+  const int32_t* lens;
+  int const_len;
+  __device__ __forceinline__ int tiles_of(int qq) const {
+    int len = lens ? lens[qq] : const_len;
+    len = len > kLP ? kLP : (len < 1 ? 1 : len);
+    return (len + kMtRows - 1) / kMtRows;
+  }
+  __device__ __forceinline__ int len_of(int qq) const {
+    const int len = lens ? lens[qq] : const_len;
+    return len > kLP ? kLP : (len < 1 ? 1 : len);
+  }
+  __device__ __forceinline__ void init(const MemAttnParams& p) {
+    q = blockIdx.x; i = 0; g = 0; qi = 0; stride = gridDim.x; B = p.B; lens = p.lens; const_len = p.const_len;
+    n = q < B ? tiles_of(q) : 0;
+  }
+  __device__ __forceinline__ bool done() const { return q >= B; }
+  __device__ __forceinline__ void next() {
+    ++g;
+    if (++i == n) {
+      i = 0;
+      q += stride;
+      ++qi;
+      n = q < B ? tiles_of(q) : 0;
+    }
+  }
+};
+
+template <int NH>
+__global__ void __launch_bounds__(kMrThreads, 1)
+mem_attn_ring_tc_kernel(const __grid_constant__ CUtensorMap tm_mem, const __grid_constant__ CUtensorMap tm_q,
+                        const MemAttnParams p) {
+  static_assert(NH == 2 || NH == 4, "heads");
+  extern __shared__ __align__(1024) uint8_t mr_smem[];
+  const uint32_t sbase = smem_u32(mr_smem);
+  if ((sbase & 1023u) != 0) __trap();
+  float* s_wmax = reinterpret_cast<float*>(mr_smem + kMrOffMisc);  // [warp][4]
+  float* s_wsum = s_wmax + 16;                                     // [warp][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mr_smem + kMrOffMisc + 256);
+  uint64_t* bar_full = bars + 0;    // [3] stage landed (+ the queries with a question's first tile)
+  uint64_t* bar_empty = bars + 3;   // [3] the value MMAs that read the stage have retired
+  uint64_t* bar_s = bars + 6;       // [2] score accumulator of tile parity complete
+  uint64_t* bar_p = bars + 8;       // [2] P of tile parity written (128 arrivals)
+  uint64_t* bar_u = bars + 10;      // [2] value accumulators of question parity complete
+  uint64_t* bar_ufree = bars + 12;  // [2] ... and read by the combine step (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tm_mem);
+    tma_prefetch_desc(&tm_q);
+    for (int i = 0; i < kMrStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 128);
+      mbar_init(&bar_u[i], 1);
+      mbar_init(&bar_ufree[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  pdl_launch_dependents();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  MrTileIter t;
+  t.init(p);
+  // TMEM columns: scores [tile parity] at 16 * parity; values [question parity][half of the memory][half of the channels]
+  auto u_col = [](int qpar, int i, int half) { return uint32_t(32 + ((qpar * 2 + i) * 2 + half) * 16); };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (; !t.done(); t.next()) {
+        const int st = t.g % kMrStages;
+        mbar_wait(&bar_empty[st], ((t.g / kMrStages) & 1) ^ 1);  // passes at once on a fresh barrier
+        mbar_expect_tx(&bar_full[st], kMtTileBytes + (t.i == 0 ? 4 * NH * 128 : 0));
+        if (t.i == 0) {
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+            tma_load_2d_u32(&tm_q, &bar_full[st], sbase + kMrOffQ + (t.qi & 1) * 4096 + cb * 1024, cb * 64, t.q * NH);
+        }
+        const int row = t.q * int(p.rows_per_q) + t.i * kMtRows;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+          tma_load_2d_u32(&tm_mem, &bar_full[st], sbase + st * kMtTileBytes + cb * kMtBlockBytes, cb * 64, row);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(kFmtBF16, 128, 16, 0, 0);
+      constexpr uint32_t idesc_v = make_idesc(kFmtBF16, 128, 16, 1, 0);
+      auto issue_scores = [&](const MrTileIter& x) {
+        const int st = x.g % kMrStages;
+        mbar_wait(&bar_full[st], (x.g / kMrStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t tile = sbase + st * kMtTileBytes, qb = sbase + kMrOffQ + (x.qi & 1) * 4096;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem + (x.g & 1) * 16, make_smem_desc_sw128(tile + (k / 4) * kMtBlockBytes + (k % 4) * 32, 16, 1024),
+                    make_smem_desc_sw128(qb + (k / 4) * 1024 + (k % 4) * 32, 16, kMtQSbo), idesc_s, k != 0);
+        umma_commit(&bar_s[x.g & 1]);
+      };
+      if (!t.done()) issue_scores(t);
+      while (!t.done()) {
+        MrTileIter nx = t;
+        nx.next();
+        if (!nx.done()) issue_scores(nx);  // S(t + 1) runs under the softmax of tile t
+        const int st = t.g % kMrStages, qpar = t.qi & 1;
+        mbar_wait(&bar_p[t.g & 1], (t.g >> 1) & 1);
+        if (t.i == 0 && t.qi >= 2) mbar_wait(&bar_ufree[qpar], ((t.qi >> 1) - 1) & 1);  // accumulators of question qi - 2 read
+        tc_fence_after_sync();
+        const uint32_t tile = sbase + st * kMtTileBytes, pb = sbase + kMrOffP + (t.g & 1) * 2048;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int k = 0; k < kMtRows / 16; ++k)
+            umma_bf16(tmem + u_col(qpar, t.i, half),
+                      make_smem_desc_sw128(tile + half * 2 * kMtBlockBytes + k * 2048, kMtBlockBytes, 1024),
+                      make_smem_desc_sw128(pb + (k / 4) * 1024 + (k % 4) * 32, 16, kMtPSbo), idesc_v, k != 0);
+        umma_commit(&bar_empty[st]);
+        if (t.i == t.n - 1) umma_commit(&bar_u[qpar]);
+        t = nx;
+      }
+    }
+  } else {
+    const int r = threadIdx.x;  // memory row inside a tile == TMEM lane; in the combine step: channels r and 128 + r
+    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
+    const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
+    float m_t[2][NH], l_t[2][NH];  // per half of the memory: max and sum of exp2(S - max) of the current question
+    for (; !t.done(); t.next()) {
+      const int valid = min(kMtRows, t.len_of(t.q) - t.i * kMtRows);
+      const int sp = t.g & 1;
+      mbar_wait(&bar_s[sp], (t.g >> 1) & 1);  // also: the value MMAs of tile g - 2 (readers of this P buffer) have retired
+      __syncwarp();
+      tc_fence_after_sync();
+      uint32_t sv[4];
+      tmem_ld4(tlane + sp * 16, sv);
+      tmem_ld_wait();
+      float v[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        v[h] = r < valid ? __uint_as_float(sv[h]) * sl2 : -INFINITY;
+        const float wm = warp_max(v[h]);
+        if (lane == 0) s_wmax[warp * 4 + h] = wm;
+      }
+      named_bar_sync(1, 128);
+      uint8_t* prow = mr_smem + kMrOffP + sp * 2048 + (r >> 6) * 1024 + (r & 7) * 2;
+      float ps[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float m = fmaxf(fmaxf(s_wmax[h], s_wmax[4 + h]), fmaxf(s_wmax[8 + h], s_wmax[12 + h]));  // finite: row 0 is valid
+        const __nv_bfloat16 pb = __float2bfloat16(exp2f(v[h] - m));
+        *reinterpret_cast<__nv_bfloat16*>(prow + h * 128 + ((((r & 63) >> 3) ^ h) << 4)) = pb;
+        ps[h] = __bfloat162float(pb);  // normalise by what the tensor core will actually sum
+        if (t.i == 0) m_t[0][h] = m; else m_t[1][h] = m;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_p[sp]);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float ws = warp_sum(ps[h]);
+        if (lane == 0) s_wsum[warp * 4 + h] = ws;
+      }
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float l = (s_wsum[h] + s_wsum[4 + h]) + (s_wsum[8 + h] + s_wsum[12 + h]);
+        if (t.i == 0) l_t[0][h] = l; else l_t[1][h] = l;
+      }
+      if (t.i == t.n - 1) {
+        // combine the halves of the question: u = (w_0 U_0 + w_1 U_1) / (w_0 l_0 + w_1 l_1), w_i = exp2(max_i - max)
+        const int qpar = t.qi & 1;
+        float w0[NH], w1[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const float m1 = t.n == 2 ? m_t[1][h] : -INFINITY, l1 = t.n == 2 ? l_t[1][h] : 0.f;
+          const float m = fmaxf(m_t[0][h], m1);
+          const float a = exp2f(m_t[0][h] - m), b = exp2f(m1 - m);
+          const float inv = 1.f / (a * l_t[0][h] + b * l1);
+          w0[h] = a * inv;
+          w1[h] = b * inv;
+        }
+        mbar_wait(&bar_u[qpar], (t.qi >> 1) & 1);
+        __syncwarp();
+        tc_fence_after_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t a[4], b[4] = {0u, 0u, 0u, 0u};
+          tmem_ld4(tlane + u_col(qpar, 0, half), a);
+          if (t.n == 2) tmem_ld4(tlane + u_col(qpar, 1, half), b);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+            p.out[(size_t(t.q) * NH + h) * kD + half * kMtRows + r] =
+                __float2bfloat16(w0[h] * __uint_as_float(a[h]) + (t.n == 2 ? w1[h] * __uint_as_float(b[h]) : 0.f));
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&bar_ufree[qpar]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
 __global__ void publish_tokens_kernel(const PublishParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * p.n_cols) return;
@@ -742,6 +975,32 @@ cudaError_t launch_mem_attn_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_
     return launch_kernel(mem_attn_tc_kernel<4>, dim3(2 * clusters), dim3(kMtThreads), kMtSmem, stream, p.pdl, tm_mem, tm_q, p);
   if (p.nhead == 2)
     return launch_kernel(mem_attn_tc_kernel<2>, dim3(2 * clusters), dim3(kMtThreads), kMtSmem, stream, p.pdl, tm_mem, tm_q, p);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_mem_attn_ring_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
+                                    cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(mem_attn_ring_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMrSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mem_attn_ring_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMrSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int grid = std::min(p.B, num_sms);  // persistent: one CTA per SM, questions blockIdx.x, + gridDim.x, ...
+  if (p.nhead == 4)
+    return launch_kernel(mem_attn_ring_tc_kernel<4>, dim3(grid), dim3(kMrThreads), kMrSmem, stream, p.pdl, tm_mem, tm_q, p);
+  if (p.nhead == 2)
+    return launch_kernel(mem_attn_ring_tc_kernel<2>, dim3(grid), dim3(kMrThreads), kMrSmem, stream, p.pdl, tm_mem, tm_q, p);
   return cudaErrorInvalidValue;
 }
 

@@ -243,6 +243,9 @@ cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, c
 // tcgen05 form: tm_mem with box {64 channels, 128 rows}; tm_q = qp as a 2D tensor [B * nhead, 256] bf16, box {64, nhead}
 cudaError_t launch_mem_attn_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
                                cudaStream_t stream);
+// tcgen05 form with one persistent CTA per SM and a three-stage ring of 128-row tiles (same tensor maps)
+cudaError_t launch_mem_attn_ring_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
+                                    cudaStream_t stream);
 
 // Weight packing for the absorbed cross-attention: in_proj_weight [3d, d] / in_proj_bias [3d] fp32 ->
 //   w_qk [nhead*d, d] bf16, row h*d + i = sum_e W_k[h*dh+e][i] * W_q[h*dh+e][:]     b_qk [nhead*d] likewise with b_q

@@ -342,7 +342,7 @@ B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, 
 /* absorbed decode cross-attention of one position: qp [B, nhead*256] bf16 (absorbed queries), memory [B*256, 256] bf16
  * -> out [B, nhead*256] bf16 (per-head attention-weighted memory); lens NULL -> const_len.
  * impl 0 = warp-MMA ring kernel, 1 = tcgen05 cluster kernel (persistent clusters), 2 = the same with one cluster per
- * question; stamps: optional device int64 [2*B, 16] stage stamps of the tcgen05 kernel (tools/microbench_mem_attn.py) */
+ * question, 3 = tcgen05 ring kernel (one persistent CTA per SM); stamps: optional device int64 [2*B, 16] stage stamps of the tcgen05 kernel (tools/microbench_mem_attn.py) */
 B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const int32_t* lens, int const_len, int B, int nhead,
                          int impl, void* out, long long* stamps, void* stream);
 

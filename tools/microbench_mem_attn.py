@@ -1,4 +1,5 @@
-"""Times the two absorbed cross-attention kernels (b200vqa_dbg_mem_attn: impl 0 = warp-MMA ring, 1 = tcgen05 cluster kernel with persistent clusters, 2 = one cluster per question)
+"""Times the two absorbed cross-attention kernels (b200vqa_dbg_mem_attn: impl 0 = warp-MMA ring, 1 = tcgen05 cluster kernel with persistent clusters, 2 = one cluster per question,
+3 = tcgen05 with one persistent CTA per SM and a three-stage tile ring)
 alone on cuda:0: CUDA events around `reps` back-to-back launches over `nbuf` rotating memory buffers (> L2 in total).
 
     python tools/microbench_mem_attn.py [B ...]
@@ -71,8 +72,8 @@ def stamps(B, impl, nhead=4, length=243):
 if __name__ == "__main__":
     sizes = [int(x) for x in sys.argv[1:]] or [128, 256, 512, 1024, 2048, 4096]
     for B in sizes:
-        for impl in (0, 1, 2):
+        for impl in (0, 1, 2, 3):
             us, gbs = run(B, impl)
-            print(f"B {B:5d} impl {('mma', 'tc ', 'tc1')[impl]} {us:8.2f} us/launch {gbs:8.1f} GB/s algorithmic", flush=True)
+            print(f"B {B:5d} impl {('mma', 'tc ', 'tc1', 'tcr')[impl]} {us:8.2f} us/launch {gbs:8.1f} GB/s algorithmic", flush=True)
     for impl in (1, 2):
         stamps(1024, impl)
