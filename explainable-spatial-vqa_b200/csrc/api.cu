@@ -47,6 +47,9 @@ struct LayerPacked {
   // decoder layers: absorbed cross-attention query weights, row h*d + i = W_k,h^T W_q,h (kernels.h: MemAttnParams)
   __nv_bfloat16* w_qk = nullptr;  // [nhead*d, d]
   float* b_qk = nullptr;          // [nhead*d]
+  // ... and the value + output projections as one map of the attention-weighted memory (kernels.h: launch_absorb_ov)
+  __nv_bfloat16* w_ov = nullptr;  // [d, nhead*d]
+  float* b_ov = nullptr;          // [d]
 };
 
 // Bump allocator over one cudaMalloc'ed arena (first pass measures, second pass assigns).
@@ -133,6 +136,10 @@ struct b200vqa_handle {
   bool absorb = true;          // cross-attention reads the encoder memory directly (B200VQA_NO_ABSORB=1: K|V rows)
   int stagger_us = 0;          // start delay of every other decode branch (B200VQA_BRANCH_STAGGER_US)
   int stagger_mod = 2;
+  bool absorb_ov = false;      // B200VQA_ABSORB_OV=1: value + output projection of the absorbed cross-attention folded into
+                               // ONE K = nhead*256 LayerNorm GEMM instead of grouped value GEMM + out_proj LayerNorm GEMM
+                               // (one launch fewer per layer and position, but four CTAs stream 4x the weight bytes:
+                               // measured 4.57 vs 4.47 ms per step, so off by default)
   int mem_attn_impl = 0;       // B200VQA_MEM_ATTN=mma|tc|ring: absorbed cross-attention on warp-level MMAs (persistent ring
                                // kernel, 0), on tcgen05 with a cluster of two CTAs per question (1) or on tcgen05 with
                                // one persistent CTA per SM and a three-stage tile ring (3)
@@ -197,6 +204,8 @@ void layout_weights(b200vqa_handle* h, Arena& a) {
     layout_mha(a, L.cross_attn, D);
     L.w_qk = a.take<__nv_bfloat16>(size_t(d.nhead) * D * D);
     L.b_qk = a.take<float>(size_t(d.nhead) * D);
+    L.w_ov = a.take<__nv_bfloat16>(size_t(d.nhead) * D * D);
+    L.b_ov = a.take<float>(D);
     L.w1 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
     L.b1 = a.take<float>(d.dim_ff);
     L.w2 = a.take<__nv_bfloat16>(size_t(d.dim_ff) * D);
@@ -263,6 +272,9 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
     PACK_OK(pack_mha(w.self_attn, L.self_attn, D, s));
     PACK_OK(pack_mha(w.multihead_attn, L.cross_attn, D, s));
     PACK_OK(launch_absorb_qk(w.multihead_attn.in_proj_weight, w.multihead_attn.in_proj_bias, d.nhead, L.w_qk, L.b_qk,
+                             s));
+    PACK_OK(launch_absorb_ov(w.multihead_attn.in_proj_weight, w.multihead_attn.in_proj_bias,
+                             w.multihead_attn.out_proj_weight, w.multihead_attn.out_proj_bias, d.nhead, L.w_ov, L.b_ov,
                              s));
     PACK_OK(launch_cast_bf16(w.linear1_weight, L.w1, size_t(d.dim_ff) * D, s));
     PACK_OK(copy_f32(L.b1, w.linear1_bias, d.dim_ff, s));
@@ -475,7 +487,8 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
   // statistics exchanged through distributed shared memory) instead of one SM owning the whole 128 x 256 epilogue.
   // Chosen per call site, never by M: the two kernels round the statistics differently, and a question's result must
   // not depend on how many other questions share its batch.
-  if (epi == kEpiBiasResLN && p.ln_cluster && K == 256 && N == 256 && !h->no_ln_cluster) bn = 64;
+  if (epi == kEpiBiasResLN && p.ln_cluster && (K == 256 || K == 512 || K == 1024) && N == 256 && !h->no_ln_cluster)
+    bn = 64;
   const CUtensorMap *ta, *tw;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(a_cols > 0 ? a_cols : K), uint64_t(lda), 128, &ta));
@@ -662,13 +675,15 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
           RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
           LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
         }
-        GemmParams vp;
-        vp.bias = L.cross_attn.b_in + 2 * kD;
-        vp.out = dattn;
-        vp.ldc = kD;
-        vp.a_group_cols = kD / d.nhead;
-        h->cur_tag = kTagDecGemm;
-        RC_OK(gemm(h, kEpiBias, false, du, B, kD, NHD, L.cross_attn.w_in + size_t(2) * kD * kD, kD, vp, s, NHD));
+        if (!h->absorb_ov) {
+          GemmParams vp;
+          vp.bias = L.cross_attn.b_in + 2 * kD;
+          vp.out = dattn;
+          vp.ldc = kD;
+          vp.a_group_cols = kD / d.nhead;
+          h->cur_tag = kTagDecGemm;
+          RC_OK(gemm(h, kEpiBias, false, du, B, kD, NHD, L.cross_attn.w_in + size_t(2) * kD * kD, kD, vp, s, NHD));
+        }
       } else {
         h->cur_tag = kTagDecGemm;
         RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
@@ -689,8 +704,11 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         LAUNCH_OK(h, launch_row_attn(cp, s));
       }
       h->cur_tag = kTagDecGemmLn;
-      RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s,
-                        true));
+      if (h->absorb && h->absorb_ov)  // x2 = LN2(x1 + W_ov u + b_ov): K = nhead * 256 streamed through the cluster kernel
+        RC_OK(gemm_res_ln(h, du, B, d.nhead * kD, L.w_ov, L.b_ov, dx1, L.n2w, L.n2b, dx2, nullptr, s, true));
+      else
+        RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s,
+                          true));
       {
         // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
         const CUtensorMap *tx, *tw1, *tw2;
@@ -1012,6 +1030,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_ABSORB")) h->absorb = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
+  if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_impl = g[0] == 't' ? 1 : (g[0] == 'r' ? 3 : 0);
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));

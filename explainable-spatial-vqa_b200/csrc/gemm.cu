@@ -622,27 +622,34 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const G
 // ------------------------------------------------------------------------------------------
 constexpr int kLnCl = 4;                      // CTAs per cluster = column slices of the 256-wide row
 constexpr int kLnBN = 256 / kLnCl;            // 64 columns per CTA
-constexpr int kLnKb = 4;                      // K = 256 bf16 = 4 k-blocks of 128 B
+constexpr int kLnMaxStages = 8;               // k-block stages of shared memory (A 16 KB + W 8 KB each)
 constexpr int kLnThreads = 32 + 8 * 32;
+// NKB = K / 64 k-blocks of 128 B: 4 (K = 256, every k-block has its own stage), 8 (K = 512) or 16 (K = 1024: the fused
+// value + output projection of the absorbed cross-attention; k-blocks 8..15 refill the stages as their MMAs retire)
+template <int NKB>
 struct LnClSmem {
-  static constexpr int kOffA = 0;                                   // 4 x [128 rows x 128 B]
-  static constexpr int kOffW = kOffA + kLnKb * kBM * kKBytes;       // 4 x [64 rows x 128 B]
-  static constexpr int kOffStg = kOffW + kLnKb * kLnBN * kKBytes;   // 8 warps x 2 KB
+  static constexpr int kStages = NKB < kLnMaxStages ? NKB : kLnMaxStages;
+  static constexpr int kOffA = 0;                                   // kStages x [128 rows x 128 B]
+  static constexpr int kOffW = kOffA + kStages * kBM * kKBytes;     // kStages x [64 rows x 128 B]
+  static constexpr int kOffStg = kOffW + kStages * kLnBN * kKBytes; // 8 warps x 2 KB
   static constexpr int kOffPart = kOffStg + 8 * 2048;               // float2 [2 * kLnCl parts][128 rows]
   static constexpr int kOffTab = kOffPart + 2 * kLnCl * kBM * 8;    // bias | gamma | beta of this slice (3 x 64 fp32)
   static constexpr int kOffBar = kOffTab + 3 * kLnBN * 4;
-  static constexpr int kBytes = kOffBar + 64;
+  static constexpr int kBytes = kOffBar + 256;
 };
 
+template <int NKB>
 __global__ void __cluster_dims__(kLnCl, 1, 1) __launch_bounds__(kLnThreads, 1)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                        const GemmParams p) {
-  using L = LnClSmem;
+  using L = LnClSmem<NKB>;
+  constexpr int NS = L::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [kLnKb] A k-blocks
-  uint64_t* w_full = full_bar + kLnKb;
-  uint64_t* acc_full = w_full + 1;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);  // [NS] A k-blocks (refills: A + W)
+  uint64_t* w_full = full_bar + NS;                                     // [NS] W k-blocks of the first pass
+  uint64_t* empty_bar = w_full + NS;                                    // [NS] the stage's MMAs have retired
+  uint64_t* acc_full = empty_bar + NS;
   uint64_t* stat_full = acc_full + 1;  // completes when all 2 * kLnCl statistic parts of the 128 rows have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 1);
   float* tab = reinterpret_cast<float*>(smem + L::kOffTab);
@@ -662,16 +669,20 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     if (lane == 0) {
       tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_w);
-      for (int kb = 0; kb < kLnKb; ++kb) mbar_init(&full_bar[kb], 1);
-      mbar_init(w_full, 1);
+      for (int kb = 0; kb < NS; ++kb) {
+        mbar_init(&full_bar[kb], 1);
+        mbar_init(&w_full[kb], 1);
+        mbar_init(&empty_bar[kb], 1);
+      }
       mbar_init(acc_full, 1);
       mbar_init(stat_full, 1);
       fence_mbar_init();
       mbar_expect_tx(stat_full, 2 * kLnCl * kBM * 8);
       // weights do not depend on the previous kernel
-      mbar_expect_tx(w_full, kLnKb * kLnBN * kKBytes);
-      for (int kb = 0; kb < kLnKb; ++kb)
-        tma_load_2d(&tm_w, w_full, smem + L::kOffW + kb * kLnBN * kKBytes, kb * 64, n0);
+      for (int kb = 0; kb < NS; ++kb) {
+        mbar_expect_tx(&w_full[kb], kLnBN * kKBytes);
+        tma_load_2d(&tm_w, &w_full[kb], smem + L::kOffW + kb * kLnBN * kKBytes, kb * 64, n0);
+      }
     }
   } else if (warp == 1) {
     tmem_alloc<kLnBN>(tmem_slot);
@@ -698,23 +709,35 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     if (lane == 0) {
       pdl_wait();  // A belongs to the previous kernel until here
       B200VQA_STAMP(2);
-      for (int kb = 0; kb < kLnKb; ++kb) {
+      for (int kb = 0; kb < NS; ++kb) {
         mbar_expect_tx(&full_bar[kb], kBM * kKBytes);
         tma_load_2d(&tm_a, &full_bar[kb], smem + L::kOffA + kb * kBM * kKBytes, kb * 64, m0);
       }
       constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, kLnBN, 0, 0);
-      mbar_wait(w_full, 0);
-      for (int kb = 0; kb < kLnKb; ++kb) {
-        mbar_wait(&full_bar[kb], 0);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int st = kb % NS;
+        if (kb < NS) mbar_wait(&w_full[st], 0);
+        mbar_wait(&full_bar[st], uint32_t(kb / NS) & 1u);
         tc_fence_after_sync();
         if (kb == 0) B200VQA_STAMP(4);
-        if (kb == kLnKb - 1) B200VQA_STAMP(5);
-        const uint32_t sa = smem_u32(smem + L::kOffA + kb * kBM * kKBytes);
-        const uint32_t sb = smem_u32(smem + L::kOffW + kb * kLnBN * kKBytes);
+        if (kb == NKB - 1) B200VQA_STAMP(5);
+        const uint32_t sa = smem_u32(smem + L::kOffA + st * kBM * kKBytes);
+        const uint32_t sb = smem_u32(smem + L::kOffW + st * kLnBN * kKBytes);
 #pragma unroll
         for (int k = 0; k < kKBytes / kUmmaKBytes; ++k)
           umma_bf16(tmem_base, make_smem_desc_sw128(sa + k * kUmmaKBytes, 16, 1024),
                     make_smem_desc_sw128(sb + k * kUmmaKBytes, 16, 1024), idesc, (kb | k) != 0);
+        if constexpr (NKB > NS) {
+          if (kb + NS < NKB) umma_commit(&empty_bar[st]);
+          // refill the previous k-block's stage (its MMAs retire while this k-block's run): k-block kb - 1 + NS
+          if (kb >= 1 && kb - 1 + NS < NKB) {
+            const int sp = (kb - 1) % NS, nk = kb - 1 + NS;
+            mbar_wait(&empty_bar[sp], uint32_t((kb - 1) / NS) & 1u);
+            mbar_expect_tx(&full_bar[sp], (kBM + kLnBN) * kKBytes);
+            tma_load_2d(&tm_a, &full_bar[sp], smem + L::kOffA + sp * kBM * kKBytes, nk * 64, m0);
+            tma_load_2d(&tm_w, &full_bar[sp], smem + L::kOffW + sp * kLnBN * kKBytes, nk * 64, n0);
+          }
+        }
       }
       umma_commit(acc_full);
     }
@@ -833,19 +856,29 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 #undef B200VQA_STAMP
 }
 
-cudaError_t launch_ln_cluster(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
-                              cudaStream_t stream) {
+template <int NKB>
+cudaError_t launch_ln_cluster_k(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
+                                cudaStream_t stream) {
+  using L = LnClSmem<NKB>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         LnClSmem::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const int tiles_m = (p.M + kBM - 1) / kBM;
   if (tiles_m <= 0) return cudaSuccess;
-  return launch_kernel(gemm_ln_cluster_kernel, dim3(kLnCl, tiles_m), dim3(kLnThreads), LnClSmem::kBytes, stream, p.pdl,
+  return launch_kernel(gemm_ln_cluster_kernel<NKB>, dim3(kLnCl, tiles_m), dim3(kLnThreads), L::kBytes, stream, p.pdl,
                        tm_a, tm_w, p);
+}
+
+cudaError_t launch_ln_cluster(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
+                              cudaStream_t stream) {
+  if (p.K == 256) return launch_ln_cluster_k<4>(tm_a, tm_w, p, stream);
+  if (p.K == 512) return launch_ln_cluster_k<8>(tm_a, tm_w, p, stream);
+  if (p.K == 1024) return launch_ln_cluster_k<16>(tm_a, tm_w, p, stream);
+  return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -870,7 +903,7 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
   if (epilogue == kEpiHead && (p.N != block_n || p.head_V > p.N)) return cudaErrorInvalidValue;
   if (epilogue == kEpiLstm && (block_n != 256 || p.N % 256 != 0)) return cudaErrorInvalidValue;
   if (epilogue == kEpiBiasResLN && block_n == kLnBN) {  // cluster-of-4 variant for the decode-sized launches
-    if (p.N != 256 || p.K != 256 || tf32) return cudaErrorInvalidValue;
+    if (p.N != 256 || (p.K != 256 && p.K != 512 && p.K != 1024) || tf32) return cudaErrorInvalidValue;
     return launch_ln_cluster(tm_a, tm_w, p, stream);
   }
   if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;

@@ -252,6 +252,13 @@ cudaError_t launch_mem_attn_ring_tc(const CUtensorMap& tm_mem, const CUtensorMap
 cudaError_t launch_absorb_qk(const float* in_proj_weight, const float* in_proj_bias, int nhead, __nv_bfloat16* w_qk,
                              float* b_qk, cudaStream_t stream);
 
+// ... and for the other side of the attention: the per-head value projection followed by out_proj is one linear map of
+// the attention-weighted memory u [nhead*d]:  out_proj(concat_h(W_v,h u_h + b_v,h)) = W_ov u + b_ov with
+//   w_ov [d, nhead*d] bf16, w_ov[n][h*d + i] = sum_e W_o[n][h*dh+e] * W_v[h*dh+e][i]     b_ov = b_o + W_o b_v
+cudaError_t launch_absorb_ov(const float* in_proj_weight, const float* in_proj_bias, const float* out_proj_weight,
+                             const float* out_proj_bias, int nhead, __nv_bfloat16* w_ov, float* b_ov,
+                             cudaStream_t stream);
+
 // tok[B, tok_ld] -> caller layout.
 //   out_i64 : out[b*out_ld + j] = tok[b, src_col0 + j], j < n_cols                       (IQAP programs, FA `ys`)
 //   out_i32 : FA step cache row: out[b*out_ld + j] = (j == 0 || !forced) ? tok[b, j] : forced[b*forced_ld + j-1],

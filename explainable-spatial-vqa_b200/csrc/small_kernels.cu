@@ -425,6 +425,33 @@ __global__ void __launch_bounds__(kD) absorb_qk_kernel(const float* __restrict__
   if (d == 0) b_qk[blockIdx.x] = accb;
 }
 
+// Absorbed value-output weights of one cross-attention block (kernels.h: launch_absorb_ov).  Block = one output channel
+// n, thread = memory channel i of head blockIdx.y; fp32 accumulation over the head dimension.
+__global__ void __launch_bounds__(kD) absorb_ov_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                                       const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                                       int nhead, __nv_bfloat16* __restrict__ w_ov,
+                                                       float* __restrict__ b_ov) {
+  const int dh = kD / nhead;
+  const int n = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
+  const float* wv = w_in + size_t(2) * kD * kD;  // rows 2d .. 3d-1
+  float acc = 0.f;
+  for (int e = 0; e < dh; ++e) acc = fmaf(w_out[size_t(n) * kD + h * dh + e], wv[size_t(h * dh + e) * kD + i], acc);
+  w_ov[size_t(n) * nhead * kD + h * kD + i] = __float2bfloat16(acc);
+  if (h == 0 && i == 0) {
+    float accb = b_out[n];
+    for (int c = 0; c < kD; ++c) accb = fmaf(w_out[size_t(n) * kD + c], b_in[2 * kD + c], accb);
+    b_ov[n] = accb;
+  }
+}
+
+cudaError_t launch_absorb_ov(const float* in_proj_weight, const float* in_proj_bias, const float* out_proj_weight,
+                             const float* out_proj_bias, int nhead, __nv_bfloat16* w_ov, float* b_ov,
+                             cudaStream_t stream) {
+  absorb_ov_kernel<<<dim3(kD, nhead), kD, 0, stream>>>(in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias,
+                                                      nhead, w_ov, b_ov);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_absorb_qk(const float* in_proj_weight, const float* in_proj_bias, int nhead, __nv_bfloat16* w_qk,
                              float* b_qk, cudaStream_t stream) {
   absorb_qk_kernel<<<nhead * kD, kD, 0, stream>>>(in_proj_weight, in_proj_bias, nhead, w_qk, b_qk);

@@ -277,3 +277,22 @@ def test_absorbed_cross_attention_equals_projected_kv_path(monkeypatch):
     assert torch.equal(a1, a2)
     assert common.rel_err(l1, l2) < 4e-3
     assert plain.native_launch_count() != absorbed.native_launch_count()   # really two different kernel sequences
+
+
+def test_absorbed_value_output_projection_equals_two_step_form(monkeypatch):
+    """The per-head value projection followed by out_proj is one linear map of the attention-weighted memory:
+    W_ov u + b_ov as ONE K = nhead*256 LayerNorm GEMM (csrc/kernels.h: launch_absorb_ov, B200VQA_ABSORB_OV=1) against
+    the default grouped value GEMM followed by out_proj + LayerNorm: same teacher-forced logits to bf16 rounding, one
+    launch fewer per decode layer and position (measured slower inside the step, hence opt-in)."""
+    img, q = orc.iqap_inputs(16, seed=98)
+    g = torch.Generator().manual_seed(4)
+    forced = torch.randint(0, 44, (16, 27), generator=g)
+    plain = common.seeded_iqap().cuda()
+    a2, _, l2, _ = plain.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    n_plain = plain.native_launch_count()
+    monkeypatch.setenv("B200VQA_ABSORB_OV", "1")
+    fused = common.seeded_iqap().cuda()          # the switch is read when the native handle is created
+    a1, _, l1, _ = fused.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    assert torch.equal(a1, a2)
+    assert common.rel_err(l1, l2) < 4e-3
+    assert n_plain - fused.native_launch_count() == 2 * 27   # two decoder layers x 27 positions

@@ -98,12 +98,14 @@ def test_gemm_residual_layernorm(M, K):
     assert common.rel_err(out.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("M", [1, 128, 130, 1000, 4096])
-def test_gemm_residual_layernorm_cluster(M):
+@pytest.mark.parametrize("M,K", [(1, 256), (128, 256), (130, 256), (1000, 256), (4096, 256), (128, 512), (300, 512),
+                                 (1, 1024), (128, 1024), (1000, 1024)])
+def test_gemm_residual_layernorm_cluster(M, K):
     """Decode-sized variant: four CTAs per 128-row tile, LayerNorm statistics exchanged through cluster shared memory
-    (block_n = 64 selects it); residual rows carry a large common offset to exercise the variance merge."""
-    g = torch.Generator(device="cuda").manual_seed(M)
-    N = K = 256
+    (block_n = 64 selects it); residual rows carry a large common offset to exercise the variance merge.  K = 512 / 1024
+    (the fused value + output projection of the absorbed cross-attention) stream k-blocks through an 8-stage ring."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    N = 256
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g)
@@ -214,3 +216,4 @@ def test_memory_attention_tc_full_batch_and_constant_len():
         assert torch.equal(o1, o2)
         err = (o1.float() - ref).abs().amax(1) / ref.abs().amax(1)
         assert float(err.max()) < 1.5e-2, (impl, int(err.argmax()))
+
