@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   int len = p.lens ? p.lens[b] : p.const_len;
   len = len > kLP ? kLP : len;
 
-  if (p.new_k) {  // append this position's key / value to the caches, then attend over them (self-attention)
-    if (threadIdx.x < 64) {
-      const bool is_v = threadIdx.x >= 32;
-      const __nv_bfloat16* src = (is_v ? p.new_v : p.new_k) + size_t(b) * p.ld_new + lane * 8;
-      __nv_bfloat16* dst = (is_v ? p.v_app : p.k_app) + (size_t(b) * p.rows_per_q + p.append_pos) * p.ld + lane * 8;
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-    }
-    __syncthreads();
+  // self-attention: this position's key / value are appended to the caches for the later positions; the attention
+  // below takes row append_pos straight from new_k / new_v, so nothing waits for the appended rows to land
+  const __nv_bfloat16* fresh_k = p.new_k ? p.new_k + size_t(b) * p.ld_new + lane * 8 : nullptr;
+  const __nv_bfloat16* fresh_v = p.new_k ? p.new_v + size_t(b) * p.ld_new + lane * 8 : nullptr;
+  if (p.new_k && threadIdx.x >= 64 && threadIdx.x < 128) {  // warps 2 and 3: their first row batch is the shortest
+    const bool is_v = threadIdx.x >= 96;
+    __nv_bfloat16* dst = (is_v ? p.v_app : p.k_app) + (size_t(b) * p.rows_per_q + p.append_pos) * p.ld + lane * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(is_v ? fresh_v : fresh_k);
   }
 
   float q[8];
@@ -95,17 +95,18 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
   // software-pipelined: the next batch of rows is in flight while the current one is consumed, and the first
   // batch of V rows is requested before the softmax barrier so the HBM stream never drains
   constexpr int kStep = kAttnWarps * kKeysInFlight;
-  auto load_rows = [&](const __nv_bfloat16* base, int j0, uint4 (&raw)[kKeysInFlight]) {
+  auto load_rows = [&](const __nv_bfloat16* base, const __nv_bfloat16* fresh, int j0, uint4 (&raw)[kKeysInFlight]) {
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;
-      raw[u] = (j < len) ? ld_stream16(base + size_t(j) * p.ld) : make_uint4(0, 0, 0, 0);
+      const __nv_bfloat16* src = (fresh && j == p.append_pos) ? fresh : base + size_t(j) * p.ld;
+      raw[u] = (j < len) ? ld_stream16(src) : make_uint4(0, 0, 0, 0);
     }
   };
   uint4 cur[kKeysInFlight], nxt[kKeysInFlight];
-  load_rows(kbase, warp, cur);
+  load_rows(kbase, fresh_k, warp, cur);
   for (int j0 = warp; j0 < len; j0 += kStep) {
-    if (j0 + kStep < len) load_rows(kbase, j0 + kStep, nxt);
+    if (j0 + kStep < len) load_rows(kbase, fresh_k, j0 + kStep, nxt);
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) cur[u] = nxt[u];
   }
-  load_rows(vbase, warp, cur);  // first V batch: in flight across the softmax
+  load_rows(vbase, fresh_v, warp, cur);  // first V batch: in flight across the softmax
   __syncthreads();
 
   if (warp < p.nhead) {  // softmax statistics of head `warp`
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (int j0 = warp; j0 < len; j0 += kStep) {
-    if (j0 + kStep < len) load_rows(vbase, j0 + kStep, nxt);
+    if (j0 + kStep < len) load_rows(vbase, fresh_v, j0 + kStep, nxt);
 #pragma unroll
     for (int u = 0; u < kKeysInFlight; ++u) {
       const int j = j0 + u * kAttnWarps;

@@ -194,12 +194,24 @@ __global__ void __launch_bounds__(256) ffn_reduce_ln_kernel(const FfnSmallParams
   }
   const float* src = p.partial + size_t(row) * kD + lane * 8;
   const size_t stride = size_t(p.M) * kD;
-#pragma unroll 4
-  for (int s = 0; s < p.n_slices; ++s) {
-    const float4 a = *reinterpret_cast<const float4*>(src + s * stride);
-    const float4 b = *reinterpret_cast<const float4*>(src + s * stride + 4);
-    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  // all partials of up to 16 slices are requested before the first add (one L2 round trip, not four); the sum order
+  // stays slice 0, 1, 2, ... (deterministic)
+  for (int s0 = 0; s0 < p.n_slices; s0 += 16) {
+    float4 a[16], b[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (s0 + u < p.n_slices) {
+        a[u] = *reinterpret_cast<const float4*>(src + (s0 + u) * stride);
+        b[u] = *reinterpret_cast<const float4*>(src + (s0 + u) * stride + 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (s0 + u < p.n_slices) {
+        v[0] += a[u].x; v[1] += a[u].y; v[2] += a[u].z; v[3] += a[u].w;
+        v[4] += b[u].x; v[5] += b[u].y; v[6] += b[u].z; v[7] += b[u].w;
+      }
+    }
   }
   float s1 = 0.f;
 #pragma unroll
