@@ -28,7 +28,8 @@ struct FfnSmem {
   static constexpr int kOffW2 = kOffW1 + kW1;
   static constexpr int kOffH = kOffX;  // H is written after the first GEMM has retired: it reuses X's shared memory
   static constexpr int kOffBar = kOffW2 + kW2;
-  static constexpr int kBytes = kOffBar + 64;  // 192 KB: leaves room for row-attention blocks of other branches
+  static constexpr int kOffB1 = kOffBar + 64;   // this slice's 128 linear1 biases (fp32)
+  static constexpr int kBytes = kOffB1 + 512;   // 192.6 KB: leaves room for row-attention blocks of other branches
 };
 
 __global__ void __launch_bounds__(kFfnThreads, 1)
@@ -116,11 +117,15 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    // the slice's biases are parked in shared memory while the first GEMM runs (weights: safe before the dependency
+    // wait), so no L2 round trip sits between the accumulator and H
+    float* s_b1 = reinterpret_cast<float*>(smem + L::kOffB1);
+    s_b1[r] = __ldg(p.b1 + slice * kSlice + r);
+    named_bar_sync(1, 128);
     pdl_wait();  // the partial-sum buffer is still being read by the previous reduce kernel until here
     mbar_wait(bar_d1, 0);
     __syncwarp();
     tc_fence_after_sync();
-    const float* b1 = p.b1 + slice * kSlice;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -129,7 +134,7 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c * 32 + j));
+        const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + c * 32 + j);
         o[j >> 1] = pack_bf16x2(fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f));
         o[(j >> 1) + 1] =
             pack_bf16x2(fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f));
@@ -150,20 +155,28 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     mbar_wait(bar_d2, 0);
     __syncwarp();
     tc_fence_after_sync();
-    const int row = m0 + r;
-    float* prow = p.partial + (size_t(slice) * p.M + (row < p.M ? row : 0)) * kD;
+    // fp32 partial tile, 32 rows x 32 columns per warp and chunk: transposed through a 4 KB shared tile (W1's shared
+    // memory, free since the first GEMM retired; 16-byte units XOR-swizzled with row & 7: conflict-free both ways) so
+    // that every store instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes
+    uint8_t* stg = sW1 + quarter * 4096;
+    float* pbase = p.partial + (size_t(slice) * p.M + m0 + quarter * 32) * kD;
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       uint32_t v[32];
       tmem_ld32(d2 + lane_off + c * 32, v);
       tmem_ld_wait();
-      if (row < p.M) {
-        float4* dst = reinterpret_cast<float4*>(prow + c * 32);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = (lane >> 3) + 4 * k, pc = lane & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((pc ^ (rr & 7)) << 4));
+        if (m0 + quarter * 32 + rr < p.M) *reinterpret_cast<uint4*>(pbase + size_t(rr) * kD + c * 32 + pc * 4) = val;
       }
+      __syncwarp();
     }
   }
 
