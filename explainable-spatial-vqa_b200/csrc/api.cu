@@ -143,6 +143,8 @@ struct b200vqa_handle {
   int mem_attn_impl = 0;       // B200VQA_MEM_ATTN=mma|tc|ring: absorbed cross-attention on warp-level MMAs (persistent ring
                                // kernel, 0), on tcgen05 with a cluster of two CTAs per question (1) or on tcgen05 with
                                // one persistent CTA per SM and a three-stage tile ring (3)
+  bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
+                               // of up to 64 entries (A/B runs)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
@@ -613,6 +615,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
     b200vqa_handle* h;
     ~PdlOff() { h->pdl_chain = false; }
   } pdl_off{h};
+  const bool fused_head = d.dec_vocab <= 64 && !h->no_fused_head;
   for (int t = 0; t < io.steps; ++t) {
     const __nv_bfloat16* in = dx;
     for (int l = 0; l < d.n_dec_layers; ++l) {
@@ -731,13 +734,30 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         fp.fn_gamma = last ? h->dec_fn_w : nullptr;
         fp.fn_beta = last ? h->dec_fn_b : nullptr;
         fp.pdl = true;
+        if (last && fused_head) {
+          // vocabularies of up to 64 entries: the head runs inside the reduce kernel (fp32, the row is in registers)
+          fp.head_w = h->head_w;
+          fp.head_b = h->head_b;
+          fp.head_V = d.dec_vocab;
+          fp.head_t = t;
+          fp.tok = tok;
+          fp.tok_ld = kTokLd;
+          fp.logits = logits;
+          fp.logits_T = io.logits_T;
+          fp.forced = forced;
+          fp.forced_ld = io.forced_ld;
+          fp.emb = h->dec_emb;
+          fp.vocab = d.dec_vocab;
+          fp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
+          fp.x_next = dx;
+        }
         h->cur_tag = kTagDecFfn;
         LAUNCH_OK(h, launch_ffn_small(*tx, *tw1, *tw2, fp, s));
         ++h->launches;  // two kernels
       }
       in = out;
     }
-    {
+    if (!fused_head) {
       // vocabulary head on the tensor cores (tf32 inputs, fp32 accumulate) with argmax + next embedding fused
       GemmParams hp;
       hp.bias = h->head_b;
@@ -1032,6 +1052,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_impl = g[0] == 't' ? 1 : (g[0] == 'r' ? 3 : 0);
+  if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));

@@ -268,6 +268,68 @@ __global__ void __launch_bounds__(256) ffn_reduce_ln_kernel(const FfnSmallParams
     dst[0] = make_float4(y[0], y[1], y[2], y[3]);
     dst[1] = make_float4(y[4], y[5], y[6], y[7]);
   }
+  if (p.head_w) {
+    // vocabulary head of this row: lane l ends up with the logits of tokens l and 32 + l
+    float lg[2];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      float x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int tokv = grp * 32 + i;
+        float acc = 0.f;
+        if (tokv < p.head_V) {  // warp-uniform
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.head_w + size_t(tokv) * kD + lane * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.head_w + size_t(tokv) * kD + lane * 8) + 1);
+          acc = y[0] * w0.x;
+          acc = fmaf(y[1], w0.y, acc); acc = fmaf(y[2], w0.z, acc); acc = fmaf(y[3], w0.w, acc);
+          acc = fmaf(y[4], w1.x, acc); acc = fmaf(y[5], w1.y, acc); acc = fmaf(y[6], w1.z, acc);
+          acc = fmaf(y[7], w1.w, acc);
+        }
+        x[i] = acc;
+      }
+      // transposed warp reduction (31 shuffles for 32 sums): at distance `off` a lane keeps the half of the remaining
+      // values selected by that bit of its lane index and sends the other half; lane l ends with the total of x[l]
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = upper ? x[i] : x[i + off];
+          const float keep = upper ? x[i + off] : x[i];
+          x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      const int tokv = grp * 32 + lane;
+      lg[grp] = tokv < p.head_V ? x[0] + __ldg(p.head_b + tokv) : -INFINITY;
+      if (p.logits && tokv < p.head_V)
+        p.logits[(size_t(row) * p.logits_T + p.head_t) * p.head_V + tokv] = lg[grp];
+    }
+    // argmax, first maximum wins (a NaN never wins; an all-NaN row gives token 0)
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+    if (lg[0] > best) { best = lg[0]; besti = lane; }
+    if (lg[1] > best) { best = lg[1]; besti = 32 + lane; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (besti >= p.head_V) besti = 0;
+    if (lane == 0) p.tok[size_t(row) * p.tok_ld + p.head_t + 1] = besti;
+    if (p.pe_next) {  // next decoder input x_next[row] = emb[next token] + pe[t+1]
+      long long nxt = p.forced ? p.forced[size_t(row) * p.forced_ld + p.head_t] : (long long)besti;
+      nxt = nxt < 0 ? 0 : (nxt >= p.vocab ? p.vocab - 1 : nxt);
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(nxt) * kD + lane * 8));
+      const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(nxt) * kD + lane * 8) + 1);
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.pe_next + lane * 8));
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.pe_next + lane * 8) + 1);
+      *reinterpret_cast<uint4*>(p.x_next + size_t(row) * kD + lane * 8) =
+          make_uint4(pack_bf16x2(e0.x + q0.x, e0.y + q0.y), pack_bf16x2(e0.z + q0.z, e0.w + q0.w),
+                     pack_bf16x2(e1.x + q1.x, e1.y + q1.y), pack_bf16x2(e1.z + q1.z, e1.w + q1.w));
+    }
+  }
 }
 
 }  // namespace
@@ -276,6 +338,7 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
                              const FfnSmallParams& p, cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
   if (p.ff % kSlice != 0 || p.n_slices != p.ff / kSlice) return cudaErrorInvalidValue;
+  if (p.head_w && (p.head_V < 1 || p.head_V > 64 || !p.tok || !p.head_b)) return cudaErrorInvalidValue;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e =

@@ -294,6 +294,23 @@ struct FfnSmallParams {
   float* out_f32 = nullptr;  // optional fp32 copy of the output ...
   const float* fn_gamma = nullptr;  // ... after a second LayerNorm when given (nn.Transformer's decoder.norm, FA:42)
   const float* fn_beta = nullptr;
+  // Optional vocabulary head of this decode position fused into the reduce kernel (last decoder layer, vocabularies of
+  // up to 64 entries): logits = y W_head^T + b in fp32 on the CUDA cores (the row is already in the warp's registers),
+  // argmax (lowest index wins ties) -> tok[row, t+1], next input x_next[row] = emb[next] + pe[t+1]; same meaning as
+  // the kEpiHead GEMM epilogue's fields (IQAP:230-236)
+  const float* head_w = nullptr;     // [V, 256] fp32
+  const float* head_b = nullptr;
+  int head_V = 0, head_t = 0;
+  int64_t* tok = nullptr;
+  int tok_ld = 0;
+  float* logits = nullptr;
+  int logits_T = 0;
+  const int64_t* forced = nullptr;
+  int forced_ld = 0;
+  const float* emb = nullptr;
+  int vocab = 0;
+  const float* pe_next = nullptr;
+  __nv_bfloat16* x_next = nullptr;
 };
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);

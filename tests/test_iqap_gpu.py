@@ -296,3 +296,28 @@ def test_absorbed_value_output_projection_equals_two_step_form(monkeypatch):
     assert torch.equal(a1, a2)
     assert common.rel_err(l1, l2) < 4e-3
     assert n_plain - fused.native_launch_count() == 2 * 27   # two decoder layers x 27 positions
+
+
+def test_fused_vocabulary_head_equals_tensor_core_head(monkeypatch):
+    """Program vocabularies of up to 64 tokens: the head (logits, argmax, next embedding) runs in fp32 inside the last
+    layer's reduce + LayerNorm kernel (csrc/ffn_small.cu); B200VQA_NO_FUSED_HEAD=1 keeps it as its own tf32 tensor-core
+    GEMM.  Same logits to tf32 rounding, same tokens wherever the top-2 margin exceeds that rounding, 27 launches fewer."""
+    img, q = orc.iqap_inputs(24, seed=97)
+    g = torch.Generator().manual_seed(5)
+    forced = torch.randint(0, 44, (24, 27), generator=g)
+    fused = common.seeded_iqap().cuda()
+    a1, p1, l1, _ = fused.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    n_fused = fused.native_launch_count()
+    monkeypatch.setenv("B200VQA_NO_FUSED_HEAD", "1")
+    plain = common.seeded_iqap().cuda()          # the switch is read when the native handle is created
+    a2, p2, l2, _ = plain.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    assert plain.native_launch_count() - n_fused == 27
+    assert torch.equal(a1, a2)
+    err = float((l1 - l2).abs().max())
+    assert err / float(l2.abs().max()) < 2e-3
+    top2 = l2.topk(2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 4 * err
+    assert torch.equal(l1.argmax(-1)[decisive], l2.argmax(-1)[decisive])
+    assert bool(decisive.float().mean() > 0.9)
+    # the greedy tokens the library published are the argmax of the logits it returned
+    assert torch.equal(p1, l1.argmax(-1))
