@@ -143,6 +143,7 @@ struct b200vqa_handle {
   int mem_attn_impl = 0;       // B200VQA_MEM_ATTN=mma|tc|ring: absorbed cross-attention on warp-level MMAs (persistent ring
                                // kernel, 0), on tcgen05 with a cluster of two CTAs per question (1) or on tcgen05 with
                                // one persistent CTA per SM and a three-stage tile ring (3)
+  bool no_warp_self_attn = false;  // B200VQA_NO_WARP_SELF_ATTN=1: decoder self-attention with one CTA per question (A/B runs)
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
@@ -641,6 +642,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       sp.new_v = dqkv + 2 * kD;
       sp.ld_new = 3 * kD;
       sp.append_pos = t;
+      sp.warp_form = !h->no_warp_self_attn;
       sp.k_app = kc;
       sp.v_app = vc;
       sp.out = dattn;
@@ -1052,6 +1054,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_impl = g[0] == 't' ? 1 : (g[0] == 'r' ? 3 : 0);
+  if (const char* g = getenv("B200VQA_NO_WARP_SELF_ATTN")) h->no_warp_self_attn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));

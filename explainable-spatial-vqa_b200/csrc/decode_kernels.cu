@@ -7,6 +7,7 @@
 //   (the vocabulary head + argmax + next embedding is the kEpiHead epilogue of the tensor-core GEMM, gemm.cu)
 //   publish_tokens    library token buffer -> programs / ys / HBM step cache    (IQAP:239, FA:120-121)
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -169,6 +170,107 @@ __global__ void __launch_bounds__(kAttnWarps * 32) row_attn_kernel(const RowAttn
     for (int w = 0; w < kAttnWarps; ++w) o += s_red[w][t];
     p.out[size_t(b) * kD + t] = __float2bfloat16(o * s_inv[t / DH]);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder self-attention of the first 32 positions: ONE WARP per question, no shared memory, no CTA barrier.  A lane
+// owns 8 channels (one 16-byte chunk of every 512-byte row, so each warp-wide load is one coalesced row); the cached key
+// and value rows (at most 31) are requested up front, 16 at a time, the new row comes straight from the projection and
+// is appended to the caches on the side.  Scores are reduced over the DH / 8 lanes of a head with shuffles and stay in
+// registers; softmax via exp2.  (row_attn_kernel above spends three CTA barriers and a shared-memory reduction on the
+// same 14 KB of data: 9.8 us per 1024 questions under ncu.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelfWarpMaxLen = 32;
+
+template <int DH>
+__global__ void __launch_bounds__(128) self_attn_warp_kernel(const RowAttnParams p) {
+  constexpr int LPH = DH / 8;  // lanes per head
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (b >= p.B) return;
+  const int len = p.const_len;  // 1 .. 32 keys, the last one is this position's own
+  const int n_old = len - 1;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const __nv_bfloat16* kbase = p.k + size_t(b) * p.rows_per_q * p.ld + lane * 8;
+  const __nv_bfloat16* vbase = p.v + size_t(b) * p.rows_per_q * p.ld + lane * 8;
+  const uint4 fk = ld_stream16(p.new_k + size_t(b) * p.ld_new + lane * 8);
+  const uint4 fv = ld_stream16(p.new_v + size_t(b) * p.ld_new + lane * 8);
+  uint4 kr[16], vr[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) kr[u] = u < n_old ? ld_stream16(kbase + size_t(u) * p.ld) : zero;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) vr[u] = u < n_old ? ld_stream16(vbase + size_t(u) * p.ld) : zero;
+  float q[8];
+  unpack8(*reinterpret_cast<const uint4*>(p.q + size_t(b) * p.ldq + lane * 8), q);
+  const float sl2 = rsqrtf(float(DH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] *= sl2;
+  *reinterpret_cast<uint4*>(p.k_app + (size_t(b) * p.rows_per_q + p.append_pos) * p.ld + lane * 8) = fk;
+  *reinterpret_cast<uint4*>(p.v_app + (size_t(b) * p.rows_per_q + p.append_pos) * p.ld + lane * 8) = fv;
+
+  auto score = [&](const uint4& raw) {
+    float kx[8];
+    unpack8(raw, kx);
+    float sc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sc = fmaf(q[e], kx[e], sc);
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    return sc;  // the same value in every lane of the head
+  };
+  float sc[kSelfWarpMaxLen];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) sc[u] = u < n_old ? score(kr[u]) : -INFINITY;
+  if (len > 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) kr[u] = 16 + u < n_old ? ld_stream16(kbase + size_t(16 + u) * p.ld) : zero;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) sc[16 + u] = 16 + u < n_old ? score(kr[u]) : -INFINITY;
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) sc[16 + u] = -INFINITY;
+  }
+  const float s_new = score(fk);
+  float mx = s_new;
+#pragma unroll
+  for (int j = 0; j < kSelfWarpMaxLen; ++j) mx = fmaxf(mx, sc[j]);
+  float acc[8], sum;
+  {
+    const float pn = exp2f(s_new - mx);
+    float vx[8];
+    unpack8(fv, vx);
+    sum = pn;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = pn * vx[e];
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const float pj = exp2f(sc[u] - mx);  // exactly 0 for the padding entries
+    float vx[8];
+    unpack8(vr[u], vx);
+    sum += pj;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
+  }
+  if (len > 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) vr[u] = 16 + u < n_old ? ld_stream16(vbase + size_t(16 + u) * p.ld) : zero;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float pj = exp2f(sc[16 + u] - mx);
+      float vx[8];
+      unpack8(vr[u], vx);
+      sum += pj;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vx[e], acc[e]);
+    }
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  store_bf16x8(p.out + size_t(b) * kD + lane * 8, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -915,6 +1017,13 @@ cudaError_t launch_dec_embed_start(const DecEmbedParams& p, cudaStream_t stream)
 
 cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
   const int dh = kD / p.nhead;
+  // decoder self-attention of the first 32 positions: one warp per question
+  if (p.warp_form && p.new_k && p.new_v && !p.lens && p.const_len >= 1 && p.const_len <= kSelfWarpMaxLen &&
+      p.append_pos == p.const_len - 1 && p.k_app == p.k && p.v_app == p.v && p.B > 0) {
+    const dim3 grid((p.B * 32 + 127) / 128);
+    if (dh == 64) return launch_kernel(self_attn_warp_kernel<64>, grid, dim3(128), 0, stream, p.pdl, p);
+    if (dh == 128) return launch_kernel(self_attn_warp_kernel<128>, grid, dim3(128), 0, stream, p.pdl, p);
+  }
   if (dh == 64) return launch_kernel(row_attn_kernel<64>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
   if (dh == 128) return launch_kernel(row_attn_kernel<128>, dim3(p.B), dim3(kAttnWarps * 32), 0, stream, p.pdl, p);
   return cudaErrorInvalidValue;

@@ -214,6 +214,7 @@ struct RowAttnParams {
   const __nv_bfloat16* new_v = nullptr;
   int ld_new = 0;
   int append_pos = 0;
+  bool warp_form = true;  // self-attention over <= 32 keys: one warp per question (self_attn_warp_kernel); false = CTA per question
   __nv_bfloat16* k_app = nullptr;
   __nv_bfloat16* v_app = nullptr;
   __nv_bfloat16* out = nullptr;      // [B, kD]

@@ -321,3 +321,20 @@ def test_fused_vocabulary_head_equals_tensor_core_head(monkeypatch):
     assert bool(decisive.float().mean() > 0.9)
     # the greedy tokens the library published are the argmax of the logits it returned
     assert torch.equal(p1, l1.argmax(-1))
+
+
+def test_warp_self_attention_equals_cta_form(monkeypatch):
+    """Decoder self-attention over the first 32 positions runs with one warp per question (csrc/decode_kernels.cu:
+    self_attn_warp_kernel); B200VQA_NO_WARP_SELF_ATTN=1 keeps the CTA-per-question kernel.  Same KV cache contents, so
+    the same teacher-forced logits to fp32 summation order."""
+    img, q = orc.iqap_inputs(16, seed=96)
+    g = torch.Generator().manual_seed(6)
+    forced = torch.randint(0, 44, (16, 27), generator=g)
+    warp = common.seeded_iqap().cuda()
+    a1, _, l1, _ = warp.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    monkeypatch.setenv("B200VQA_NO_WARP_SELF_ATTN", "1")
+    cta = common.seeded_iqap().cuda()            # the switch is read when the native handle is created
+    a2, _, l2, _ = cta.forward_detailed(img.cuda(), q.cuda(), forced_programs=forced.cuda(), want_logits=True)
+    assert torch.equal(a1, a2)
+    assert common.rel_err(l1, l2) < 4e-3
+    assert cta.native_launch_count() == warp.native_launch_count()
