@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(const RowAttnParams
 }
 
 // ------------------------------------------------------------------------------------------------
-// Absorbed cross-attention (MemAttnParams, kernels.h): persistent CTAs (8 warps, three per SM), ONE pass over the memory.
+// Absorbed cross-attention (MemAttnParams, kernels.h): persistent CTAs (4 warps, six per SM), ONE pass over the memory.
 //
-// The memory rows m_j (256 bf16 = 512 B) stream through a double-buffered shared-memory ring of 64-row tiles, filled
+// The memory rows m_j (256 bf16 = 512 B) stream through a double-buffered shared-memory ring of 32-row tiles, filled
 // by TMA (one elected thread, 128-byte swizzle, mbarrier completion) and running ahead ACROSS question boundaries.  Every tile is consumed once with an online softmax: HBM traffic per question is len * 512 B -
 // half of reading a projected K row and a V row - and nothing is re-read.  With NH query vectors per row a CUDA-core
 // form needs 8*NH FMAs per 16 loaded bytes and is issue-bound (measured 66 us per 1024 questions vs 47 us for the K|V
