@@ -111,6 +111,7 @@ SIGNATURES = {
     "b200vqa_dbg_gemm": (C.c_int, [C.POINTER(DbgGemmArgs), _vp]),
     "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "b200vqa_dbg_workspace": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200vqa_dbg_mem_attn": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
 }
 
@@ -212,6 +213,15 @@ class Handle:
         cnt = (C.c_int32 * n)()
         check(self._lib.b200vqa_profile_end(self._h, ms, cnt), "b200vqa_profile_end")
         return {self._lib.b200vqa_profile_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
+
+    def dbg_workspace(self, which: int, dtype: torch.dtype) -> torch.Tensor:
+        """Copy of one decode scratch buffer (test hook, see b200vqa_dbg_workspace)."""
+        n = C.c_size_t(0)
+        check(self._lib.b200vqa_dbg_workspace(self._h, int(which), _vp(0), 0, C.byref(n)), "b200vqa_dbg_workspace")
+        out = torch.empty(n.value // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=self.device)
+        check(self._lib.b200vqa_dbg_workspace(self._h, int(which), _vp(out.data_ptr()), n.value, C.byref(n)),
+              "b200vqa_dbg_workspace")
+        return out
 
     def close(self):
         if self._h:

@@ -80,6 +80,9 @@ struct Workspace {
   float* ffn_partial = nullptr;    // [ff/128, drows, 256] fp32 partial sums of the decode feed-forward block
   int64_t* tok = nullptr;          // [cap, kTokLd] greedy tokens of the running decode (column 0 = start token)
   __nv_bfloat16* img_t = nullptr;  // FA: transposed + cast image features [cap*196, 1024]
+  __nv_bfloat16** kc_dev = nullptr;  // device copies of the kc / vc pointer tables (persistent decode kernel)
+  __nv_bfloat16** vc_dev = nullptr;
+  size_t drows = 0;                // decode rows (cap rounded up to 128)
 };
 
 using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>;
@@ -87,12 +90,12 @@ using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint3
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
   kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFinalLn,
-  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagMisc, kNumTags
+  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagDecPersist, kTagMisc, kNumTags
 };
 const char* const kTagNames[kNumTags] = {
     "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
     "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_proj_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
-    "dec_cross_attention", "dec_head_argmax", "misc"};
+    "dec_cross_attention", "dec_head_argmax", "dec_persistent", "misc"};
 
 struct ProfRec {
   int tag;
@@ -147,6 +150,14 @@ struct b200vqa_handle {
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
+  // persistent decode kernel (decode_persist.cu): all positions x layers in one launch
+  bool decode_persist = false;        // B200VQA_DECODE=persist|chain
+  int persist_stagger_us = 0;         // B200VQA_PERSIST_STAGGER_US: start delay of odd question tiles
+  int persist_dbg_stop = -1;          // tests: stop after this many rendezvous of the first stage
+  __nv_bfloat16* slab_a = nullptr;    // decoder weights as rows of 256 bf16 (kernels.h: DecPersistParams)
+  __nv_bfloat16* slab_b = nullptr;    // linear2 as k-blocks of [256 x 64]
+  int slab_rows_per_layer = 0;
+  DecLayerDev* dec_layers_dev = nullptr;
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   int decode_branches = 8;            // concurrent question ranges inside the decode graph
@@ -216,6 +227,10 @@ void layout_weights(b200vqa_handle* h, Arena& a) {
     L.n1w = a.take<float>(D); L.n1b = a.take<float>(D); L.n2w = a.take<float>(D); L.n2b = a.take<float>(D);
     L.n3w = a.take<float>(D); L.n3b = a.take<float>(D);
   }
+  h->slab_rows_per_layer = 3 * D + D + d.nhead * D + D + D + d.dim_ff;
+  h->slab_a = a.take<__nv_bfloat16>(size_t(d.n_dec_layers) * h->slab_rows_per_layer * D);
+  h->slab_b = a.take<__nv_bfloat16>(size_t(d.n_dec_layers) * d.dim_ff * D);
+  h->dec_layers_dev = a.take<DecLayerDev>(d.n_dec_layers);
   if (d.enc_final_norm_weight) { h->enc_fn_w = a.take<float>(D); h->enc_fn_b = a.take<float>(D); }
   if (d.dec_final_norm_weight) { h->dec_fn_w = a.take<float>(D); h->dec_fn_b = a.take<float>(D); }
   h->head_w = a.take<float>(size_t(D) * d.dec_vocab);
@@ -286,6 +301,30 @@ cudaError_t pack_weights(b200vqa_handle* h, cudaStream_t s) {
     PACK_OK(copy_f32(L.n1w, w.norm1_weight, D, s)); PACK_OK(copy_f32(L.n1b, w.norm1_bias, D, s));
     PACK_OK(copy_f32(L.n2w, w.norm2_weight, D, s)); PACK_OK(copy_f32(L.n2b, w.norm2_bias, D, s));
     PACK_OK(copy_f32(L.n3w, w.norm3_weight, D, s)); PACK_OK(copy_f32(L.n3b, w.norm3_bias, D, s));
+  }
+  // the persistent decode kernel's view of the decoder weights: one K-major slab of 256-wide rows + linear2 k-blocks
+  {
+    std::vector<DecLayerDev> lay(d.n_dec_layers);
+    auto copy_rows = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, size_t rows) {
+      return cudaMemcpyAsync(dst, src, rows * D * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, s);
+    };
+    for (int l = 0; l < d.n_dec_layers; ++l) {
+      const auto& L = h->dec[l];
+      __nv_bfloat16* base = h->slab_a + size_t(l) * h->slab_rows_per_layer * D;
+      PACK_OK(copy_rows(base, L.self_attn.w_in, 3 * D));
+      PACK_OK(copy_rows(base + size_t(3) * D * D, L.self_attn.w_out, D));
+      PACK_OK(copy_rows(base + size_t(4) * D * D, L.w_qk, size_t(d.nhead) * D));
+      PACK_OK(copy_rows(base + size_t(4 + d.nhead) * D * D, L.cross_attn.w_in + size_t(2) * D * D, D));
+      PACK_OK(copy_rows(base + size_t(5 + d.nhead) * D * D, L.cross_attn.w_out, D));
+      PACK_OK(copy_rows(base + size_t(6 + d.nhead) * D * D, L.w1, d.dim_ff));
+      PACK_OK(launch_pack_w2_kblocks(L.w2, h->slab_b + size_t(l) * d.dim_ff * D, d.dim_ff, s));
+      DecLayerDev& v = lay[l];
+      v.b_in = L.self_attn.b_in; v.b_out = L.self_attn.b_out; v.n1w = L.n1w; v.n1b = L.n1b;
+      v.b_qk = L.b_qk; v.b_v = L.cross_attn.b_in + 2 * D; v.b_co = L.cross_attn.b_out; v.n2w = L.n2w; v.n2b = L.n2b;
+      v.b1 = L.b1; v.b2 = L.b2; v.n3w = L.n3w; v.n3b = L.n3b;
+    }
+    PACK_OK(cudaMemcpyAsync(h->dec_layers_dev, lay.data(), lay.size() * sizeof(DecLayerDev), cudaMemcpyHostToDevice, s));
+    PACK_OK(cudaStreamSynchronize(s));  // `lay` is pageable host memory
   }
   if (h->enc_fn_w) {
     PACK_OK(copy_f32(h->enc_fn_w, d.enc_final_norm_weight, D, s));
@@ -387,7 +426,10 @@ void layout_workspace(const b200vqa_handle* h, Workspace& w, Arena& a, int cap, 
   w.dxo[0] = a.take<__nv_bfloat16>(drows * kD);
   w.dxo[1] = a.take<__nv_bfloat16>(drows * kD);
   w.dout = a.take<float>(drows * kD);
-  w.ffn_partial = a.take<float>(size_t(d.dim_ff / 128) * drows * kD);
+  w.drows = drows;
+  w.ffn_partial = a.take<float>(size_t(std::max(d.dim_ff / 128, 8)) * drows * kD);
+  w.kc_dev = a.take<__nv_bfloat16*>(d.n_dec_layers);
+  w.vc_dev = a.take<__nv_bfloat16*>(d.n_dec_layers);
   w.tok = a.take<int64_t>(size_t(cap) * kTokLd);
   if (d.kind == B200VQA_MODEL_FA) w.img_t = a.take<__nv_bfloat16>(size_t(cap) * d.n_img_tokens * d.img_feat_dim);
 }
@@ -417,6 +459,8 @@ int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
   layout_workspace(h, h->ws, a, cap, tm);
   h->ws.base = base;
   h->ws.bytes = measure.off + 256;
+  B200VQA_CUDA_OK(cudaMemcpy(h->ws.kc_dev, h->ws.kc.data(), h->ws.kc.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  B200VQA_CUDA_OK(cudaMemcpy(h->ws.vc_dev, h->ws.vc.data(), h->ws.vc.size() * sizeof(void*), cudaMemcpyHostToDevice));
   return B200VQA_OK;
 }
 
@@ -425,7 +469,8 @@ int ensure_workspace(b200vqa_handle* h, int B, int t_max) {
 // ---------------------------------------------------------------------------------------------
 // cached 2D operand tensor map: 128-byte swizzle, box = {128 bytes of the inner dimension, box_rows}
 int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, uint64_t cols, uint64_t ld,
-             uint32_t box_rows, const CUtensorMap** out) {
+             uint32_t box_rows, CUtensorMap* out) {
+  // the descriptor is returned BY VALUE (128 B): the cache may be emptied by a later lookup of the same call sequence
   TmapKey key{base, int(type), rows, cols, ld, box_rows, 0u};
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
@@ -435,7 +480,7 @@ int get_tmap(b200vqa_handle* h, const void* base, TmapType type, uint64_t rows, 
     if (rc != B200VQA_OK) return rc;
     it = h->tmaps.emplace(key, m).first;
   }
-  *out = &it->second;
+  *out = it->second;
   return B200VQA_OK;
 }
 
@@ -492,14 +537,14 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
   // not depend on how many other questions share its batch.
   if (epi == kEpiBiasResLN && p.ln_cluster && (K == 256 || K == 512 || K == 1024) && N == 256 && !h->no_ln_cluster)
     bn = 64;
-  const CUtensorMap *ta, *tw;
+  CUtensorMap ta, tw;
   // rows of A are rounded up to whole tiles only virtually: TMA zero-fills rows >= M
   RC_OK(get_tmap(h, A, ty, uint64_t(M), uint64_t(a_cols > 0 ? a_cols : K), uint64_t(lda), 128, &ta));
   RC_OK(get_tmap(h, W, ty, uint64_t(epi == kEpiHead ? p.head_V : N), uint64_t(K), uint64_t(K), bn, &tw));
   p.M = M;
   p.N = N;
   p.K = K;
-  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, *ta, *tw, p, h->num_sms, s));
+  LAUNCH_OK(h, launch_gemm(epi, tf32, bn, ta, tw, p, h->num_sms, s));
   return B200VQA_OK;
 }
 
@@ -545,7 +590,7 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
     RC_OK(gemm_bias(h, false, in, M, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.qkv, s));
     {
       h->cur_tag = kTagEncAttn;
-      const CUtensorMap *tq, *tkv;
+      CUtensorMap tq, tkv;
       RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 128, &tq));
       RC_OK(get_tmap(h, w.qkv, TmapType::kBF16, uint64_t(M), 3 * kD, 3 * kD, 256, &tkv));
       EncAttnParams ap;
@@ -555,7 +600,7 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
       ap.const_len = const_len;
       ap.out = w.attn;
       ap.scale = 1.f / sqrtf(float(kD / d.nhead));
-      LAUNCH_OK(h, launch_enc_attention(*tq, *tkv, w.qkv, ap, s));
+      LAUNCH_OK(h, launch_enc_attention(tq, tkv, w.qkv, ap, s));
     }
     h->cur_tag = kTagEncOutLn;
     RC_OK(gemm_res_ln(h, w.attn, M, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.x1, nullptr, s));
@@ -667,18 +712,18 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.out = du;
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
-        const CUtensorMap* tmem_map;
+        CUtensorMap tmem_map;
         if (h->mem_attn_impl != 0) {
-          const CUtensorMap* tq_map;
+          CUtensorMap tq_map;
           RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128, &tmem_map));
           RC_OK(get_tmap(h, dq, TmapType::kBF16, uint64_t(B) * d.nhead, kD, kD, uint32_t(d.nhead), &tq_map));
           if (h->mem_attn_impl == 3)
-            LAUNCH_OK(h, launch_mem_attn_ring_tc(*tmem_map, *tq_map, mp, s));
+            LAUNCH_OK(h, launch_mem_attn_ring_tc(tmem_map, tq_map, mp, s));
           else
-            LAUNCH_OK(h, launch_mem_attn_tc(*tmem_map, *tq_map, mp, s));
+            LAUNCH_OK(h, launch_mem_attn_tc(tmem_map, tq_map, mp, s));
         } else {
           RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
-          LAUNCH_OK(h, launch_mem_attn(*tmem_map, mp, s));
+          LAUNCH_OK(h, launch_mem_attn(tmem_map, mp, s));
         }
         if (!h->absorb_ov) {
           GemmParams vp;
@@ -716,7 +761,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
                           true));
       {
         // feed-forward block with the hidden dimension split over CTAs (ffn_small.cu): 2 launches
-        const CUtensorMap *tx, *tw1, *tw2;
+        CUtensorMap tx, tw1, tw2;
         RC_OK(get_tmap(h, dx2, TmapType::kBF16, uint64_t(B), kD, kD, 128, &tx));
         RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 128, &tw1));
         RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 256, &tw2));
@@ -754,7 +799,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
           fp.x_next = dx;
         }
         h->cur_tag = kTagDecFfn;
-        LAUNCH_OK(h, launch_ffn_small(*tx, *tw1, *tw2, fp, s));
+        LAUNCH_OK(h, launch_ffn_small(tx, tw1, tw2, fp, s));
         ++h->launches;  // two kernels
       }
       in = out;
@@ -810,9 +855,68 @@ int enqueue_decode_prologue(b200vqa_handle* h, int B, const __nv_bfloat16* memor
   return B200VQA_OK;
 }
 
+bool persist_eligible(const b200vqa_handle* h, const DecodeIO& io) {
+  const auto& d = h->d;
+  return h->decode_persist && h->absorb && io.steps <= kDecPersistMaxSteps && d.dim_ff % 512 == 0 && d.dim_ff <= 2048;
+}
+
+// All positions x layers in ONE launch: a cluster of 8 CTAs per 64 questions (decode_persist.cu).
+int enqueue_decode_persist(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
+                           const DecodeIO& io, cudaStream_t s) {
+  Workspace& w = h->ws;
+  const auto& d = h->d;
+  CUtensorMap ta, tb, tm;
+  RC_OK(get_tmap(h, h->slab_a, TmapType::kBF16, uint64_t(d.n_dec_layers) * h->slab_rows_per_layer, kD, kD, 32, &ta));
+  RC_OK(get_tmap(h, h->slab_b, TmapType::kBF16, uint64_t(d.n_dec_layers) * (d.dim_ff / 64) * kD, 64, 64, 32, &tb));
+  RC_OK(get_tmap(h, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 16, &tm));
+  DecPersistParams p;
+  p.B = B;
+  p.steps = io.steps;
+  p.n_layers = d.n_dec_layers;
+  p.nhead = d.nhead;
+  p.ff = d.dim_ff;
+  p.rows_per_layer = h->slab_rows_per_layer;
+  p.layers = h->dec_layers_dev;
+  p.lens = lens;
+  p.const_len = const_len;
+  p.dx = w.dx; p.dqkv = w.dqkv; p.dattn = w.dattn; p.dx1 = w.dx1; p.dq = w.dq; p.du = w.du; p.dx2 = w.dx2;
+  p.dxo[0] = w.dxo[0]; p.dxo[1] = w.dxo[1];
+  p.dpre = w.dout;
+  p.partial = w.ffn_partial;
+  p.part_rows = (long long)w.drows;
+  p.kc = w.kc_dev;
+  p.vc = w.vc_dev;
+  p.t_max = w.t_max;
+  p.eps = d.layer_norm_eps;
+  p.fn_gamma = h->dec_fn_w;
+  p.fn_beta = h->dec_fn_b;
+  p.head_w = h->head_w;
+  p.head_b = h->head_b;
+  p.head_V = d.dec_vocab;
+  p.tok = w.tok;
+  p.tok_ld = kTokLd;
+  p.logits = io.logits;
+  p.logits_T = io.logits_T;
+  p.forced = io.forced;
+  p.forced_ld = io.forced_ld;
+  p.emb = h->dec_emb;
+  p.pe = h->pe_dec;
+  p.vocab = d.dec_vocab;
+  if (h->persist_stagger_us > 0) {
+    int khz = 0;
+    B200VQA_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+    p.stagger_cycles = int((long long)h->persist_stagger_us * khz / 1000);
+  }
+  p.dbg_stop = h->persist_dbg_stop;
+  h->cur_tag = kTagDecPersist;
+  LAUNCH_OK(h, launch_decode_persist(ta, tb, tm, p, s));
+  return B200VQA_OK;
+}
+
 int enqueue_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
                     const DecodeIO& io, cudaStream_t s) {
   RC_OK(enqueue_decode_prologue(h, B, memory, io, s));
+  if (persist_eligible(h, io)) return enqueue_decode_persist(h, B, memory, lens, const_len, io, s);
   return enqueue_decode_rows(h, 0, B, memory, lens, const_len, io, s);
 }
 
@@ -864,7 +968,9 @@ int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memo
 int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
                 const DecodeIO& io, cudaStream_t s) {
   const bool plain = !io.logits && !io.forced && !io.start_tokens;
-  if (!plain || h->profiling || !h->use_graphs) return enqueue_decoder(h, B, memory, lens, const_len, io, s);
+  // the persistent kernel is two launches (start embedding + decode): nothing for a graph to collapse
+  if (!plain || h->profiling || !h->use_graphs || persist_eligible(h, io))
+    return enqueue_decoder(h, B, memory, lens, const_len, io, s);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   B200VQA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
   if (cs != cudaStreamCaptureStatusNone) return enqueue_decoder(h, B, memory, lens, const_len, io, s);
@@ -1058,6 +1164,9 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
+  if (const char* g = getenv("B200VQA_DECODE")) h->decode_persist = g[0] == 'p';
+  if (const char* g = getenv("B200VQA_PERSIST_STAGGER_US")) h->persist_stagger_us = std::max(0, atoi(g));
+  if (const char* g = getenv("B200VQA_PERSIST_DBG_STOP")) h->persist_dbg_stop = atoi(g);
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
@@ -1752,6 +1861,35 @@ B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, 
   ap.v_mode = v_mode;
   B200VQA_CUDA_OK(launch_enc_attention(tq, tkv, static_cast<const __nv_bfloat16*>(qkv), ap,
                                        static_cast<cudaStream_t>(stream)));
+  return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_dbg_workspace(b200vqa_handle* h, int which, void* dst, size_t dst_bytes, size_t* bytes) {
+  B200VQA_REQUIRE(h != nullptr && bytes, "NULL argument");
+  void* src = nullptr;
+  void** ptr = &src;
+  B200VQA_REQUIRE(h->ws.base != nullptr, "the workspace has not been allocated yet");
+  const Workspace& w = h->ws;
+  const size_t r = w.drows, nh = size_t(h->d.nhead);
+  switch (which) {
+    case 0: *ptr = w.dx; *bytes = r * kD * 2; break;
+    case 1: *ptr = w.dqkv; *bytes = r * 3 * kD * 2; break;
+    case 2: *ptr = w.dattn; *bytes = r * kD * 2; break;
+    case 3: *ptr = w.dx1; *bytes = r * kD * 2; break;
+    case 4: *ptr = w.dq; *bytes = r * nh * kD * 2; break;
+    case 5: *ptr = w.du; *bytes = r * nh * kD * 2; break;
+    case 6: *ptr = w.dx2; *bytes = r * kD * 2; break;
+    case 7: *ptr = w.dxo[0]; *bytes = r * kD * 2; break;
+    case 8: *ptr = w.dxo[1]; *bytes = r * kD * 2; break;
+    case 9: *ptr = w.dout; *bytes = r * kD * 4; break;
+    case 10: *ptr = w.tok; *bytes = size_t(w.cap) * kTokLd * 8; break;
+    default: set_error("unknown workspace buffer %d", which); return B200VQA_ERR_BAD_ARGUMENT;
+  }
+  if (dst && dst_bytes > 0) {
+    RC_OK(set_device(h));
+    B200VQA_CUDA_OK(cudaDeviceSynchronize());
+    B200VQA_CUDA_OK(cudaMemcpy(dst, src, std::min(dst_bytes, *bytes), cudaMemcpyDeviceToDevice));
+  }
   return B200VQA_OK;
 }
 

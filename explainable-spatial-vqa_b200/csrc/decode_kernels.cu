@@ -1031,23 +1031,14 @@ cudaError_t launch_row_attn(const RowAttnParams& p, cudaStream_t stream) {
 
 cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
+  int num_sms = 0;
+  cudaError_t e = current_device_sms(&num_sms);
+  if (e != cudaSuccess) return e;
   // persistent: kMemCtasPerSm CTAs per SM, each streaming its questions back to back
   const int grid = p.B < kMemCtasPerSm * num_sms ? p.B : kMemCtasPerSm * num_sms;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(mem_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMemAttnSmem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mem_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMemAttnSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<4>), kMemAttnSmem);
+  if (e == cudaSuccess) e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<2>), kMemAttnSmem);
+  if (e != cudaSuccess) return e;
   if (p.nhead == 4)
     return launch_kernel(mem_attn_kernel<4>, dim3(grid), dim3(kMemWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   if (p.nhead == 2)

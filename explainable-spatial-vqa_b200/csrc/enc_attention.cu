@@ -247,11 +247,9 @@ cudaError_t launch_dh(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const E
                       cudaStream_t stream) {
   using L = AttnSmem<DH>;
   auto kfn = enc_attention_kernel<DH>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), L::kBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   kfn<<<p.B * p.nhead, kAttnThreads, L::kBytes, stream>>>(tm_q, tm_kv, p);
   return cudaGetLastError();

@@ -339,12 +339,9 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
   if (p.M <= 0) return cudaSuccess;
   if (p.ff % kSlice != 0 || p.n_slices != p.ff / kSlice) return cudaErrorInvalidValue;
   if (p.head_w && (p.head_V < 1 || p.head_V > 64 || !p.tok || !p.head_b)) return cudaErrorInvalidValue;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e =
-        cudaFuncSetAttribute(ffn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::kBytes);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(ffn_partial_kernel), FfnSmem::kBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   dim3 grid((p.M + 127) / 128, p.n_slices);
   cudaError_t e = launch_kernel(ffn_partial_kernel, grid, dim3(kFfnThreads), FfnSmem::kBytes, stream, p.pdl, tm_x, tm_w1,

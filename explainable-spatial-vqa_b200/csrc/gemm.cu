@@ -596,11 +596,9 @@ cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const G
                        cudaStream_t stream) {
   using L = GemmSmem<BN>;
   auto kfn = gemm_tc_kernel<BN, EPI, TF32>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), L::kBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int tiles = ((p.M + kBM - 1) / kBM) * (p.N / BN);
   if (tiles <= 0) return cudaSuccess;
@@ -860,12 +858,9 @@ template <int NKB>
 cudaError_t launch_ln_cluster_k(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
                                 cudaStream_t stream) {
   using L = LnClSmem<NKB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kBytes);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_ln_cluster_kernel<NKB>), L::kBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int tiles_m = (p.M + kBM - 1) / kBM;
   if (tiles_m <= 0) return cudaSuccess;

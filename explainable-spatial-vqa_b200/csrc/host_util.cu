@@ -3,6 +3,8 @@
 
 #include <cstring>
 #include <mutex>
+#include <set>
+#include <utility>
 
 namespace b200vqa {
 
@@ -78,6 +80,38 @@ static int encode_2d(CUtensorMap* out, const void* base, TmapType type, uint64_t
     return B200VQA_ERR_CUDA;
   }
   return B200VQA_OK;
+}
+
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes) {
+  // the attribute belongs to the (kernel, device) pair: a second handle on another GPU of the same process needs its
+  // own opt-in (pipeline slots may also call from different host threads)
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.insert({kernel, dev});
+  return e;
+}
+
+cudaError_t current_device_sms(int* sms) {
+  static int cache[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) {
+    *sms = cache[dev];
+    return cudaSuccess;
+  }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  *sms = n;
+  return cudaSuccess;
 }
 
 int require_sm100(int device, int* num_sms) {

@@ -316,6 +316,72 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------
+// Persistent decode (decode_persist.cu): ALL positions x layers of a greedy decode in one launch.
+//
+// A cluster of 8 CTAs owns a tile of 64 questions for the whole decode (questions never interact, so clusters never
+// synchronise with each other).  Inside the cluster every dense layer is split by output columns over the 8 CTAs
+// (tcgen05, M = 64 questions, weights streamed from L2 through a TMA ring, accumulator in TMEM), every per-question
+// operation (self-attention over the KV cache, LayerNorm, the absorbed cross-attention over the encoder memory, the
+// vocabulary head + argmax + next embedding) is split by rows: CTA r owns questions 8r..8r+7, one warp each.  The
+// hand-offs between the two splits go through the (L2-resident) activation scratch below and a cluster-wide mbarrier
+// rendezvous - what used to be a kernel boundary (IQAP:208-236, FA:137-145).
+// ------------------------------------------------------------------------------------------
+constexpr int kDecPersistMaxSteps = 32;  // the warp-per-question self-attention keeps <= 32 keys in registers
+
+// per-layer fp32 vectors (device pointers), one entry per decoder layer, array in device memory
+struct DecLayerDev {
+  const float *b_in, *b_out, *n1w, *n1b;   // self-attention in_proj / out_proj biases, norm1
+  const float *b_qk, *b_v, *b_co, *n2w, *n2b;  // absorbed query bias, value bias, cross out_proj bias, norm2
+  const float *b1, *b2, *n3w, *n3b;        // feed-forward biases, norm3
+};
+
+struct DecPersistParams {
+  int B = 0, steps = 0, n_layers = 0, nhead = 4, ff = 0;
+  // weight slab A: rows of 256 bf16 (K-major); per layer [in_proj 768 | out_proj 256 | w_qk nhead*256 | w_v 256 |
+  // cross out_proj 256 | linear1 ff]; slab B: linear2 as k-blocks, row (layer * ff/64 + kb) * 256 + n holds
+  // W2[n][64 kb .. 64 kb + 63]
+  int rows_per_layer = 0;
+  const DecLayerDev* layers = nullptr;
+  const int32_t* lens = nullptr;  // [B] memory rows per question, or null -> const_len
+  int const_len = 0;
+  // activation scratch, rows indexed by question (library workspace)
+  __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dattn = nullptr, *dx1 = nullptr, *dq = nullptr, *du = nullptr,
+                *dx2 = nullptr, *dxo[2] = {nullptr, nullptr};
+  float* dpre = nullptr;      // [rows, 256] pre-LayerNorm sums
+  float* partial = nullptr;   // [8][part_rows][256] feed-forward partial sums
+  long long part_rows = 0;
+  __nv_bfloat16* const* kc = nullptr;  // [n_layers] device array of self-attention key caches [rows, t_max, 256]
+  __nv_bfloat16* const* vc = nullptr;
+  int t_max = 0;
+  float eps = 1e-5f;
+  const float *fn_gamma = nullptr, *fn_beta = nullptr;  // nn.Transformer's final decoder norm (FA:42), or null
+  // vocabulary head (fp32, CUDA cores: the row is already in the owning warp's registers)
+  const float *head_w = nullptr, *head_b = nullptr;
+  int head_V = 0;
+  int64_t* tok = nullptr;
+  int tok_ld = 0;
+  float* logits = nullptr;
+  int logits_T = 0;
+  const int64_t* forced = nullptr;
+  int forced_ld = 0;
+  const float *emb = nullptr, *pe = nullptr;  // decoder embedding [vocab, 256], positional table [*, 256]
+  int vocab = 0;
+  int stagger_cycles = 0;   // start delay of odd tiles: de-phases the clusters' HBM-bound and latency-bound phases
+  int dbg_stop = -1;        // k >= 1: return after the k-th cluster rendezvous of the first stage (tests: inspect the scratch)
+};
+// tm_wa: slab A [rows, 256] bf16, box {64, 32}; tm_wb: slab B [rows, 64] bf16, box {64, 32};
+// tm_mem: encoder memory [B * kLP, 256] bf16, box {64, 16}   (all 128-byte swizzled)
+cudaError_t launch_decode_persist(const CUtensorMap& tm_wa, const CUtensorMap& tm_wb, const CUtensorMap& tm_mem,
+                                  const DecPersistParams& p, cudaStream_t stream);
+// linear2 weight [256, ff] bf16 -> k-block-major slab B rows (see above)
+cudaError_t launch_pack_w2_kblocks(const __nv_bfloat16* w2, __nv_bfloat16* out, int ff, cudaStream_t stream);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes);
+// SM count of the CURRENT device (cached per device)
+cudaError_t current_device_sms(int* sms);
+
 // programs [B,T] i64 (prefix order) -> func [B,S], deps [B,S,2], n_steps [B] (all int32) in execution order
 struct ProgToChainParams {
   int B = 0, T = 0, S = 0, prog_vocab = 0;

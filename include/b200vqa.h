@@ -345,6 +345,10 @@ B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, 
  * question, 3 = tcgen05 ring kernel (one persistent CTA per SM); stamps: optional device int64 [2*B, 16] stage stamps of the tcgen05 kernel (tools/microbench_mem_attn.py) */
 B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const int32_t* lens, int const_len, int B, int nhead,
                          int impl, void* out, long long* stamps, void* stream);
+/* Test hook: copies one decode scratch buffer of the handle's workspace (sized by an earlier call) into the device
+ * buffer dst (at most dst_bytes) after a device synchronisation; *bytes = the buffer's size.  which: 0 dx, 1 dqkv, 2 dattn, 3 dx1, 4 dq, 5 du, 6 dx2, 7 dxo[0], 8 dxo[1] (bf16), 9 dout / pre-LN (fp32),
+ * 10 tok (int64 [cap, 65]).  Used by tests / tools to compare the persistent decode kernel with the per-kernel chain. */
+B200VQA_API int b200vqa_dbg_workspace(b200vqa_handle* h, int which, void* dst, size_t dst_bytes, size_t* bytes);
 
 #ifdef __cplusplus
 }
