@@ -47,7 +47,7 @@ class ModelDesc(C.Structure):
                 ("nhead", C.c_int32), ("n_enc_layers", C.c_int32), ("n_dec_layers", C.c_int32), ("dim_ff", C.c_int32),
                 ("enc_vocab", C.c_int32), ("dec_vocab", C.c_int32), ("max_q_len", C.c_int32),
                 ("pe_enc_len", C.c_int32), ("pe_dec_len", C.c_int32), ("answer_hidden", C.c_int32),
-                ("num_classes", C.c_int32), ("layer_norm_eps", C.c_float),
+                ("num_classes", C.c_int32), ("layer_norm_eps", C.c_float), ("answer_pool_rows", C.c_int32),
                 ("image_proj_weight", _vp), ("image_proj_bias", _vp), ("cls_token", _vp),
                 ("enc_embedding", _vp), ("dec_embedding", _vp), ("pe_enc", _vp), ("pe_dec", _vp),
                 ("enc_layers", C.POINTER(EncoderLayerWeights)), ("dec_layers", C.POINTER(DecoderLayerWeights)),
@@ -81,6 +81,7 @@ SIGNATURES = {
     "b200vqa_last_error": (C.c_char_p, []),
     "b200vqa_version": (C.c_char_p, []),
     "b200vqa_launch_count": (C.c_uint64, [_vp]),
+    "b200vqa_set_start_token": (C.c_int, [_vp, C.c_int]),
     "b200vqa_profile_num_tags": (C.c_int, []),
     "b200vqa_profile_tag_name": (C.c_char_p, [C.c_int]),
     "b200vqa_profile_begin": (C.c_int, [_vp]),
@@ -196,6 +197,9 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._lib.b200vqa_launch_count(self._h))
+
+    def set_start_token(self, token: int) -> None:
+        check(self._lib.b200vqa_set_start_token(self._h, int(token)), "b200vqa_set_start_token")
 
     def workspace_bytes(self, B: int) -> int:
         return int(self._lib.b200vqa_workspace_bytes(self._h, int(B)))

@@ -150,10 +150,12 @@ struct b200vqa_handle {
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
+  int iqap_start_token = 1;           // Config.SPECIAL_TOKEN_ID (IQAP:24,205); b200vqa_set_start_token
   // persistent decode kernel (decode_persist.cu): all positions x layers in one launch
   bool decode_persist = false;        // B200VQA_DECODE=persist|chain
   int persist_stagger_us = 0;         // B200VQA_PERSIST_STAGGER_US: start delay of odd question tiles
   int persist_dbg_stop = -1;          // tests: stop after this many rendezvous of the first stage
+  long long* persist_clk = nullptr;   // B200VQA_PERSIST_STAMPS=1: [8][16] stage timeline of CTA (0, 0) (tools/)
   __nv_bfloat16* slab_a = nullptr;    // decoder weights as rows of 256 bf16 (kernels.h: DecPersistParams)
   __nv_bfloat16* slab_b = nullptr;    // linear2 as k-blocks of [256 x 64]
   int slab_rows_per_layer = 0;
@@ -379,6 +381,8 @@ int validate_desc(const b200vqa_model_desc* d) {
                     "IQAP needs cls_token and the answer classifier weights");
     B200VQA_REQUIRE(d->answer_hidden > 0 && d->answer_hidden <= 1024 && d->num_classes > 0,
                     "answer head sizes out of range (hidden %d, classes %d)", d->answer_hidden, d->num_classes);
+    B200VQA_REQUIRE(d->answer_pool_rows >= 0 && d->answer_pool_rows <= d->n_img_tokens,
+                    "answer_pool_rows %d out of range (0..%d image tokens)", d->answer_pool_rows, d->n_img_tokens);
     if (1 + d->n_img_tokens + d->max_q_len > kLP || d->pe_enc_len < 1 + d->n_img_tokens + d->max_q_len) {
       set_error("IQAP sequence 1+%d+%d exceeds %d rows or the positional table (%d)", d->n_img_tokens, d->max_q_len,
                 kLP, d->pe_enc_len);
@@ -908,6 +912,7 @@ int enqueue_decode_persist(b200vqa_handle* h, int B, const __nv_bfloat16* memory
     p.stagger_cycles = int((long long)h->persist_stagger_us * khz / 1000);
   }
   p.dbg_stop = h->persist_dbg_stop;
+  p.dbg_clk = h->persist_clk;
   h->cur_tag = kTagDecPersist;
   LAUNCH_OK(h, launch_decode_persist(ta, tb, tm, p, s));
   return B200VQA_OK;
@@ -1118,9 +1123,9 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
   }
   h->cur_tag = kTagAnswer;
   LAUNCH_OK(h, launch_answer_head(memory, B, h->ans_w0t, h->ans_b0, d.answer_hidden, h->ans_w1, h->ans_b1,
-                                  d.num_classes, answer, s));
+                                  d.num_classes, d.answer_pool_rows, answer, s));
   DecodeIO io;
-  io.start_token = 1;  // Config.SPECIAL_TOKEN_ID (IQAP:24,205)
+  io.start_token = h->iqap_start_token;  // Config.SPECIAL_TOKEN_ID (IQAP:24,205)
   io.steps = T;
   io.logits = step_logits;
   io.logits_T = T;
@@ -1167,6 +1172,10 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_DECODE")) h->decode_persist = g[0] == 'p';
   if (const char* g = getenv("B200VQA_PERSIST_STAGGER_US")) h->persist_stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_PERSIST_DBG_STOP")) h->persist_dbg_stop = atoi(g);
+  if (const char* g = getenv("B200VQA_PERSIST_STAMPS")) {
+    if (g[0] && g[0] != '0' && cudaMalloc(&h->persist_clk, 8 * 24 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(h->persist_clk, 0, 8 * 24 * sizeof(long long));
+  }
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
@@ -1206,6 +1215,7 @@ B200VQA_API int b200vqa_refresh_weights(b200vqa_handle* h, const b200vqa_model_d
                       desc->enc_vocab == o.enc_vocab && desc->dec_vocab == o.dec_vocab &&
                       desc->pe_enc_len == o.pe_enc_len && desc->pe_dec_len == o.pe_dec_len &&
                       desc->answer_hidden == o.answer_hidden && desc->num_classes == o.num_classes &&
+                      desc->answer_pool_rows == o.answer_pool_rows &&
                       desc->img_feat_dim == o.img_feat_dim,
                   "refresh_weights: the new descriptor has different dimensions; create a new handle");
   RC_OK(set_device(h));
@@ -1229,6 +1239,7 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
   if (h->wbase) cudaFree(h->wbase);
   if (h->stage) cudaFree(h->stage);
   if (h->img_tok) cudaFree(h->img_tok);
+  if (h->persist_clk) cudaFree(h->persist_clk);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
@@ -1252,6 +1263,14 @@ B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B) {
 }
 
 B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h) { return h ? h->launches : 0; }
+
+B200VQA_API int b200vqa_set_start_token(b200vqa_handle* h, int start_token) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(start_token >= 0 && start_token < h->d.dec_vocab, "start token %d outside the decoder vocabulary (%d)",
+                  start_token, h->d.dec_vocab);
+  h->iqap_start_token = start_token;
+  return B200VQA_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ profiler
 B200VQA_API int b200vqa_profile_num_tags(void) { return kNumTags; }
@@ -1411,7 +1430,7 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
     h->cur_tag = kTagMisc;
     LAUNCH_OK(h, launch_memory_import(memory + size_t(b0) * kD, S, nb, B, h->ws.mem, s));
     DecodeIO io;
-    io.start_token = 1;
+    io.start_token = h->iqap_start_token;
     io.steps = program_len;
     io.logits = opt_step_logits ? opt_step_logits + size_t(b0) * program_len * V : nullptr;
     io.logits_T = program_len;
@@ -1883,6 +1902,9 @@ B200VQA_API int b200vqa_dbg_workspace(b200vqa_handle* h, int which, void* dst, s
     case 8: *ptr = w.dxo[1]; *bytes = r * kD * 2; break;
     case 9: *ptr = w.dout; *bytes = r * kD * 4; break;
     case 10: *ptr = w.tok; *bytes = size_t(w.cap) * kTokLd * 8; break;
+    case 11:
+      B200VQA_REQUIRE(h->persist_clk != nullptr, "no stage timeline: create the handle with B200VQA_PERSIST_STAMPS=1");
+      *ptr = h->persist_clk; *bytes = 8 * 24 * sizeof(long long); break;
     default: set_error("unknown workspace buffer %d", which); return B200VQA_ERR_BAD_ARGUMENT;
   }
   if (dst && dst_bytes > 0) {

@@ -24,6 +24,9 @@
 //   cluster scope); the producer and MMA-issue warps never take part, so weight prefetch is not stopped by it.
 //   R6 takes the ring's shared memory for the per-warp memory tiles (16 rows x 512 B, two slots per warp, each warp
 //   its own TMA producer); the weight producer resumes when the 8 warps have finished (attn_done).
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -396,6 +399,11 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
       while (clock64() - t0 < p.stagger_cycles) {}
     }
 
+    // optional timeline of CTA (0, 0): clock64() of worker thread 0 at 16 points of each of the first 8 stages,
+    // + [16] cycles its warp waited for memory tiles in R6, [17] R6 start, [18] queries loaded (tools/)
+    const bool stamping = p.dbg_clk != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && wt == 0;
+#define DP_STAMP(i) \
+  if (stamping && st < 8) p.dbg_clk[st * 24 + (i)] = clock64()
     for (int st = 0; st < n_stage && !stop; ++st) {
       const int t = st / p.n_layers, l = st % p.n_layers;
       const bool last = l == p.n_layers - 1;
@@ -404,8 +412,11 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
       __nv_bfloat16* xout = p.dxo[l & 1];
 
       // ---------------------------------------------------------------- G1: qkv
+      DP_STAMP(0);
       load_a(xin, kD);
+      DP_STAMP(1);
       wait_acc();
+      DP_STAMP(2);
       epilogue(96, [&](int col, const uint32_t (&v)[16]) {
         const int n = 96 * r + col;
         float b[16];
@@ -419,7 +430,9 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       });
+      DP_STAMP(3);
       rendezvous();
+      DP_STAMP(4);
       if (stop) break;
 
       // ---------------------------------------------------------------- R2: self-attention over <= 32 keys
@@ -507,6 +520,7 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         *reinterpret_cast<uint4*>(p.dattn + size_t(qrow) * kD + lane * 8) = pack8(acc);
       }
       rendezvous();
+      DP_STAMP(5);
       if (stop) break;
 
       // ---------------------------------------------------------------- G3: out_proj + residual -> pre-LN sums
@@ -542,15 +556,18 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
       wait_acc();
       out_proj_epilogue(L.b_out, xin);
       rendezvous();
+      DP_STAMP(6);
       if (stop) break;
       // ---------------------------------------------------------------- R4: LN1
       ln_rows(L.n1w, L.n1b, p.dx1);
       rendezvous();
+      DP_STAMP(7);
       if (stop) break;
 
       // ---------------------------------------------------------------- G5: absorbed queries
       load_a(p.dx1, kD);
       wait_acc();
+      DP_STAMP(8);
       // every weight chunk issued so far has been consumed: the ring's shared memory is this warp's until attn_done
       if (lane == 0) {
         if (n_tiles > 0) issue_tile(0);
@@ -570,10 +587,12 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       });
       rendezvous();
+      DP_STAMP(9);
       // (a debug stop must still drain the two tiles in flight: fall through R6 and stop at its rendezvous)
 
       // ---------------------------------------------------------------- R6: absorbed cross-attention on the memory
       {
+        DP_STAMP(17);
         const int g = lane >> 2, q4 = lane & 3;
         const float sl2 = rsqrtf(float(DH)) * 1.4426950408889634f;
         uint32_t bq[16][2];
@@ -585,6 +604,8 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
             bq[k][1] = (qvalid && g < NH) ? __ldcg(reinterpret_cast<const uint32_t*>(qp + 16 * k + 8)) : 0u;
           }
         }
+        DP_STAMP(18);
+        long long waited = 0;
         float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
         float acc[16][4];
 #pragma unroll
@@ -593,7 +614,9 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
           for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
         for (int i = 0; i < n_tiles; ++i) {
           const int s = i & 1;
+          const long long tw0 = stamping ? clock64() : 0;
           dp_wait(&memfull[w * 2 + s], (mem_phase >> s) & 1u, 8);
+          if (stamping) waited += clock64() - tw0;
           mem_phase ^= 1u << s;
           const uint32_t tile = ring + s * 8192;
           float c[4][4];
@@ -690,8 +713,11 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(attn_done);
+        if (stamping && st < 8) p.dbg_clk[st * 24 + 16] = waited;
       }
+      DP_STAMP(10);
       rendezvous();
+      DP_STAMP(11);
       if (stop) break;
 
       // ---------------------------------------------------------------- G7: per-head value projection
@@ -711,6 +737,7 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       });
       rendezvous();
+      DP_STAMP(12);
       if (stop) break;
 
       // ---------------------------------------------------------------- G8 + R9: cross out_proj + residual, LN2
@@ -721,6 +748,7 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
       if (stop) break;
       ln_rows(L.n2w, L.n2b, p.dx2);
       rendezvous();
+      DP_STAMP(13);
       if (stop) break;
 
       // ---------------------------------------------------------------- G10: hidden slice -> shared memory (A of G11)
@@ -759,6 +787,7 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
                                __uint_as_float(v[4 * j + 3]));
       });
       rendezvous();
+      DP_STAMP(14);
       if (stop) break;
 
       // ---------------------------------------------------------------- R12: reduce + LN3 (+ final norm, head, next input)
@@ -852,7 +881,9 @@ decode_persist_kernel(const __grid_constant__ CUtensorMap tm_wa, const __grid_co
         }
       }
       rendezvous();
+      DP_STAMP(15);
     }
+#undef DP_STAMP
   }
 
   // nobody leaves while a peer may still arrive on its barriers
@@ -892,6 +923,28 @@ cudaError_t launch_decode_persist(const CUtensorMap& tm_wa, const CUtensorMap& t
       p.n_layers < 1)
     return cudaErrorInvalidValue;
   const dim3 grid(kDpCluster, (p.B + kDpTile - 1) / kDpTile);
+  if (getenv("B200VQA_PERSIST_VERBOSE")) {
+    static bool once = false;
+    if (!once) {
+      once = true;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(kDpThreads);
+      cfg.dynamicSmemBytes = kDpSmem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kDpCluster;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = -1;
+      ensure_dyn_smem(reinterpret_cast<const void*>(decode_persist_kernel<4>), kDpSmem);
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_persist_kernel<4>, &cfg);
+      fprintf(stderr, "b200vqa: decode_persist grid %d x %d, smem %d B, max active clusters %d (%s)\n", grid.x, grid.y,
+              kDpSmem, n, cudaGetErrorString(e));
+    }
+  }
   if (p.nhead == 4) {
     cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_persist_kernel<4>), kDpSmem);
     if (e != cudaSuccess) return e;

@@ -169,8 +169,10 @@ cudaError_t launch_memory_import(const float* mem, int S, int B, int ldb, __nv_b
 cudaError_t launch_memory_export(const __nv_bfloat16* x, int S, int B, int ldb, float* mem, cudaStream_t stream);
 
 // IQAP answer head on the CLS row: Linear(256,hidden)+ReLU+Linear(hidden,C), fp32 weights (IQAP:122-127,179).
+// pool_rows > 0: on the mean of memory rows 1..pool_rows instead (bbox regressor, train_transformer_iqap_bb.py:304-310).
 cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0, const float* b0, int hidden,
-                               const float* w1, const float* b1, int classes, float* out, cudaStream_t stream);
+                               const float* w1, const float* b1, int classes, int pool_rows, float* out,
+                               cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------
 // Decoder (decode_kernels.cu).  All decode positions of a question are produced on the device; the greedy
@@ -368,6 +370,7 @@ struct DecPersistParams {
   const float *emb = nullptr, *pe = nullptr;  // decoder embedding [vocab, 256], positional table [*, 256]
   int vocab = 0;
   int stagger_cycles = 0;   // start delay of odd tiles: de-phases the clusters' HBM-bound and latency-bound phases
+  long long* dbg_clk = nullptr;  // optional [8][24] int64: timeline of CTA (0, 0) over the first 8 stages (tools/)
   int dbg_stop = -1;        // k >= 1: return after the k-th cluster rendezvous of the first stage (tests: inspect the scratch)
 };
 // tm_wa: slab A [rows, 256] bf16, box {64, 32}; tm_wb: slab B [rows, 64] bf16, box {64, 32};

@@ -205,17 +205,34 @@ __global__ void memory_export_kernel(const __nv_bfloat16* __restrict__ x, int S,
 // ------------------------------------------------------------------------------------------------
 // IQAP answer head (IQAP:122-127,176-179) on the CLS row; fp32 weights, one block per question.
 // w0_t is answer_classifier.0.weight transposed to [d, hidden] so thread j reads coalesced.
+// pool_rows > 0: the input is the mean of memory rows 1..pool_rows instead (the image tokens) - the bounding-box
+// regressor of train_transformer_iqap_bb.py:304-310 (same Linear -> ReLU -> Linear shape, 40 outputs).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) answer_head_kernel(const __nv_bfloat16* __restrict__ memory,
                                                           const float* __restrict__ w0_t,
                                                           const float* __restrict__ b0, int hidden,
                                                           const float* __restrict__ w1,
-                                                          const float* __restrict__ b1, int classes,
+                                                          const float* __restrict__ b1, int classes, int pool_rows,
                                                           float* __restrict__ out) {
   __shared__ float xs[kD];
   __shared__ float hs[1024];
   const int b = blockIdx.x;
-  xs[threadIdx.x] = __bfloat162float(memory[size_t(b) * kLP * kD + threadIdx.x]);
+  const __nv_bfloat16* mrow = memory + size_t(b) * kLP * kD + threadIdx.x;  // thread = channel: coalesced 512-byte rows
+  if (pool_rows <= 0) {
+    xs[threadIdx.x] = __bfloat162float(mrow[0]);
+  } else {
+    float acc = 0.f;
+    int r = 1;
+    for (; r + 7 <= pool_rows; r += 8) {  // eight rows in flight
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __bfloat162float(mrow[size_t(r + u) * kD]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; r <= pool_rows; ++r) acc += __bfloat162float(mrow[size_t(r) * kD]);
+    xs[threadIdx.x] = acc / float(pool_rows);
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < hidden; j += 256) {
     float acc = b0[j];
@@ -472,9 +489,10 @@ cudaError_t launch_gather_image_rows(const __nv_bfloat16* img_tok, const int32_t
 }
 
 cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* w0_t, const float* b0, int hidden,
-                               const float* w1, const float* b1, int classes, float* out, cudaStream_t stream) {
-  if (hidden > 1024) return cudaErrorInvalidValue;
-  answer_head_kernel<<<B, 256, 0, stream>>>(memory, w0_t, b0, hidden, w1, b1, classes, out);
+                               const float* w1, const float* b1, int classes, int pool_rows, float* out,
+                               cudaStream_t stream) {
+  if (hidden > 1024 || pool_rows >= kLP) return cudaErrorInvalidValue;
+  answer_head_kernel<<<B, 256, 0, stream>>>(memory, w0_t, b0, hidden, w1, b1, classes, pool_rows, out);
   return cudaGetLastError();
 }
 

@@ -150,7 +150,9 @@ class VQAModel(nn.Module):
         return d, keep
 
     def _native(self, slot: int = 0) -> nat.Handle:
-        return self._pool.get(slot)
+        h = self._pool.get(slot)
+        h.set_start_token(Config.SPECIAL_TOKEN_ID)  # read at decode time like the reference (IQAP:205)
+        return h
 
     @staticmethod
     def _check_input(t, what, dtype):

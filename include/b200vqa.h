@@ -104,6 +104,9 @@ typedef struct b200vqa_model_desc {
   int32_t answer_hidden; /* IQAP hidden_dim (256) */
   int32_t num_classes;   /* IQAP answer classes */
   float layer_norm_eps;  /* 1e-5 */
+  int32_t answer_pool_rows; /* 0: the answer head reads the [CLS] row of the memory (IQAP:176-179); n > 0: it reads the mean
+                             * of memory rows 1..n - the bounding-box regressor of train_transformer_iqap_bb.py:304-310
+                             * (answer_w0/b0/w1/b1 = bbox_regressor.0 / .2, num_classes = 40 = 10 boxes x 4) */
 
   const float* image_proj_weight; /* [d, 1024] */
   const float* image_proj_bias;   /* [d] */
@@ -136,6 +139,9 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
 B200VQA_API void b200vqa_destroy(b200vqa_handle* h);
 /* Re-pack after the caller changed parameter values in place (load_state_dict on a live module). */
 B200VQA_API int b200vqa_refresh_weights(b200vqa_handle* h, const b200vqa_model_desc* desc);
+/* <START> token the IQAP decode begins with: the reference reads Config.SPECIAL_TOKEN_ID at decode time (IQAP:24,205).
+ * Default 1.  Applies to every later b200vqa_iqap_* call on this handle. */
+B200VQA_API int b200vqa_set_start_token(b200vqa_handle* h, int start_token);
 /* Device bytes of activations the library will hold for a batch of B questions. */
 B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B);
 B200VQA_API const char* b200vqa_last_error(void);

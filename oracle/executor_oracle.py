@@ -10,6 +10,7 @@ F.linear / softmax / layer_norm only and cites the lines it follows:
 
   IQAP = /root/reference/code/inference_transformer_iqap.py
   FA   = /root/reference/code/inference_transformer_full_annotation_new.py
+  BB   = /root/reference/code/train_transformer_iqap_bb.py (the continuous bounding-box head, model class only)
 
 Parity pin: the reference ships no tests, checkpoints or golden vectors for this path, so the
 pins are outputs of the reference ITSELF, generated in the build container by oracle/make_golden.py
@@ -195,6 +196,46 @@ def iqap_forward(sd, image_features, questions, T=27, forced=None, recompute=Fal
     answer = iqap_answer(sd, memory)
     programs, logits = iqap_decode(sd, memory, T, 1, 4, forced, recompute)
     return {"answer": answer, "programs": programs, "logits": logits, "memory": memory.transpose(0, 1).contiguous()}
+
+
+# ------------------------------------------------------------------------------------------------
+# IQAP with the continuous bounding-box head: VQAModel.forward / autoregressive_decode of
+# BB = /root/reference/code/train_transformer_iqap_bb.py (:287-356)
+# ------------------------------------------------------------------------------------------------
+def iqap_bb_boxes(sd, memory, n_img=196):
+    """memory (B, S, d) batch-first -> boxes (B, 10, 4): bbox_regressor(mean(memory[1 : 1 + 196]))   (BB:304-310)."""
+    pooled = memory[:, 1:1 + n_img].mean(dim=1)                                              # BB:305-307
+    h = torch.relu(F.linear(pooled, sd["bbox_regressor.0.weight"], sd["bbox_regressor.0.bias"]))
+    return F.linear(h, sd["bbox_regressor.2.weight"], sd["bbox_regressor.2.bias"]).view(memory.shape[0], 10, 4)
+
+
+@torch.no_grad()
+def iqap_bb_forward(sd, image_features, questions, seq_len=28, forced=None, recompute=False, nhead=4):
+    """-> dict(seq_logits (B, 28, Vp), boxes (B, 10, 4), tokens (B, 28)).  The encoder is IQAP's (BB:287-302 ==
+    IQAP:152-173); the decoder is one layer over program + answer tokens, start token <SOS> = 1 (BB:312-356)."""
+    memory = iqap_encode(sd, image_features.float(), questions.long(), nhead)
+    boxes = iqap_bb_boxes(sd, memory)
+    B = memory.shape[0]
+    emb, pe = sd["decoder_embedding.weight"], sd["pos_decoder.pe"][:, 0]
+    prefix = torch.full((B, 1), 1, dtype=torch.long)                                         # BB:323-329
+    dec = None if recompute else _CachedDecoder(sd, "transformer_decoder.layers.", memory, nhead)
+    n_layers = count_layers(sd, "transformer_decoder.layers.")
+    toks, logits = [], []
+    for t in range(seq_len):                                                                 # BB:333
+        if recompute:
+            x = F.embedding(prefix, emb) + pe[: prefix.shape[1]][None]                       # BB:334-336
+            for l in range(n_layers):
+                x = decoder_layer(sd, f"transformer_decoder.layers.{l}.", x, memory, nhead)  # BB:341-345
+            last = x[:, -1]
+        else:
+            last = dec.step(F.embedding(prefix[:, -1:], emb) + pe[t][None, None])[:, 0]
+        lg = F.linear(last, sd["output_layer.weight"], sd["output_layer.bias"])              # BB:347
+        nxt = torch.max(lg, dim=1)[1]                                                        # BB:351
+        toks.append(nxt)
+        logits.append(lg)
+        feed = forced[:, t] if forced is not None else nxt
+        prefix = torch.cat([prefix, feed[:, None]], dim=1)                                   # BB:353
+    return {"seq_logits": torch.stack(logits, dim=1), "boxes": boxes, "tokens": torch.stack(toks, dim=1)}
 
 
 # ------------------------------------------------------------------------------------------------

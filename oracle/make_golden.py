@@ -110,6 +110,22 @@ def golden_fa():
     print("fa: chain final =", final)
 
 
+def golden_iqap_bb():
+    """The reference's bounding-box variant (train_transformer_iqap_bb.py:222-356): boxes + 28 x Vp logits."""
+    import train_transformer_iqap_bb as ref_bb
+    torch.manual_seed(0)
+    model = ref_bb.VQAModel(85, 256, 256, 44, 27, 196).eval()
+    img, q = orc.iqap_inputs(4, seed=4321)
+    with torch.no_grad():
+        seq_logits, boxes = model(img, q)
+    keys, sums, asums = pack_checksums(model.state_dict())
+    np.savez_compressed(os.path.join(OUT, "iqap_bb_b4.npz"), torch_version=torch.__version__, sd_keys=keys, sd_sums=sums,
+                        sd_abs_sums=asums, img_sum=img.double().sum().item(), questions=q.numpy(),
+                        seq_logits=seq_logits.numpy(), boxes=boxes.numpy(),
+                        tokens=seq_logits.argmax(-1).numpy())
+    print("iqap_bb: boxes[0,0] =", boxes[0, 0].tolist())
+
+
 def golden_lstm():
     import run_model_lstm_qp as ref_qp
     from oracle import lstm_oracle
@@ -134,8 +150,9 @@ def golden_lstm():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_iqap()
-    golden_fa()
-    golden_lstm()
+    only = sys.argv[1:]
+    for name, fn in (("iqap", golden_iqap), ("fa", golden_fa), ("lstm", golden_lstm), ("iqap_bb", golden_iqap_bb)):
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
