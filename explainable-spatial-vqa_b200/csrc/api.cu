@@ -143,9 +143,6 @@ struct b200vqa_handle {
                                // ONE K = nhead*256 LayerNorm GEMM instead of grouped value GEMM + out_proj LayerNorm GEMM
                                // (one launch fewer per layer and position, but four CTAs stream 4x the weight bytes:
                                // measured 4.57 vs 4.47 ms per step, so off by default)
-  int mem_attn_impl = 0;       // B200VQA_MEM_ATTN=mma|tc|ring: absorbed cross-attention on warp-level MMAs (persistent ring
-                               // kernel, 0), on tcgen05 with a cluster of two CTAs per question (1) or on tcgen05 with
-                               // one persistent CTA per SM and a three-stage tile ring (3)
   bool no_warp_self_attn = false;  // B200VQA_NO_WARP_SELF_ATTN=1: decoder self-attention with one CTA per question (A/B runs)
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
@@ -717,18 +714,8 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.pdl = true;
         h->cur_tag = kTagDecCrossAttn;
         CUtensorMap tmem_map;
-        if (h->mem_attn_impl != 0) {
-          CUtensorMap tq_map;
-          RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128, &tmem_map));
-          RC_OK(get_tmap(h, dq, TmapType::kBF16, uint64_t(B) * d.nhead, kD, kD, uint32_t(d.nhead), &tq_map));
-          if (h->mem_attn_impl == 3)
-            LAUNCH_OK(h, launch_mem_attn_ring_tc(tmem_map, tq_map, mp, s));
-          else
-            LAUNCH_OK(h, launch_mem_attn_tc(tmem_map, tq_map, mp, s));
-        } else {
-          RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
-          LAUNCH_OK(h, launch_mem_attn(tmem_map, mp, s));
-        }
+        RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
+        LAUNCH_OK(h, launch_mem_attn(tmem_map, mp, s));
         if (!h->absorb_ov) {
           GemmParams vp;
           vp.bias = L.cross_attn.b_in + 2 * kD;
@@ -1164,7 +1151,6 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
-  if (const char* g = getenv("B200VQA_MEM_ATTN")) h->mem_attn_impl = g[0] == 't' ? 1 : (g[0] == 'r' ? 3 : 0);
   if (const char* g = getenv("B200VQA_NO_WARP_SELF_ATTN")) h->no_warp_self_attn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
@@ -1493,6 +1479,10 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16
   float* d_ans = reinterpret_cast<float*>(p); p += ans_b;
   int64_t* d_prog = reinterpret_cast<int64_t*>(p);
 
+  // the copy stream must not overwrite staging that earlier, still unsynchronised work of `s` may read (a previous
+  // *_host_async call on this handle): everything enqueued on `s` so far precedes the first upload
+  B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[0], s));
+  B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[0], 0));
   int it = 0;
   for (int b0 = 0; b0 < B; b0 += chunk, ++it) {
     const int nb = std::min(chunk, B - b0);
@@ -1824,6 +1814,125 @@ B200VQA_API int b200vqa_fa_run_chain_indexed(b200vqa_handle* h, const void* img_
                            cache, h_active, opt_logits, opt_forced, stream);
 }
 
+// Host buffers in, host cache out: the reference's driver loop does one H2D and one D2H PER PROGRAM STEP
+// (FA:193-206 -> 109-121); here a sub-batch of questions is uploaded once (double-buffered, projected as it lands),
+// executed longest-program-first with the cache resident in HBM, and its cache rows are downloaded once - while the
+// next sub-batch uploads.
+B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
+                                          const int32_t* h_deps, const int32_t* h_n_steps, int B, int S, int start_token,
+                                          int max_len, int32_t* h_cache, int chunk, void* stream) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
+  B200VQA_REQUIRE(B >= 0 && S >= 0, "negative batch or step count");
+  if (B == 0 || S == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(h_img && h_func && h_deps && h_n_steps && h_cache, "a required buffer is NULL");
+  B200VQA_REQUIRE(max_len >= 2 && 1 + 2 * max_len <= 60, "max_len %d out of range (2..29)", max_len);
+  RC_OK(set_device(h));
+  const auto& d = h->d;
+  if (chunk <= 0) chunk = 2048;
+  chunk = std::min({chunk, B, default_cap(h)});
+  const int ichunk = std::min(chunk, 256);  // images per upload: 256 x 803 KB = 205 MB of staging
+  RC_OK(ensure_workspace(h, chunk, std::max(max_len - 1, 20)));  // 20: what b200vqa_fa_project_images asks for
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->copy_stream) {
+    B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t ingest = h->copy_stream;  // upload + image projection of sub-batch k+1 run here while k executes on `s`
+  auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
+  const size_t per_img = size_t(d.n_img_tokens) * d.img_feat_dim;
+  const size_t img_b = up(size_t(ichunk) * per_img * sizeof(float));
+  const size_t tok_b = up(size_t(chunk) * d.n_img_tokens * kD * sizeof(__nv_bfloat16));
+  const size_t func_b = up(size_t(chunk) * S * sizeof(int32_t));
+  const size_t deps_b = up(size_t(chunk) * S * 2 * sizeof(int32_t));
+  const size_t ns_b = up(size_t(chunk) * sizeof(int32_t));
+  const size_t cache_b = up(size_t(chunk) * S * max_len * sizeof(int32_t));
+  // image tokens, program tables and caches are double-buffered: sub-batch k+1 is prepared while k still runs
+  const size_t need = img_b + 2 * (tok_b + func_b + deps_b + 2 * ns_b + 2 * cache_b);
+  if (h->stage_bytes < need) {
+    if (h->stage) {
+      B200VQA_CUDA_OK(cudaDeviceSynchronize());
+      B200VQA_CUDA_OK(cudaFree(h->stage));
+      h->stage = nullptr;
+      h->stage_bytes = 0;
+      h->tmaps.clear();
+    }
+    B200VQA_CUDA_OK(cudaMalloc(&h->stage, need));
+    h->stage_bytes = need;
+  }
+  uint8_t* p = h->stage;
+  float* d_img = reinterpret_cast<float*>(p); p += img_b;
+  __nv_bfloat16* d_tok[2];
+  int32_t *d_func[2], *d_deps[2], *d_ns[2], *d_order[2], *d_cache_sorted[2], *d_cache[2];
+  for (int i = 0; i < 2; ++i) {
+    d_tok[i] = reinterpret_cast<__nv_bfloat16*>(p); p += tok_b;
+    d_func[i] = reinterpret_cast<int32_t*>(p); p += func_b;
+    d_deps[i] = reinterpret_cast<int32_t*>(p); p += deps_b;
+    d_ns[i] = reinterpret_cast<int32_t*>(p); p += ns_b;
+    d_order[i] = reinterpret_cast<int32_t*>(p); p += ns_b;
+    d_cache_sorted[i] = reinterpret_cast<int32_t*>(p); p += cache_b;
+    d_cache[i] = reinterpret_cast<int32_t*>(p); p += cache_b;
+  }
+  // staging may still be read by earlier unsynchronised work of `s`
+  B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[0], s));
+  B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[0], 0));
+
+  std::vector<int32_t> order, func_s, deps_s, ns_s, active(S);
+  int sub = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++sub) {
+    const int nb = std::min(chunk, B - b0);
+    const int par = sub & 1;
+    // ---- ingest stream: features in caller order, projected as they land (image_proj + PE once per question)
+    if (sub >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));  // chain sub-2 has released d_tok[par]
+    for (int i0 = 0; i0 < nb; i0 += ichunk) {
+      const int ni = std::min(ichunk, nb - i0);
+      B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, h_img + (size_t(b0) + i0) * per_img, size_t(ni) * per_img * sizeof(float),
+                                      cudaMemcpyHostToDevice, ingest));
+      RC_OK(b200vqa_fa_project_images(h, d_img, ni, d_tok[par] + size_t(i0) * d.n_img_tokens * kD, ingest));
+    }
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[par], ingest));
+    // ---- host: longest program first (stable), so that finished questions drop out of the later steps
+    order.resize(nb);
+    for (int i = 0; i < nb; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return h_n_steps[b0 + a] > h_n_steps[b0 + b]; });
+    func_s.resize(size_t(nb) * S);
+    deps_s.resize(size_t(nb) * S * 2);
+    ns_s.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+      const size_t src = size_t(b0) + order[i];
+      std::memcpy(&func_s[size_t(i) * S], h_func + src * S, size_t(S) * sizeof(int32_t));
+      std::memcpy(&deps_s[size_t(i) * S * 2], h_deps + src * S * 2, size_t(S) * 2 * sizeof(int32_t));
+      ns_s[i] = h_n_steps[src];
+    }
+    for (int i = 0; i < S; ++i) {
+      int a = 0;
+      while (a < nb && ns_s[a] > i) ++a;
+      active[i] = a;
+    }
+    // ---- compute stream (pageable sources: these small copies are staged before the call returns)
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_func[par], func_s.data(), func_s.size() * 4, cudaMemcpyHostToDevice, s));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_deps[par], deps_s.data(), deps_s.size() * 4, cudaMemcpyHostToDevice, s));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_ns[par], ns_s.data(), ns_s.size() * 4, cudaMemcpyHostToDevice, s));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_order[par], order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
+    B200VQA_CUDA_OK(cudaMemsetAsync(d_cache_sorted[par], 0xff, size_t(nb) * S * max_len * sizeof(int32_t), s));
+    B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[par], 0));
+    // question i of the sorted batch uses the image tokens of question order[i]
+    RC_OK(fa_run_chain_impl(h, d_tok[par], d_order[par], nb, d_func[par], d_deps[par], d_ns[par], nb, S, start_token,
+                            max_len, d_cache_sorted[par], active.data(), nullptr, nullptr, s));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[par], s));
+    h->cur_tag = kTagMisc;
+    LAUNCH_OK(h, launch_scatter_rows_i32(d_cache_sorted[par], d_order[par], nb, S * max_len, d_cache[par], s));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(h_cache + size_t(b0) * S * max_len, d_cache[par],
+                                    size_t(nb) * S * max_len * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  return B200VQA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ test hooks
 B200VQA_API int b200vqa_dbg_gemm(const b200vqa_dbg_gemm_args* a, void* stream) {
   B200VQA_REQUIRE(a != nullptr, "args is NULL");
@@ -1929,20 +2038,10 @@ B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const i
   mp.lens = lens;
   mp.const_len = const_len;
   mp.out = static_cast<__nv_bfloat16*>(out);
-  CUtensorMap tm, tq;
-  mp.tc_persistent = impl == 1;
-  mp.dbg = stamps;
-  if (impl >= 1) {
-    RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, 128));
-    RC_OK(make_tmap_2d(&tq, qp, TmapType::kBF16, uint64_t(B) * nhead, kD, kD, uint32_t(nhead)));
-    if (impl == 3)
-      B200VQA_CUDA_OK(launch_mem_attn_ring_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
-    else
-      B200VQA_CUDA_OK(launch_mem_attn_tc(tm, tq, mp, static_cast<cudaStream_t>(stream)));
-  } else {
-    RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows));
-    B200VQA_CUDA_OK(launch_mem_attn(tm, mp, static_cast<cudaStream_t>(stream)));
-  }
+  B200VQA_REQUIRE(impl == 0 && stamps == nullptr, "only the warp-MMA kernel (impl 0) exists");
+  CUtensorMap tm;
+  RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows));
+  B200VQA_CUDA_OK(launch_mem_attn(tm, mp, static_cast<cudaStream_t>(stream)));
   return B200VQA_OK;
 }
 

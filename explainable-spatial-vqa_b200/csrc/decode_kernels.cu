@@ -502,497 +502,6 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Absorbed cross-attention on tcgen05 (same algorithm and MemAttnParams as above; the warp-MMA form is bound by the
-// legacy HMMA pipe at ~1070 cycles per 32 rows per SM).  A cluster of two CTAs serves one question, one 128-row half of
-// the memory each (TMA, 4 swizzled 64-channel blocks = 64 KB; three CTAs per SM keep ~190 KB of loads in flight):
-//   scores  S[j, h]  = sum_d M[j, d] q'[h, d]   UMMA M = 128 memory rows (K-major A = the tile), N = 16 (heads padded;
-//                                               rows >= NH of the B operand are never written: garbage there only
-//                                               reaches accumulator columns nobody reads), K = 256: 16 instructions
-//   softmax thread j owns row j (= TMEM lane): per-head max / sum over the 128 rows through warp shuffles + one
-//           4-warp exchange; P[h, j] = exp2(S - max_tile) as bf16 into a K-major swizzled B operand
-//   values  U^T[d, h] = sum_j M[j, d] P[h, j]   the same tile as the MN-major A operand (channels on the 128 accumulator
-//                                               lanes, two halves), N = 16, K = 128 rows: 2 x 8 instructions
-//   combine the two CTAs hold (max_i, sum_i, U_i) of their halves relative to their own maxima; each sends the other
-//           CTA's 128 channels and its statistics through distributed shared memory, one cluster barrier, and writes
-//           u[b, h, 128 rank + t] = (w_0 U_0 + w_1 U_1) / (w_0 l_0 + w_1 l_1), w_i = exp2(max_i - max).
-// Rows past the sequence length are read as they lie in the buffer (finite) and get weight exactly 0; a half with no
-// valid row (len <= 128) loads nothing and contributes (max -inf, sum 0, U 0).
-// ------------------------------------------------------------------------------------------------
-constexpr int kMtRows = 128;
-constexpr int kMtThreads = 160;                  // warps 0-3: softmax / combine (TMEM lane quarter = warp), warp 4: TMA + MMA issue
-constexpr int kMtBlockBytes = kMtRows * 128;     // one 64-channel column block of the tile
-constexpr int kMtTileBytes = 4 * kMtBlockBytes;
-constexpr int kMtOffQ = kMtTileBytes;            // 4 x 1 KB: heads 0..7 of the query operand per 64-channel block ...
-constexpr int kMtQSbo = 4096;                    // ... "heads 8..15" alias whatever lies 4 KB further (never read back)
-constexpr int kMtOffP = kMtOffQ + 4096;          // 2 x 1 KB: heads 0..7 of P per 64-row block
-constexpr int kMtPSbo = 2048;
-constexpr int kMtOffRecv = kMtOffP + 2048;       // [128] float4: the peer's partial product for this CTA's channels, odd questions;
-                                                 // even questions: the unused head rows 4..7 of the query blocks
-constexpr int kMtOffMisc = kMtOffRecv + 2048;    // statistics, mbarriers, TMEM slot
-constexpr int kMtSmem = kMtOffMisc + 512;        // (the aliased operand rows reach kMtOffQ + 3 KB + 4 KB + 1 KB)
-constexpr int kMtCtasPerSm = 3;
-static_assert(kMtOffQ + 3 * 1024 + kMtQSbo + 1024 <= kMtSmem && kMtOffP + 1024 + kMtPSbo + 1024 <= kMtSmem, "aliases");
-
-__device__ __forceinline__ long long mt_clock() { return clock64(); }
-__device__ __forceinline__ long long mt_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return (long long)t;
-}
-
-template <int NH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMtThreads, kMtCtasPerSm)
-mem_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_mem, const __grid_constant__ CUtensorMap tm_q,
-                   const MemAttnParams p) {
-  static_assert(NH == 2 || NH == 4, "heads");
-  extern __shared__ __align__(1024) uint8_t mt_smem[];
-  const uint32_t sbase = smem_u32(mt_smem);
-  if ((sbase & 1023u) != 0) __trap();
-  float* s_wmax = reinterpret_cast<float*>(mt_smem + kMtOffMisc);  // [warp][4]
-  float* s_wsum = s_wmax + 16;                                     // [warp][4]
-  float* s_peer = s_wsum + 16;                                     // [parity][0..3 max, 4..7 sum] of the peer's half
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mt_smem + kMtOffMisc + 256);
-  uint64_t* bar_full = bars + 0;  // [4] 64-channel block of the tile (+ of the queries) landed
-  uint64_t* bar_s = bars + 4;     // score accumulator complete
-  uint64_t* bar_p = bars + 5;     // P written (128 arrivals)
-  uint64_t* bar_u = bars + 6;     // value accumulators complete: tile, queries and P are free again
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // which 128-row half of the memory
-  const int n_clusters = gridDim.x >> 1;
-
-  if (threadIdx.x == 128) {
-    tma_prefetch_desc(&tm_mem);
-    tma_prefetch_desc(&tm_q);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_full[i], 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_u, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc<64>(tmem_slot);
-  pdl_launch_dependents();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  cluster_arrive_release();  // generation 0: this CTA's shared memory is live (the peer waits before its remote stores)
-  const uint32_t tmem = *tmem_slot;
-  pdl_wait();
-
-  // rows of this CTA's half of question q that take part (<= 0: none; the half then contributes max -inf, sum 0, U 0)
-  auto valid_of = [&](int q) {
-    int len = p.lens ? p.lens[q] : p.const_len;
-    len = len > kLP ? kLP : (len < 1 ? 1 : len);
-    return min(kMtRows, len - int(rank) * kMtRows);
-  };
-  long long* dbg = p.dbg;
-  auto stamp = [&](int q, int k, long long v) {
-    if (dbg) dbg[(size_t(q) * 2 + rank) * 16 + k] = v;
-  };
-
-  if (warp == 4) {
-    // ---- control warp: one thread issues the loads and the MMAs; the single 64 KB stage is refilled for the next
-    // question as soon as the value MMAs of the current one have retired, so the combine step overlaps the load
-    auto issue_loads = [&](int q) {
-      const int row = q * int(p.rows_per_q) + int(rank) * kMtRows;
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        mbar_expect_tx(&bar_full[cb], kMtBlockBytes + NH * 128);
-        tma_load_2d_u32(&tm_q, &bar_full[cb], sbase + kMtOffQ + cb * 1024, cb * 64, q * NH);
-        tma_load_2d_u32(&tm_mem, &bar_full[cb], sbase + cb * kMtBlockBytes, cb * 64, row);
-      }
-      stamp(q, 3, mt_clock());
-    };
-    int b = blockIdx.x >> 1;
-    int valid = valid_of(b);
-    if (lane == 0 && valid > 0) issue_loads(b);
-    uint32_t ph = 0;  // phase of the mbarriers: they complete once per question with valid rows
-    while (b < p.B) {
-      const int nb = b + n_clusters;
-      const int nvalid = nb < p.B ? valid_of(nb) : 0;
-      if (lane == 0) {
-        if (valid > 0) {
-          constexpr uint32_t idesc_s = make_idesc(kFmtBF16, 128, 16, 0, 0);
-#pragma unroll
-          for (int k = 0; k < kD / 16; ++k) {
-            if (k % 4 == 0) {
-              mbar_wait(&bar_full[k / 4], ph);
-              tc_fence_after_sync();
-            }
-            umma_bf16(tmem, make_smem_desc_sw128(sbase + (k / 4) * kMtBlockBytes + (k % 4) * 32, 16, 1024),
-                      make_smem_desc_sw128(sbase + kMtOffQ + (k / 4) * 1024 + (k % 4) * 32, 16, kMtQSbo), idesc_s,
-                      k != 0);
-          }
-          umma_commit(bar_s);
-          stamp(b, 4, mt_clock());
-          mbar_wait(bar_p, ph);
-          tc_fence_after_sync();
-          constexpr uint32_t idesc_v = make_idesc(kFmtBF16, 128, 16, 1, 0);
-#pragma unroll
-          for (int half = 0; half < 2; ++half)
-#pragma unroll
-            for (int k = 0; k < kMtRows / 16; ++k)
-              umma_bf16(tmem + 16 + half * 16,
-                        make_smem_desc_sw128(sbase + half * 2 * kMtBlockBytes + k * 2048, kMtBlockBytes, 1024),
-                        make_smem_desc_sw128(sbase + kMtOffP + (k / 4) * 1024 + (k % 4) * 32, 16, kMtPSbo), idesc_v,
-                        k != 0);
-          umma_commit(bar_u);
-          mbar_wait(bar_u, ph);  // the stage, the queries and P are free again
-        }
-        if (nvalid > 0) issue_loads(nb);
-      }
-      if (valid > 0) ph ^= 1u;
-      __syncwarp();
-      // every thread of the cluster arrives once per question (generation 0 = start-up); this warp waits only just
-      // before its next arrival, so it never stalls on the softmax warps' exchange
-      cluster_wait_acquire();
-      cluster_arrive_release();
-      b = nb;
-      valid = nvalid;
-    }
-    cluster_wait_acquire();
-  } else {
-    const int r = threadIdx.x;  // memory row of the half == TMEM lane; later: output channel 128 rank + r
-    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
-    const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
-    uint32_t ph = 0, it = 0;
-    cluster_wait_acquire();  // generation 0: the peer CTA has started, its shared memory may be written
-    for (int b = blockIdx.x >> 1; b < p.B; b += n_clusters, ++it) {
-      const int valid = valid_of(b);
-      if (r == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        stamp(b, 0, smid);
-        stamp(b, 1, mt_globaltimer());
-        stamp(b, 2, mt_clock());
-        stamp(b, 11, it);
-      }
-      float m_own[NH], l_own[NH], u_own[4] = {0.f, 0.f, 0.f, 0.f}, u_snd[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        m_own[h] = -INFINITY;
-        l_own[h] = 0.f;
-      }
-      if (valid > 0) {
-        mbar_wait(bar_s, ph);
-        __syncwarp();
-        tc_fence_after_sync();
-        if (r == 0) stamp(b, 5, mt_clock());
-        uint32_t sv[4];
-        tmem_ld4(tlane, sv);
-        tmem_ld_wait();
-        float v[NH];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          v[h] = r < valid ? __uint_as_float(sv[h]) * sl2 : -INFINITY;
-          const float wm = warp_max(v[h]);
-          if (lane == 0) s_wmax[warp * 4 + h] = wm;
-        }
-        named_bar_sync(1, 128);
-        uint8_t* prow = mt_smem + kMtOffP + (r >> 6) * 1024 + (r & 7) * 2;
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          // finite: row 0 of a half with valid rows is valid
-          m_own[h] = fmaxf(fmaxf(s_wmax[h], s_wmax[4 + h]), fmaxf(s_wmax[8 + h], s_wmax[12 + h]));
-          const __nv_bfloat16 pb = __float2bfloat16(exp2f(v[h] - m_own[h]));
-          *reinterpret_cast<__nv_bfloat16*>(prow + h * 128 + ((((r & 63) >> 3) ^ h) << 4)) = pb;
-          const float ws = warp_sum(__bfloat162float(pb));  // normalise by what the tensor core will actually sum
-          if (lane == 0) s_wsum[warp * 4 + h] = ws;
-        }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        mbar_arrive(bar_p);
-        if (r == 0) stamp(b, 6, mt_clock());
-        named_bar_sync(1, 128);
-#pragma unroll
-        for (int h = 0; h < NH; ++h) l_own[h] = (s_wsum[h] + s_wsum[4 + h]) + (s_wsum[8 + h] + s_wsum[12 + h]);
-        mbar_wait(bar_u, ph);
-        __syncwarp();
-        tc_fence_after_sync();
-        if (r == 0) stamp(b, 7, mt_clock());
-        uint32_t a[4], c[4];
-        tmem_ld4(tlane + 16 + rank * 16, a);
-        tmem_ld4(tlane + 16 + (rank ^ 1u) * 16, c);
-        tmem_ld_wait();
-        tc_fence_before_sync();  // the next question's MMAs overwrite these columns only after this thread's bar_p arrival
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          u_own[h] = __uint_as_float(a[h]);
-          u_snd[h] = __uint_as_float(c[h]);
-        }
-        ph ^= 1u;
-      }
-      // exchange buffers alternate with the question's parity: the peer's stores of question it + 2 follow its wait
-      // on generation it + 2, which needs this thread's arrival of question it + 1 - after the reads below
-      const uint32_t par = it & 1u;
-      const uint32_t recv_off = par ? kMtOffRecv + r * 16 : kMtOffQ + (r >> 5) * 1024 + 512 + (r & 31) * 16;
-      st_cluster_f32x4(cluster_map_shared(sbase + recv_off, rank ^ 1u), u_snd[0], u_snd[1], u_snd[2], u_snd[3]);
-      if (r < NH) {
-        const uint32_t peer_stats = cluster_map_shared(smem_u32(s_peer + par * 8), rank ^ 1u);
-        st_cluster_f32(peer_stats + r * 4, m_own[r]);
-        st_cluster_f32(peer_stats + 16 + r * 4, l_own[r]);
-      }
-      cluster_arrive_release();
-      cluster_wait_acquire();
-      if (r == 0) stamp(b, 8, mt_clock());
-      const float4 rc = *reinterpret_cast<const float4*>(mt_smem + recv_off);
-      const float u_rcv[4] = {rc.x, rc.y, rc.z, rc.w};
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const float mp = s_peer[par * 8 + h], lp = s_peer[par * 8 + 4 + h];
-        const float m = fmaxf(m_own[h], mp);
-        const float w0 = exp2f(m_own[h] - m), w1 = exp2f(mp - m);
-        const float o = (w0 * u_own[h] + w1 * u_rcv[h]) / (w0 * l_own[h] + w1 * lp);
-        p.out[(size_t(b) * NH + h) * kD + rank * kMtRows + r] = __float2bfloat16(o);
-      }
-      if (r == 0) {
-        stamp(b, 9, mt_clock());
-        stamp(b, 10, mt_globaltimer());
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc<64>(tmem);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same tcgen05 arithmetic as mem_attn_tc_kernel with ONE persistent CTA per SM that owns whole questions: the
-// 128-row halves stream through a ring of three 64 KB stages filled by a producer thread that runs ahead across
-// question boundaries (two stages are always loading while the third is being consumed), the MMA thread issues the
-// score MMAs of tile t + 1 before the value MMAs of tile t (score accumulators and P double-buffered by tile parity),
-// and the halves of a question are combined inside the CTA (value accumulators per (question parity, half of the
-// memory, half of the channels) in TMEM) - no cluster, no distributed shared memory.
-// ------------------------------------------------------------------------------------------------
-constexpr int kMrStages = 3;
-constexpr int kMrThreads = 192;  // warps 0-3 softmax / combine, warp 4 TMA producer, warp 5 MMA issue
-constexpr int kMrOffQ = kMrStages * kMtTileBytes;  // [2 question parities] 4 x 1 KB query blocks (heads 8..15 alias + 4 KB)
-constexpr int kMrOffP = kMrOffQ + 2 * 4096;        // [2 tile parities] 2 x 1 KB P blocks (heads 8..15 alias + 2 KB)
-constexpr int kMrOffMisc = kMrOffP + 2 * 2048;     // statistics, mbarriers, TMEM slot
-constexpr int kMrSmem = kMrOffMisc + 3072;         // the aliased rows of the last P buffer end at kMrOffP + 2048 + 4096
-static_assert(kMrOffQ + 4096 + 3 * 1024 + kMtQSbo + 1024 <= kMrSmem && kMrOffP + 2048 + 1024 + kMtPSbo + 1024 <= kMrSmem,
-              "aliases");
-
-struct MrTileIter {  // the tiles of this CTA in processing order; every role walks the same sequence
-  int q, i, n, g, qi, stride, B;
-  const int32_t* lens;
-  int const_len;
-  __device__ __forceinline__ int tiles_of(int qq) const {
-    int len = lens ? lens[qq] : const_len;
-    len = len > kLP ? kLP : (len < 1 ? 1 : len);
-    return (len + kMtRows - 1) / kMtRows;
-  }
-  __device__ __forceinline__ int len_of(int qq) const {
-    const int len = lens ? lens[qq] : const_len;
-    return len > kLP ? kLP : (len < 1 ? 1 : len);
-  }
-  __device__ __forceinline__ void init(const MemAttnParams& p) {
-    q = blockIdx.x; i = 0; g = 0; qi = 0; stride = gridDim.x; B = p.B; lens = p.lens; const_len = p.const_len;
-    n = q < B ? tiles_of(q) : 0;
-  }
-  __device__ __forceinline__ bool done() const { return q >= B; }
-  __device__ __forceinline__ void next() {
-    ++g;
-    if (++i == n) {
-      i = 0;
-      q += stride;
-      ++qi;
-      n = q < B ? tiles_of(q) : 0;
-    }
-  }
-};
-
-template <int NH>
-__global__ void __launch_bounds__(kMrThreads, 1)
-mem_attn_ring_tc_kernel(const __grid_constant__ CUtensorMap tm_mem, const __grid_constant__ CUtensorMap tm_q,
-                        const MemAttnParams p) {
-  static_assert(NH == 2 || NH == 4, "heads");
-  extern __shared__ __align__(1024) uint8_t mr_smem[];
-  const uint32_t sbase = smem_u32(mr_smem);
-  if ((sbase & 1023u) != 0) __trap();
-  float* s_wmax = reinterpret_cast<float*>(mr_smem + kMrOffMisc);  // [warp][4]
-  float* s_wsum = s_wmax + 16;                                     // [warp][4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mr_smem + kMrOffMisc + 256);
-  uint64_t* bar_full = bars + 0;    // [3] stage landed (+ the queries with a question's first tile)
-  uint64_t* bar_empty = bars + 3;   // [3] the value MMAs that read the stage have retired
-  uint64_t* bar_s = bars + 6;       // [2] score accumulator of tile parity complete
-  uint64_t* bar_p = bars + 8;       // [2] P of tile parity written (128 arrivals)
-  uint64_t* bar_u = bars + 10;      // [2] value accumulators of question parity complete
-  uint64_t* bar_ufree = bars + 12;  // [2] ... and read by the combine step (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 128) {
-    tma_prefetch_desc(&tm_mem);
-    tma_prefetch_desc(&tm_q);
-    for (int i = 0; i < kMrStages; ++i) {
-      mbar_init(&bar_full[i], 1);
-      mbar_init(&bar_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 128);
-      mbar_init(&bar_u[i], 1);
-      mbar_init(&bar_ufree[i], 128);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  pdl_launch_dependents();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  pdl_wait();
-  MrTileIter t;
-  t.init(p);
-  // TMEM columns: scores [tile parity] at 16 * parity; values [question parity][half of the memory][half of the channels]
-  auto u_col = [](int qpar, int i, int half) { return uint32_t(32 + ((qpar * 2 + i) * 2 + half) * 16); };
-
-  if (warp == 4) {
-    if (lane == 0) {
-      for (; !t.done(); t.next()) {
-        const int st = t.g % kMrStages;
-        mbar_wait(&bar_empty[st], ((t.g / kMrStages) & 1) ^ 1);  // passes at once on a fresh barrier
-        mbar_expect_tx(&bar_full[st], kMtTileBytes + (t.i == 0 ? 4 * NH * 128 : 0));
-        if (t.i == 0) {
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb)
-            tma_load_2d_u32(&tm_q, &bar_full[st], sbase + kMrOffQ + (t.qi & 1) * 4096 + cb * 1024, cb * 64, t.q * NH);
-        }
-        const int row = t.q * int(p.rows_per_q) + t.i * kMtRows;
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb)
-          tma_load_2d_u32(&tm_mem, &bar_full[st], sbase + st * kMtTileBytes + cb * kMtBlockBytes, cb * 64, row);
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(kFmtBF16, 128, 16, 0, 0);
-      constexpr uint32_t idesc_v = make_idesc(kFmtBF16, 128, 16, 1, 0);
-      auto issue_scores = [&](const MrTileIter& x) {
-        const int st = x.g % kMrStages;
-        mbar_wait(&bar_full[st], (x.g / kMrStages) & 1);
-        tc_fence_after_sync();
-        const uint32_t tile = sbase + st * kMtTileBytes, qb = sbase + kMrOffQ + (x.qi & 1) * 4096;
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_bf16(tmem + (x.g & 1) * 16, make_smem_desc_sw128(tile + (k / 4) * kMtBlockBytes + (k % 4) * 32, 16, 1024),
-                    make_smem_desc_sw128(qb + (k / 4) * 1024 + (k % 4) * 32, 16, kMtQSbo), idesc_s, k != 0);
-        umma_commit(&bar_s[x.g & 1]);
-      };
-      if (!t.done()) issue_scores(t);
-      while (!t.done()) {
-        MrTileIter nx = t;
-        nx.next();
-        if (!nx.done()) issue_scores(nx);  // S(t + 1) runs under the softmax of tile t
-        const int st = t.g % kMrStages, qpar = t.qi & 1;
-        mbar_wait(&bar_p[t.g & 1], (t.g >> 1) & 1);
-        if (t.i == 0 && t.qi >= 2) mbar_wait(&bar_ufree[qpar], ((t.qi >> 1) - 1) & 1);  // accumulators of question qi - 2 read
-        tc_fence_after_sync();
-        const uint32_t tile = sbase + st * kMtTileBytes, pb = sbase + kMrOffP + (t.g & 1) * 2048;
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-          for (int k = 0; k < kMtRows / 16; ++k)
-            umma_bf16(tmem + u_col(qpar, t.i, half),
-                      make_smem_desc_sw128(tile + half * 2 * kMtBlockBytes + k * 2048, kMtBlockBytes, 1024),
-                      make_smem_desc_sw128(pb + (k / 4) * 1024 + (k % 4) * 32, 16, kMtPSbo), idesc_v, k != 0);
-        umma_commit(&bar_empty[st]);
-        if (t.i == t.n - 1) umma_commit(&bar_u[qpar]);
-        t = nx;
-      }
-    }
-  } else {
-    const int r = threadIdx.x;  // memory row inside a tile == TMEM lane; in the combine step: channels r and 128 + r
-    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
-    const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
-    float m_t[2][NH], l_t[2][NH];  // per half of the memory: max and sum of exp2(S - max) of the current question
-    for (; !t.done(); t.next()) {
-      const int valid = min(kMtRows, t.len_of(t.q) - t.i * kMtRows);
-      const int sp = t.g & 1;
-      mbar_wait(&bar_s[sp], (t.g >> 1) & 1);  // also: the value MMAs of tile g - 2 (readers of this P buffer) have retired
-      __syncwarp();
-      tc_fence_after_sync();
-      uint32_t sv[4];
-      tmem_ld4(tlane + sp * 16, sv);
-      tmem_ld_wait();
-      float v[NH];
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        v[h] = r < valid ? __uint_as_float(sv[h]) * sl2 : -INFINITY;
-        const float wm = warp_max(v[h]);
-        if (lane == 0) s_wmax[warp * 4 + h] = wm;
-      }
-      named_bar_sync(1, 128);
-      uint8_t* prow = mr_smem + kMrOffP + sp * 2048 + (r >> 6) * 1024 + (r & 7) * 2;
-      float ps[NH];
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const float m = fmaxf(fmaxf(s_wmax[h], s_wmax[4 + h]), fmaxf(s_wmax[8 + h], s_wmax[12 + h]));  // finite: row 0 is valid
-        const __nv_bfloat16 pb = __float2bfloat16(exp2f(v[h] - m));
-        *reinterpret_cast<__nv_bfloat16*>(prow + h * 128 + ((((r & 63) >> 3) ^ h) << 4)) = pb;
-        ps[h] = __bfloat162float(pb);  // normalise by what the tensor core will actually sum
-        if (t.i == 0) m_t[0][h] = m; else m_t[1][h] = m;
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(&bar_p[sp]);
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const float ws = warp_sum(ps[h]);
-        if (lane == 0) s_wsum[warp * 4 + h] = ws;
-      }
-      named_bar_sync(1, 128);
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const float l = (s_wsum[h] + s_wsum[4 + h]) + (s_wsum[8 + h] + s_wsum[12 + h]);
-        if (t.i == 0) l_t[0][h] = l; else l_t[1][h] = l;
-      }
-      if (t.i == t.n - 1) {
-        // combine the halves of the question: u = (w_0 U_0 + w_1 U_1) / (w_0 l_0 + w_1 l_1), w_i = exp2(max_i - max)
-        const int qpar = t.qi & 1;
-        float w0[NH], w1[NH];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          const float m1 = t.n == 2 ? m_t[1][h] : -INFINITY, l1 = t.n == 2 ? l_t[1][h] : 0.f;
-          const float m = fmaxf(m_t[0][h], m1);
-          const float a = exp2f(m_t[0][h] - m), b = exp2f(m1 - m);
-          const float inv = 1.f / (a * l_t[0][h] + b * l1);
-          w0[h] = a * inv;
-          w1[h] = b * inv;
-        }
-        mbar_wait(&bar_u[qpar], (t.qi >> 1) & 1);
-        __syncwarp();
-        tc_fence_after_sync();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t a[4], b[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(tlane + u_col(qpar, 0, half), a);
-          if (t.n == 2) tmem_ld4(tlane + u_col(qpar, 1, half), b);
-          tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < NH; ++h)
-            p.out[(size_t(t.q) * NH + h) * kD + half * kMtRows + r] =
-                __float2bfloat16(w0[h] * __uint_as_float(a[h]) + (t.n == 2 ? w1[h] * __uint_as_float(b[h]) : 0.f));
-        }
-        tc_fence_before_sync();
-        mbar_arrive(&bar_ufree[qpar]);
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc<256>(tmem);
-  }
-}
-
 __global__ void publish_tokens_kernel(const PublishParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * p.n_cols) return;
@@ -1043,65 +552,6 @@ cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, c
     return launch_kernel(mem_attn_kernel<4>, dim3(grid), dim3(kMemWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
   if (p.nhead == 2)
     return launch_kernel(mem_attn_kernel<2>, dim3(grid), dim3(kMemWarps * 32), kMemAttnSmem, stream, p.pdl, tm_mem, p);
-  return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_mem_attn_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
-                               cudaStream_t stream) {
-  if (p.B <= 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-      const void* fn = i == 0 ? reinterpret_cast<const void*>(mem_attn_tc_kernel<4>)
-                              : reinterpret_cast<const void*>(mem_attn_tc_kernel<2>);
-      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMtSmem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
-  // one cluster of two CTAs per question; persistent (three CTAs per SM) when there are more questions than that
-  int clusters = p.B;
-  if (p.tc_persistent) clusters = std::min(p.B, kMtCtasPerSm * num_sms / 2);
-  if (p.nhead == 4)
-    return launch_kernel(mem_attn_tc_kernel<4>, dim3(2 * clusters), dim3(kMtThreads), kMtSmem, stream, p.pdl, tm_mem, tm_q, p);
-  if (p.nhead == 2)
-    return launch_kernel(mem_attn_tc_kernel<2>, dim3(2 * clusters), dim3(kMtThreads), kMtSmem, stream, p.pdl, tm_mem, tm_q, p);
-  return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_mem_attn_ring_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
-                                    cudaStream_t stream) {
-  if (p.B <= 0) return cudaSuccess;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(mem_attn_ring_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMrSmem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mem_attn_ring_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMrSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  const int grid = std::min(p.B, num_sms);  // persistent: one CTA per SM, questions blockIdx.x, + gridDim.x, ...
-  if (p.nhead == 4)
-    return launch_kernel(mem_attn_ring_tc_kernel<4>, dim3(grid), dim3(kMrThreads), kMrSmem, stream, p.pdl, tm_mem, tm_q, p);
-  if (p.nhead == 2)
-    return launch_kernel(mem_attn_ring_tc_kernel<2>, dim3(grid), dim3(kMrThreads), kMrSmem, stream, p.pdl, tm_mem, tm_q, p);
   return cudaErrorInvalidValue;
 }
 

@@ -237,18 +237,10 @@ struct MemAttnParams {
   const int32_t* lens = nullptr;     // [B] or null -> const_len
   int const_len = 0;
   __nv_bfloat16* out = nullptr;
-  bool tc_persistent = true;  // tcgen05 form: clusters loop over questions instead of one launch slot per question
-  long long* dbg = nullptr;   // tcgen05 form, optional [2 B][16] int64: per-(question, half) stage stamps (tools/)
 };
 constexpr int kMemAttnTileRows = 32;  // memory rows per shared-memory tile of the absorbed cross-attention
 // tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, kMemAttnTileRows}
 cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, cudaStream_t stream);
-// tcgen05 form: tm_mem with box {64 channels, 128 rows}; tm_q = qp as a 2D tensor [B * nhead, 256] bf16, box {64, nhead}
-cudaError_t launch_mem_attn_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
-                               cudaStream_t stream);
-// tcgen05 form with one persistent CTA per SM and a three-stage ring of 128-row tiles (same tensor maps)
-cudaError_t launch_mem_attn_ring_tc(const CUtensorMap& tm_mem, const CUtensorMap& tm_q, const MemAttnParams& p,
-                                    cudaStream_t stream);
 
 // Weight packing for the absorbed cross-attention: in_proj_weight [3d, d] / in_proj_bias [3d] fp32 ->
 //   w_qk [nhead*d, d] bf16, row h*d + i = sum_e W_k[h*dh+e][i] * W_q[h*dh+e][:]     b_qk [nhead*d] likewise with b_q
@@ -412,6 +404,10 @@ cudaError_t launch_tally(const TallyParams& p, cudaStream_t stream);
 // Image rows of each question's block copied from per-image tokens (several questions per image).
 cudaError_t launch_gather_image_rows(const __nv_bfloat16* img_tok, const int32_t* image_idx, int n_img, int n_img_tokens,
                                      int B, __nv_bfloat16* x, cudaStream_t stream);
+
+// dst[order[r]] = src[r] for rows of `width` int32 (results of a sorted batch back into the caller's order)
+cudaError_t launch_scatter_rows_i32(const int32_t* src, const int32_t* order, int n, int width, int32_t* dst,
+                                    cudaStream_t stream);
 
 cudaError_t launch_delay(long long cycles, cudaStream_t stream);
 

@@ -496,6 +496,22 @@ cudaError_t launch_answer_head(const __nv_bfloat16* memory, int B, const float* 
   return cudaGetLastError();
 }
 
+__global__ void scatter_rows_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ order, int n,
+                                        int width, int32_t* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * width) return;
+  const int r = int(i / width), c = int(i % width);
+  dst[(long long)order[r] * width + c] = src[i];
+}
+
+cudaError_t launch_scatter_rows_i32(const int32_t* src, const int32_t* order, int n, int width, int32_t* dst,
+                                    cudaStream_t stream) {
+  const long long total = (long long)n * width;
+  if (total <= 0) return cudaSuccess;
+  scatter_rows_i32_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(src, order, n, width, dst);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_programs_to_chain(const ProgToChainParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
   programs_to_chain_kernel<<<(p.B + 127) / 128, 128, 0, stream>>>(p);

@@ -266,9 +266,12 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
                    img_tokens, sort_by_steps, slot, image_idx=None):
     h = model._native(slot)
     dev = model.image_proj.weight.device
-    func = _dev(func.to(dev), "func", torch.int32)
-    deps = _dev(deps.to(dev), "deps", torch.int32)
-    n_steps = _dev(n_steps.to(dev), "n_steps", torch.int32)
+    # program lengths on the host size the per-step launches (finished questions drop out): taken from the caller's
+    # tensor when it already lives on the host - a device tensor costs one device->host read here
+    ns_host_in = n_steps.detach().to(torch.int32).numpy() if not n_steps.is_cuda else None
+    func = _dev(func.to(dev, non_blocking=True), "func", torch.int32)
+    deps = _dev(deps.to(dev, non_blocking=True), "deps", torch.int32)
+    n_steps = _dev(n_steps.to(dev, non_blocking=True), "n_steps", torch.int32)
     B, S = func.shape
     if tuple(deps.shape) != (B, S, MAX_DEPS) or tuple(n_steps.shape) != (B,):
         raise ValueError("deps must be (B,S,2) and n_steps (B,)")
@@ -286,7 +289,11 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
     order = None
     active = None
     if sort_by_steps and B > 1:
-        order = torch.argsort(n_steps, descending=True, stable=True)
+        if ns_host_in is not None:
+            order_host = np.argsort(-ns_host_in.astype(np.int64), kind="stable")
+            order = torch.from_numpy(order_host).to(dev, non_blocking=True)
+        else:
+            order = torch.argsort(n_steps, descending=True, stable=True)
         func, deps, n_steps = func[order].contiguous(), deps[order].contiguous(), n_steps[order].contiguous()
         if image_idx is not None:
             image_idx = image_idx[order].contiguous()     # the tokens themselves stay where they are
@@ -294,7 +301,7 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
             img_tokens = img_tokens[order].contiguous()
         if forced is not None:
             forced = forced.to(dev)[order]
-        ns_host = n_steps.cpu().numpy()
+        ns_host = ns_host_in[order_host] if ns_host_in is not None else n_steps.cpu().numpy()
         active = np.ascontiguousarray([(ns_host > i).sum() for i in range(S)], dtype=np.int32)
     fz = None if forced is None else _dev(forced.to(dev), "forced", torch.int64)
     cache = torch.full((B, S, max_infer_len), -1, dtype=torch.int32, device=dev)
@@ -320,6 +327,35 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
         if logits is not None:
             logits = logits[inv]
     return (cache, logits) if want_logits else cache
+
+
+@torch.no_grad()
+def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, start_token=0, max_infer_len=20,
+                             chunk=2048):
+    """`run_inference_chain_batched` with HOST tensors in and out - the library call that replaces the reference's
+    driver loop (FA:193-206) with its per-step uploads and downloads (FA:109-121): image_features_cpu (B,1024,14,14) f32
+    (pinned for full PCIe speed), func (B,S), deps (B,S,2), n_steps (B,) on the host -> cache (B,S,max_infer_len) i32
+    in pinned host memory.  Features are uploaded and projected in sub-batches of `chunk` questions while the previous
+    sub-batch executes.  This is what bench.py times as `e2e` for the FA workloads."""
+    h = model._native(0)
+    img = image_features_cpu.to(torch.float32).contiguous()
+    f = func.to(torch.int32).contiguous()
+    d = deps.to(torch.int32).contiguous()
+    n = n_steps.to(torch.int32).contiguous()
+    if img.is_cuda or f.is_cuda or d.is_cuda or n.is_cuda:
+        raise ValueError("run_inference_chain_host takes CPU tensors; use run_inference_chain_batched for device tensors")
+    B, S = f.shape
+    if tuple(d.shape) != (B, S, MAX_DEPS) or tuple(n.shape) != (B,) or img.shape[0] != B:
+        raise ValueError("expected image_features (B,1024,14,14), func (B,S), deps (B,S,2), n_steps (B,)")
+    if img[0].numel() != model.image_proj.in_features * model.max_img_tokens:
+        raise ValueError(f"image_features must hold {model.image_proj.in_features} x {model.max_img_tokens} values per question")
+    cache = torch.empty(B, S, max_infer_len, dtype=torch.int32).pin_memory()
+    dev = model.image_proj.weight.device
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().b200vqa_fa_run_chain_host(h.raw, nat.ptr(img), nat.ptr(f), nat.ptr(d), nat.ptr(n), B, S,
+                                                      int(start_token), int(max_infer_len), nat.ptr(cache), int(chunk),
+                                                      nat.stream_ptr(dev)), "b200vqa_fa_run_chain_host")
+    return cache
 
 
 def run_inference_chain(model, image_features, final_chain, device, start_token, max_infer_len=20, rev_vocab=None):

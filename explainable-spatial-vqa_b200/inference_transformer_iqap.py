@@ -106,6 +106,7 @@ class VQAModel(nn.Module):
         self._nhead = 4
         self._pool = nat.HandlePool(self, self._build_desc)
         self._next_slot = 0
+        self._host_inflight = []  # host tensors of submit_host calls that have not been drained yet
 
     # ------------------------------------------------------------------ native handle
     def _build_desc(self):
@@ -315,7 +316,8 @@ class VQAModel(nn.Module):
     def submit(self, image_features, questions, depth=2):
         """Asynchronous forward of an independent batch on one of `depth` internal (handle, stream) slots, taken
         round-robin.  Returns (answer_output, programs) whose contents are valid only after `drain()` (or after the
-        caller's stream waited for the slot stream).  Inputs are consumed in the caller's stream order."""
+        caller's stream waited for the slot stream).  The slot stream first waits for the caller's stream, so inputs
+        produced there are complete before they are read."""
         slot = 1 + self._next_slot % depth
         self._next_slot += 1
         st = self._pool.stream(slot)
@@ -323,6 +325,14 @@ class VQAModel(nn.Module):
         st.wait_stream(torch.cuda.current_stream(st.device))
         with torch.cuda.stream(st):
             answer, programs, _, _ = self.forward_detailed(image_features, questions, slot=slot)
+        # inputs are read, and outputs written, on the slot stream: the caching allocator must not recycle their memory
+        # for the caller's stream before that work has finished
+        for t in (image_features, questions):
+            if t.is_cuda:
+                t.record_stream(st)
+        cur = torch.cuda.current_stream(st.device)
+        answer.record_stream(cur)
+        programs.record_stream(cur)
         return answer, programs
 
     @torch.no_grad()
@@ -342,6 +352,9 @@ class VQAModel(nn.Module):
             nat.check(nat.lib().b200vqa_iqap_forward_host_async(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
                                                                 nat.ptr(programs), int(chunk), C.c_void_p(st.cuda_stream)),
                       "b200vqa_iqap_forward_host_async")
+        # the asynchronous upload reads `img` / `q` (possibly temporaries made by .to() / .contiguous() above) and the
+        # download writes `answer` / `programs` until the slot stream has drained: keep all four alive until drain_host()
+        self._host_inflight.append((img, q, answer, programs))
         return answer, programs
 
     def drain(self):
@@ -352,6 +365,7 @@ class VQAModel(nn.Module):
         """Blocks the host until every `submit_host` has delivered its results."""
         for st in list(self._pool._streams.values()):
             st.synchronize()
+        self._host_inflight.clear()
 
 
 def get_data_info(questions_h5_path):

@@ -78,6 +78,30 @@ def gather_varlen(local: torch.Tensor, counts: Sequence[int], group=None) -> tor
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
+class JobGather:
+    """Results of a whole job - `steps` batches of `rows` result rows per rank - collected with ONE collective at the
+    end: every step copies its rows into a preallocated device buffer (no communication), `finish()` runs
+    a single all_gather_into_tensor into a preallocated [world, steps, rows, width] buffer."""
+
+    def __init__(self, steps: int, rows: int, width: int, dtype, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = torch.zeros(steps, rows, width, dtype=dtype, device=device)
+        self.full = torch.zeros(self.world, steps, rows, width, dtype=dtype, device=device) if self.world > 1 else None
+        self.steps = steps
+
+    def put(self, step: int, rows: torch.Tensor) -> None:
+        """Device-to-device copy on the CURRENT stream (the stream that produced `rows`)."""
+        self.local[step % self.steps].copy_(rows, non_blocking=True)
+
+    def finish(self) -> torch.Tensor:
+        """[world, steps, rows, width] on every rank; call after the producing streams have been joined."""
+        if self.world == 1:
+            return self.local[None]
+        dist.all_gather_into_tensor(self.full, self.local, group=self.group)
+        return self.full
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Max-reduction of a scalar timing across ranks (the bench's max-over-ranks rule)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -309,6 +309,17 @@ B200VQA_API int b200vqa_programs_to_chain(const int64_t* programs, int B, int T,
                                           const int32_t* func_map, int prog_vocab, int S, int32_t* func,
                                           int32_t* deps, int32_t* n_steps, void* stream);
 
+/* Replaces the reference's driver loop around run_inference_chain (FA:193-206) and its per-step host round trips
+ * (FA:109-121): HOST buffers in, HOST cache out.  h_img [B, 1024, 196] fp32 (the H5 layout, FA:201; pinned memory for
+ * full PCIe speed), h_func [B,S], h_deps [B,S,2], h_n_steps [B], h_cache [B,S,max_len] (rows of steps that are not
+ * executed are set to -1).  Questions are processed in sub-batches of `chunk` (<= 0: 2048): a sub-batch's features are
+ * uploaded and projected on an internal stream while the previous sub-batch executes, each sub-batch runs
+ * longest-program-first with the cache in HBM, and its cache is downloaded once.  Synchronises `stream` before
+ * returning. */
+B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
+                                          const int32_t* h_deps, const int32_t* h_n_steps, int B, int S, int start_token,
+                                          int max_len, int32_t* h_cache, int chunk, void* stream);
+
 /* b200vqa_fa_run_chain with image-level de-duplication ("dedup of img_tokens (image_idxs)"):
  * img_tokens_bf16 [n_images,196,256] holds every image once, image_idx [B] i32 (device) names the image of each
  * question (reference preprocess_questions/preprocess_questions.py:122).  Everything else as above. */
@@ -347,8 +358,7 @@ B200VQA_API int b200vqa_dbg_enc_attention(const void* qkv, const int32_t* lens, 
                               void* out, void* stream);
 /* absorbed decode cross-attention of one position: qp [B, nhead*256] bf16 (absorbed queries), memory [B*256, 256] bf16
  * -> out [B, nhead*256] bf16 (per-head attention-weighted memory); lens NULL -> const_len.
- * impl 0 = warp-MMA ring kernel, 1 = tcgen05 cluster kernel (persistent clusters), 2 = the same with one cluster per
- * question, 3 = tcgen05 ring kernel (one persistent CTA per SM); stamps: optional device int64 [2*B, 16] stage stamps of the tcgen05 kernel (tools/microbench_mem_attn.py) */
+ * impl must be 0 (the warp-MMA ring kernel); stamps must be NULL (kept for ABI stability). */
 B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const int32_t* lens, int const_len, int B, int nhead,
                          int impl, void* out, long long* stamps, void* stream);
 /* Test hook: copies one decode scratch buffer of the handle's workspace (sized by an earlier call) into the device

@@ -357,53 +357,5 @@ def iqap_tally(answer_output, generated_programs, gt_answers, gt_programs):
     return counts, preds
 
 
-def iqap_inputs(B, seed=1234, relu=True):
-    g = torch.Generator().manual_seed(seed)
-    img = torch.randn(B, 196, 1024, generator=g)
-    if relu:
-        img.relu_()  # conv4 features are post-ReLU
-    q = torch.zeros(B, 46, dtype=torch.long)
-    for b in range(B):
-        n = int(torch.randint(8, 47, (1,), generator=g))
-        q[b, 0] = 1
-        q[b, 1:n - 1] = torch.randint(4, 85, (n - 2,), generator=g)
-        q[b, n - 1] = 2
-    return img, q
-
-
-def fa_vocab(V=170):
-    """ids 0..26 are the digit strings "0".."26" (dependency pointers), the rest are opaque tokens."""
-    return {i: (str(i) if i < 27 else f"tok{i}") for i in range(V)}
-
-
-def fa_programs(B, seed=4321, max_steps=25, V=170):
-    """CLEVR-shaped DAGs: n_steps~U[2,25]; step 0 is a root; later steps: 15 % new root, 75 % unary on the
-    previous step, 10 % binary on two distinct earlier steps.  -> func (B,S) i32, deps (B,S,2) i32, n_steps (B,)"""
-    g = torch.Generator().manual_seed(seed)
-    func = torch.zeros(B, max_steps, dtype=torch.int32)
-    deps = torch.full((B, max_steps, 2), -1, dtype=torch.int32)
-    n_steps = torch.randint(2, max_steps + 1, (B,), generator=g, dtype=torch.int32)
-    for b in range(B):
-        for i in range(int(n_steps[b])):
-            func[b, i] = int(torch.randint(27, min(67, V), (1,), generator=g))
-            if i == 0:
-                continue
-            r = float(torch.rand(1, generator=g))
-            if r < 0.15:
-                continue
-            if r < 0.90 or i < 2:
-                deps[b, i, 0] = i - 1
-            else:
-                a = int(torch.randint(0, i - 1, (1,), generator=g))
-                deps[b, i, 0] = a
-                deps[b, i, 1] = i - 1
-    return func, deps, n_steps
-
-
-def chain_strings(func_row, deps_row, n):
-    """arrays -> the reference's `final_chain_of_thought` strings (dependency k is written as vocab id k)."""
-    out = []
-    for i in range(int(n)):
-        toks = [str(int(func_row[i]))] + [str(int(d)) for d in deps_row[i] if int(d) >= 0]
-        out.append(" ".join(toks))
-    return out
+# the seeded input generators live in the product package's neutral module (no model arithmetic there)
+from explainable_spatial_vqa_b200.synthetic import chain_strings, fa_programs, fa_vocab, iqap_inputs  # noqa: E402,F401

@@ -38,51 +38,6 @@ def generate(sd, questions, program_seq_len=27, start_token=1, forced=None):
     return torch.stack(toks, 1), torch.stack(logits, 1)
 
 
-def questions(B, seed=4242):
-    g = torch.Generator().manual_seed(seed)
-    q = torch.zeros(B, 46, dtype=torch.long)
-    for b in range(B):
-        n = int(torch.randint(8, 47, (1,), generator=g))
-        q[b, 0] = 1
-        q[b, 1:n - 1] = torch.randint(4, 85, (n - 2,), generator=g)
-        q[b, n - 1] = 2
-    return q
-
-
-# ---- synthetic CLEVR-shaped PREFIX programs in the generator's token space (for the glue tests and bench config 4)
-# token ids: 0 <NULL>, 1 <START>, 2 <END>, 3 <UNK> (all end a program), 4 = scene (no input), 5..9 binary functions
-# (equal_* / union / intersect / less_than / greater_than in the reference's get_num_inputs), 10..43 unary.
-def program_arity(prog_vocab=44):
-    a = torch.ones(prog_vocab, dtype=torch.int32)
-    a[:4] = -1
-    a[4] = 0
-    a[5:10] = 2
-    return a
-
-
-def program_func_map(prog_vocab=44):
-    return (27 + torch.arange(prog_vocab, dtype=torch.int32) % 40).to(torch.int32)  # FA function ids 27..66
-
-
-def prefix_programs(B, T=27, seed=777, max_nodes=25):
-    """-> (programs (B,T) i64 padded with <END> then <NULL>, node counts (B,))."""
-    g = torch.Generator().manual_seed(seed)
-    out = torch.zeros(B, T, dtype=torch.long)
-    counts = torch.zeros(B, dtype=torch.long)
-    for b in range(B):
-        budget = int(torch.randint(2, max_nodes + 1, (1,), generator=g))
-
-        def build(n):  # a subtree with exactly n nodes, prefix order
-            if n == 1:
-                return [4]
-            if n >= 3 and float(torch.rand(1, generator=g)) < 0.2:
-                left = int(torch.randint(1, n - 1, (1,), generator=g))
-                return [int(torch.randint(5, 10, (1,), generator=g))] + build(left) + build(n - 1 - left)
-            return [int(torch.randint(10, 44, (1,), generator=g))] + build(n - 1)
-
-        toks = build(budget)
-        counts[b] = len(toks)
-        out[b, : len(toks)] = torch.tensor(toks)
-        if len(toks) < T:
-            out[b, len(toks)] = 2
-    return out, counts
+# seeded input generators: the product package's neutral module (no model arithmetic there)
+from explainable_spatial_vqa_b200.synthetic import (lstm_questions as questions, prefix_programs, program_arity,  # noqa: E402,F401
+                                                    program_func_map)
