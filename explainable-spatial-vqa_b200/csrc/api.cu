@@ -1154,7 +1154,10 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_WARP_SELF_ATTN")) h->no_warp_self_attn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
-  if (const char* g = getenv("B200VQA_NO_PDL")) set_pdl_enabled(!(g[0] && g[0] != '0'));
+  {  // process-wide (the launch helper is shared by every handle): re-evaluated on every create
+    const char* g = getenv("B200VQA_NO_PDL");
+    set_pdl_enabled(!(g && g[0] && g[0] != '0'));
+  }
   if (const char* g = getenv("B200VQA_DECODE")) h->decode_persist = g[0] == 'p';
   if (const char* g = getenv("B200VQA_PERSIST_STAGGER_US")) h->persist_stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_PERSIST_DBG_STOP")) h->persist_dbg_stop = atoi(g);
