@@ -427,7 +427,8 @@ def run_ours(args):
         def step_e2e():
             if generator is None:
                 # the library's host-buffer entry: sub-batches uploaded + projected while the previous one executes
-                return fa.run_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk)
+                return fa.run_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk,
+                                                   parts=args.fa_host_parts)
             else:
                 generator(q_h.to(dev, non_blocking=True))
                 f, d, n = qp.programs_to_chain(p_h.to(dev, non_blocking=True), arity, fmap)
@@ -669,7 +670,8 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="independent batches in flight (1 = strictly serial steps)")
     ap.add_argument("--blocks", type=int, default=5, help="timed K-step blocks (the first gives `value`; the median is reported too)")
-    ap.add_argument("--fa-host-chunk", type=int, default=2048, help="questions per sub-batch of the FA host-buffer call")
+    ap.add_argument("--fa-host-chunk", type=int, default=1024, help="questions per sub-batch of the FA host-buffer call")
+    ap.add_argument("--fa-host-parts", type=int, default=4, help="concurrent parts (handle + stream slots) of the FA host-buffer call")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

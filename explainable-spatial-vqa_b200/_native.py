@@ -104,6 +104,8 @@ SIGNATURES = {
                                        _vp, _vp]),
     "b200vqa_fa_run_chain_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int,
                                             _vp]),
+    "b200vqa_fa_run_chain_host_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                                  C.c_int, _vp]),
     "b200vqa_fa_run_chain_indexed": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                                C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "b200vqa_lstm_create": (C.c_int, [C.POINTER(LstmDesc), C.c_int, C.POINTER(_vp)]),

@@ -143,6 +143,7 @@ struct b200vqa_handle {
                                // ONE K = nhead*256 LayerNorm GEMM instead of grouped value GEMM + out_proj LayerNorm GEMM
                                // (one launch fewer per layer and position, but four CTAs stream 4x the weight bytes:
                                // measured 4.57 vs 4.47 ms per step, so off by default)
+  bool enc_attn_whole_head = false;  // B200VQA_ENC_ATTN_WHOLE_HEAD=1: dh = 64 encoder attention with one CTA per (question, head)
   bool no_warp_self_attn = false;  // B200VQA_NO_WARP_SELF_ATTN=1: decoder self-attention with one CTA per question (A/B runs)
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
@@ -601,6 +602,7 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
       ap.const_len = const_len;
       ap.out = w.attn;
       ap.scale = 1.f / sqrtf(float(kD / d.nhead));
+      ap.one_cta_per_head = h->enc_attn_whole_head;
       LAUNCH_OK(h, launch_enc_attention(tq, tkv, w.qkv, ap, s));
     }
     h->cur_tag = kTagEncOutLn;
@@ -1151,6 +1153,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_US")) h->stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
+  if (const char* g = getenv("B200VQA_ENC_ATTN_WHOLE_HEAD")) h->enc_attn_whole_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_WARP_SELF_ATTN")) h->no_warp_self_attn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';
@@ -1821,9 +1824,9 @@ B200VQA_API int b200vqa_fa_run_chain_indexed(b200vqa_handle* h, const void* img_
 // (FA:193-206 -> 109-121); here a sub-batch of questions is uploaded once (double-buffered, projected as it lands),
 // executed longest-program-first with the cache resident in HBM, and its cache rows are downloaded once - while the
 // next sub-batch uploads.
-B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
-                                          const int32_t* h_deps, const int32_t* h_n_steps, int B, int S, int start_token,
-                                          int max_len, int32_t* h_cache, int chunk, void* stream) {
+static int fa_run_chain_host_impl(b200vqa_handle* h, const float* h_img, const int32_t* h_func, const int32_t* h_deps,
+                                  const int32_t* h_n_steps, int B, int S, int start_token, int max_len,
+                                  int32_t* h_cache, int chunk, void* stream, bool sync) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
   B200VQA_REQUIRE(B >= 0 && S >= 0, "negative batch or step count");
@@ -1883,13 +1886,28 @@ B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img,
   B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[0], s));
   B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[0], 0));
 
+  // B200VQA_FA_HOST_TRACE=1: GPU timeline of the call (ms since its start) printed to stderr after the final sync
+  const bool trace = getenv("B200VQA_FA_HOST_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tr_ev;
+  std::vector<const char*> tr_name;
+  auto mark = [&](const char* name, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tr_ev.push_back(e);
+    tr_name.push_back(name);
+  };
+  mark("start (compute stream)", s);
   std::vector<int32_t> order, func_s, deps_s, ns_s, active(S);
-  int sub = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++sub) {
+  // ingest stream: features of sub-batch k in caller order, projected as they land (image_proj + PE once per question).
+  // Enqueued one sub-batch AHEAD of the chains on the host as well: enqueueing a chain (hundreds of launches) can block
+  // the host on the launch queue, and the next upload must already be behind it
+  auto enqueue_ingest = [&](int k) -> int {
+    const int b0 = k * chunk;
     const int nb = std::min(chunk, B - b0);
-    const int par = sub & 1;
-    // ---- ingest stream: features in caller order, projected as they land (image_proj + PE once per question)
-    if (sub >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));  // chain sub-2 has released d_tok[par]
+    const int par = k & 1;
+    if (k >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));  // chain k-2 has released d_tok[par]
     for (int i0 = 0; i0 < nb; i0 += ichunk) {
       const int ni = std::min(ichunk, nb - i0);
       B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, h_img + (size_t(b0) + i0) * per_img, size_t(ni) * per_img * sizeof(float),
@@ -1897,6 +1915,18 @@ B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img,
       RC_OK(b200vqa_fa_project_images(h, d_img, ni, d_tok[par] + size_t(i0) * d.n_img_tokens * kD, ingest));
     }
     B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[par], ingest));
+    mark("ingest done", ingest);
+    return B200VQA_OK;
+  };
+  const int n_sub = (B + chunk - 1) / chunk;
+  RC_OK(enqueue_ingest(0));
+  int sub = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++sub) {
+    const int nb = std::min(chunk, B - b0);
+    const int par = sub & 1;
+    // sub-batch sub+1 may be uploaded as soon as chain sub-1 (which reads the same d_tok buffer) has been ENQUEUED: its
+    // release event exists by then
+    if (sub + 1 < n_sub) RC_OK(enqueue_ingest(sub + 1));
     // ---- host: longest program first (stable), so that finished questions drop out of the later steps
     order.resize(nb);
     for (int i = 0; i < nb; ++i) order[i] = i;
@@ -1923,6 +1953,7 @@ B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img,
     B200VQA_CUDA_OK(cudaMemcpyAsync(d_order[par], order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
     B200VQA_CUDA_OK(cudaMemsetAsync(d_cache_sorted[par], 0xff, size_t(nb) * S * max_len * sizeof(int32_t), s));
     B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[par], 0));
+    mark("chain start", s);
     // question i of the sorted batch uses the image tokens of question order[i]
     RC_OK(fa_run_chain_impl(h, d_tok[par], d_order[par], nb, d_func[par], d_deps[par], d_ns[par], nb, S, start_token,
                             max_len, d_cache_sorted[par], active.data(), nullptr, nullptr, s));
@@ -1931,9 +1962,34 @@ B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img,
     LAUNCH_OK(h, launch_scatter_rows_i32(d_cache_sorted[par], d_order[par], nb, S * max_len, d_cache[par], s));
     B200VQA_CUDA_OK(cudaMemcpyAsync(h_cache + size_t(b0) * S * max_len, d_cache[par],
                                     size_t(nb) * S * max_len * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    mark("chain + download done", s);
   }
-  B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  if (sync || trace) B200VQA_CUDA_OK(cudaStreamSynchronize(s));
+  if (trace) {
+    B200VQA_CUDA_OK(cudaStreamSynchronize(ingest));
+    for (size_t i = 0; i < tr_ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tr_ev[0], tr_ev[i]);
+      fprintf(stderr, "b200vqa fa_run_chain_host: %-28s %8.2f ms\n", tr_name[i], ms);
+      if (i) cudaEventDestroy(tr_ev[i]);
+    }
+    cudaEventDestroy(tr_ev[0]);
+  }
   return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
+                                          const int32_t* h_deps, const int32_t* h_n_steps, int B, int S, int start_token,
+                                          int max_len, int32_t* h_cache, int chunk, void* stream) {
+  return fa_run_chain_host_impl(h, h_img, h_func, h_deps, h_n_steps, B, S, start_token, max_len, h_cache, chunk, stream,
+                                true);
+}
+
+B200VQA_API int b200vqa_fa_run_chain_host_async(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
+                                                const int32_t* h_deps, const int32_t* h_n_steps, int B, int S,
+                                                int start_token, int max_len, int32_t* h_cache, int chunk, void* stream) {
+  return fa_run_chain_host_impl(h, h_img, h_func, h_deps, h_n_steps, B, S, start_token, max_len, h_cache, chunk, stream,
+                                false);
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks

@@ -242,6 +242,202 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// dh = 64 (IQAP, four heads): ONE query tile per CTA, TWO CTAs per SM.
+//
+// The kernel above owns its SM alone (160 KB, all 512 TMEM columns) and runs its phases one after the other - load, score
+// MMA, two softmax passes over TMEM, P.V MMA, store: 12.4 us per (question, head), tensor pipe 9.5 % busy.  Here a CTA
+// handles one 128-query tile: K | Q | spare (64 KB, overwritten by P once the score MMA has retired) + V (32 KB) = 96 KB,
+// and the output accumulator reuses the score accumulator's TMEM columns (dead once P is in shared memory), so a CTA
+// allocates 256 columns and two CTAs share an SM: one CTA's loads and MMAs run under the other's softmax.  K and V are
+// fetched once per tile (twice per head) - from L2, the packed q|k|v rows of a question were just written.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 64 + 256;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
+
+struct TileSmem {
+  static constexpr int kOffK = 0;                 // 256 keys x 64 x 2 B = 32 KB
+  static constexpr int kOffQ = 32768;             // 128 queries = 16 KB
+  static constexpr int kOffP = 0;                 // 128 x 256 x 2 B = 64 KB over K | Q | spare
+  static constexpr int kOffV = 65536;             // 32 KB
+  static constexpr int kOffXch = kOffV + 32768;   // [2 halves][128 rows] float2 (max, sum)
+  static constexpr int kOffBar = kOffXch + 2 * 128 * 8;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+__global__ void __launch_bounds__(kTileThreads, 2)
+enc_attention_tile_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                          const EncAttnParams p) {
+  using L = TileSmem;
+  constexpr int DH = 64;
+  const int t = blockIdx.x & 1;  // query tile
+  const int h = (blockIdx.x >> 1) % p.nhead;
+  const int b = (blockIdx.x >> 1) / p.nhead;
+  int len = p.lens ? p.lens[b] : p.const_len;
+  len = len < 1 ? 1 : (len > kKeysMax ? kKeysMax : len);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t row0 = size_t(b) * kLP;
+
+  if (t == 1 && len <= 128) {
+    // a tile that holds only padding rows: keep them finite (they are masked as keys downstream)
+    if (threadIdx.x < 256) {
+      const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (row0 + 128 + r) * kD + h * DH + half * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sK = smem + L::kOffK;
+  uint8_t* sQ = smem + L::kOffQ;
+  uint8_t* sP = smem + L::kOffP;
+  uint8_t* sV = smem + L::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;  // score accumulator complete (K and Q are no longer read)
+  uint64_t* bar_p = bars + 3;  // P written (256 arrivals)
+  uint64_t* bar_o = bars + 4;  // output accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int keys16 = (len + 15) & ~15;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_qk, 32768 + 16384);
+      tma_load_2d(&tm_kv, bar_qk, sK, kD + h * DH, int(row0));
+      tma_load_2d(&tm_q, bar_qk, sQ, h * DH, int(row0) + t * 128);
+      mbar_expect_tx(bar_v, 32768);
+      tma_load_2d(&tm_kv, bar_v, sV, 2 * kD + h * DH, int(row0));
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar_qk, 0);
+      tc_fence_after_sync();
+      const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)
+        umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                  make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k != 0);
+      umma_commit(bar_s);
+      // O = P V overwrites the score accumulator's first 64 columns: every thread has read its scores (twice) and
+      // published P before bar_p completes
+      const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
+      const int nkk = keys16 / 16;
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after_sync();
+      for (int kk = 0; kk < nkk; ++kk) {
+        const uint32_t pa = smem_u32(sP) + (kk / 4) * 16384 + (kk % 4) * 32;
+        const uint32_t va = smem_u32(sV) + kk * 2048;
+        umma_bf16(tmem_base, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 32768, 1024), idesc_o, kk != 0);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    const int hc = ((warp - 2) >> 2) & 1;   // which half of the row's 32-column chunks (alternating) this thread takes
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;      // query row inside the tile == TMEM lane
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    __nv_bfloat16* orow = p.out + (row0 + t * 128 + r) * kD + h * DH;
+    float2* xch = reinterpret_cast<float2*>(smem + L::kOffXch);  // [hc][r]
+    float2* mine = xch + hc * 128 + r;
+    const float2* theirs = xch + (hc ^ 1) * 128 + r;
+    const uint32_t pair_bar = 1 + quarter;  // the two warps sharing these 32 rows
+
+    mbar_wait(bar_s, 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    const int nchunks = (len + 31) / 32;
+    float mx = -INFINITY;
+    for (int c = hc; c < nchunks; c += 2) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    mine->x = mx;
+    named_bar_sync(pair_bar, 64);
+    mx = fmaxf(mx, theirs->x);
+    const float mxs = mx * sl2;
+    float sum = 0.f;
+    for (int c = hc; c < nchunks; c += 2) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = (c * 32 + j < len) ? exp2f(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
+        const float p1 = (c * 32 + j + 1 < len) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - mxs) : 0.f;
+        const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        const float2 pr = __bfloat1622float2(pb);
+        sum += pr.x + pr.y;  // normalise by what the tensor core will actually sum
+        o[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+      }
+      uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = (c & 1) * 4 + q;
+        *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+    mine->y = sum;
+    fence_proxy_async_smem();
+    tc_fence_before_sync();  // this thread's TMEM reads precede the output MMA that overwrites the columns
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    named_bar_sync(pair_bar, 64);  // partner's partial row sum is visible
+    const float inv = 1.f / (sum + theirs->y);
+    {
+      uint32_t v[32];
+      tmem_ld32(taddr + hc * 32, v);
+      tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        o[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+      uint4* dst = reinterpret_cast<uint4*>(orow + hc * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 template <int DH>
 cudaError_t launch_dh(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const EncAttnParams& p,
                       cudaStream_t stream) {
@@ -261,6 +457,12 @@ cudaError_t launch_enc_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_
                                  const EncAttnParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
   const int dh = kD / p.nhead;
+  if (dh == 64 && !p.one_cta_per_head) {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(enc_attention_tile_kernel), TileSmem::kBytes);
+    if (e != cudaSuccess) return e;
+    enc_attention_tile_kernel<<<p.B * p.nhead * 2, kTileThreads, TileSmem::kBytes, stream>>>(tm_q, tm_kv, p);
+    return cudaGetLastError();
+  }
   if (dh == 64) return launch_dh<64>(tm_q, tm_kv, p, stream);
   if (dh == 128) return launch_dh<128>(tm_q, tm_kv, p, stream);
   return cudaErrorInvalidValue;

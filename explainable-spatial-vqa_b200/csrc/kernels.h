@@ -118,6 +118,7 @@ struct EncAttnParams {
   __nv_bfloat16* out = nullptr;   // [B*kLP, kD]
   float scale = 0.125f;           // 1/sqrt(dh)
   int v_mode = 0;                 // 0: V as MN-major operand straight from TMA; 1: transposed in smem first
+  bool one_cta_per_head = false;  // dh = 64 only: the 160 KB both-tiles-per-CTA kernel instead of one tile per CTA (A/B runs)
 };
 cudaError_t launch_enc_attention(const CUtensorMap& tm_qkv, const CUtensorMap& tm_v, const __nv_bfloat16* qkv,
                                  const EncAttnParams& p, cudaStream_t stream);

@@ -14,6 +14,7 @@ host round trip between program steps (the reference does one H2D and one D2H pe
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import logging
 import re
@@ -331,13 +332,15 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
 
 @torch.no_grad()
 def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, start_token=0, max_infer_len=20,
-                             chunk=2048):
+                             chunk=2048, parts=2):
     """`run_inference_chain_batched` with HOST tensors in and out - the library call that replaces the reference's
     driver loop (FA:193-206) with its per-step uploads and downloads (FA:109-121): image_features_cpu (B,1024,14,14) f32
     (pinned for full PCIe speed), func (B,S), deps (B,S,2), n_steps (B,) on the host -> cache (B,S,max_infer_len) i32
-    in pinned host memory.  Features are uploaded and projected in sub-batches of `chunk` questions while the previous
-    sub-batch executes.  This is what bench.py times as `e2e` for the FA workloads."""
-    h = model._native(0)
+    in pinned host memory.  The batch is cut into `parts` contiguous ranges that run concurrently on separate
+    (handle, stream) slots - a chain is a dependent sequence of small kernels per program step, two of them overlap well
+    - and inside a part features are uploaded and projected in sub-batches of `chunk` questions while the previous
+    sub-batch executes.  Results do not depend on `chunk` / `parts` (questions never interact).  This is what bench.py
+    times as `e2e` for the FA workload."""
     img = image_features_cpu.to(torch.float32).contiguous()
     f = func.to(torch.int32).contiguous()
     d = deps.to(torch.int32).contiguous()
@@ -347,14 +350,30 @@ def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, sta
     B, S = f.shape
     if tuple(d.shape) != (B, S, MAX_DEPS) or tuple(n.shape) != (B,) or img.shape[0] != B:
         raise ValueError("expected image_features (B,1024,14,14), func (B,S), deps (B,S,2), n_steps (B,)")
-    if img[0].numel() != model.image_proj.in_features * model.max_img_tokens:
+    if B and img[0].numel() != model.image_proj.in_features * model.max_img_tokens:
         raise ValueError(f"image_features must hold {model.image_proj.in_features} x {model.max_img_tokens} values per question")
     cache = torch.empty(B, S, max_infer_len, dtype=torch.int32).pin_memory()
     dev = model.image_proj.weight.device
+    parts = max(1, min(int(parts), B // 256 if B >= 512 else 1))
     with torch.cuda.device(dev):
-        nat.check(nat.lib().b200vqa_fa_run_chain_host(h.raw, nat.ptr(img), nat.ptr(f), nat.ptr(d), nat.ptr(n), B, S,
-                                                      int(start_token), int(max_infer_len), nat.ptr(cache), int(chunk),
-                                                      nat.stream_ptr(dev)), "b200vqa_fa_run_chain_host")
+        if parts == 1:
+            h = model._native(0)
+            nat.check(nat.lib().b200vqa_fa_run_chain_host(h.raw, nat.ptr(img), nat.ptr(f), nat.ptr(d), nat.ptr(n), B, S,
+                                                          int(start_token), int(max_infer_len), nat.ptr(cache), int(chunk),
+                                                          nat.stream_ptr(dev)), "b200vqa_fa_run_chain_host")
+            return cache
+        streams = []
+        for i in range(parts):
+            lo, hi = B * i // parts, B * (i + 1) // parts
+            h = model._native(1 + i)
+            st = model._pool.stream(1 + i)
+            streams.append(st)
+            nat.check(nat.lib().b200vqa_fa_run_chain_host_async(
+                h.raw, nat.ptr(img[lo:hi]), nat.ptr(f[lo:hi]), nat.ptr(d[lo:hi]), nat.ptr(n[lo:hi]), hi - lo, S,
+                int(start_token), int(max_infer_len), nat.ptr(cache[lo:hi]), int(min(chunk, hi - lo)),
+                C.c_void_p(st.cuda_stream)), "b200vqa_fa_run_chain_host_async")
+        for st in streams:
+            st.synchronize()   # img / f / d / n / cache are referenced by this frame until every part has finished
     return cache
 
 

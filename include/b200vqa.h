@@ -319,6 +319,12 @@ B200VQA_API int b200vqa_programs_to_chain(const int64_t* programs, int B, int T,
 B200VQA_API int b200vqa_fa_run_chain_host(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
                                           const int32_t* h_deps, const int32_t* h_n_steps, int B, int S, int start_token,
                                           int max_len, int32_t* h_cache, int chunk, void* stream);
+/* Same without the final synchronisation: h_cache is valid (and the host inputs may be released) once `stream` has been
+ * synchronised by the caller.  Lets independent parts of a batch run on several handles / streams at once: a chain is a
+ * dependent sequence of small kernels per program step, so two of them overlap well. */
+B200VQA_API int b200vqa_fa_run_chain_host_async(b200vqa_handle* h, const float* h_img, const int32_t* h_func,
+                                                const int32_t* h_deps, const int32_t* h_n_steps, int B, int S,
+                                                int start_token, int max_len, int32_t* h_cache, int chunk, void* stream);
 
 /* b200vqa_fa_run_chain with image-level de-duplication ("dedup of img_tokens (image_idxs)"):
  * img_tokens_bf16 [n_images,196,256] holds every image once, image_idx [B] i32 (device) names the image of each

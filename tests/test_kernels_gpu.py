@@ -66,12 +66,15 @@ def test_gemm_matches_cuda_core_check_kernel():
     assert common.rel_err(out.float(), chk) < 6e-3
 
 
-def test_gemm_tf32_pe_remap_matches_image_projection_layout():
-    """image_proj epilogue: row (item, pos) of the GEMM lands at item*256 + 1 + pos with bias + pe[1+pos]."""
-    g = torch.Generator(device="cuda").manual_seed(9)
-    B, P, K, N = 5, 196, 1024, 256
-    A = torch.randn(B * P, K, device="cuda", generator=g).relu()
-    W = torch.randn(N, K, device="cuda", generator=g) / 32
+@pytest.mark.parametrize("B", [5, 1, 3, 7, 200])   # 8 / 2 / 5 / 11 / 307 m-tiles: even and odd counts (pair mode's phantom tile)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_pe_remap_matches_image_projection_layout(B, dtype):
+    """image_proj epilogue: row (item, pos) of the GEMM lands at item*256 + 1 + pos with bias + pe[1+pos].  The kernel
+    serves two m-tiles per pass over the weight (pair mode); fp32 features run as tf32, 16-bit features as bf16."""
+    g = torch.Generator(device="cuda").manual_seed(9 + B)
+    P, K, N = 196, 1024, 256
+    A = torch.randn(B * P, K, device="cuda", generator=g).relu().to(dtype)
+    W = (torch.randn(N, K, device="cuda", generator=g) / 32).to(dtype)
     bias = torch.randn(N, device="cuda", generator=g)
     pe = torch.randn(243, N, device="cuda", generator=g)
     out = dbg_gemm(A, W, bias, epilogue=3, rows_in=P, rows_out=256, row_off=1, pe=pe, pe_off=1, out_rows=B * 256)

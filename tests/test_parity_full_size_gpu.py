@@ -113,3 +113,10 @@ def test_fa_host_entry_equals_device_entry():
     assert torch.equal(fa.run_inference_chain_host(model, img.pin_memory(), func, deps, n_steps, 0, 20, chunk=4), want)
     with pytest.raises(ValueError):
         fa.run_inference_chain_host(model, img.cuda(), func, deps, n_steps)
+    # two concurrent parts on separate (handle, stream) slots, several sub-batches each
+    B = 600
+    func, deps, n_steps = orc.fa_programs(B, seed=18, max_steps=3)
+    img = torch.randn(B, 1024, 14, 14, generator=g).relu_()
+    want = fa.run_inference_chain_batched(model, img.cuda(), func, deps, n_steps, 0, 20).cpu()
+    got = fa.run_inference_chain_host(model, img.pin_memory(), func, deps, n_steps, 0, 20, chunk=128, parts=2)
+    assert torch.equal(got, want)
