@@ -667,8 +667,8 @@ def main():
     ap.add_argument("--workload", default="iqap", choices=["iqap", "fa", "e2e"])
     ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
     ap.add_argument("--e2e-chunk", type=int, default=1024)
-    ap.add_argument("--pipeline-depth", type=int, default=2,
-                    help="independent batches in flight (1 = strictly serial steps)")
+    ap.add_argument("--pipeline-depth", type=int, default=None,
+                    help="independent batches in flight (1 = strictly serial steps); default 2 (iqap) / 3 (fa, e2e)")
     ap.add_argument("--blocks", type=int, default=5, help="timed K-step blocks (the first gives `value`; the median is reported too)")
     ap.add_argument("--fa-host-chunk", type=int, default=1024, help="questions per sub-batch of the FA host-buffer call")
     ap.add_argument("--fa-host-parts", type=int, default=4, help="concurrent parts (handle + stream slots) of the FA host-buffer call")
@@ -677,7 +677,10 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 1024 if args.workload == "iqap" else 4096
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.pipeline_depth is None:
+        args.pipeline_depth = 2 if args.workload == "iqap" else 3
+    # every pipeline slot allocates its workspace and captures its graphs on first use: all of them warm up
+    args.warmup = max(args.warmup, 3, args.pipeline_depth) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -968,6 +968,11 @@ int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   B200VQA_CUDA_OK(cudaStreamIsCapturing(s, &cs));
   if (cs != cudaStreamCaptureStatusNone) return enqueue_decoder(h, B, memory, lens, const_len, io, s);
+  // The step-wise executor calls this with the per-step count of still-active questions, which differs from step to
+  // step and from batch to batch on a ragged data set: rounded up to a multiple of 128 rows (within the workspace) so
+  // that a handful of graphs serve every count.  The surplus rows are earlier steps' (finite) leftovers: they are
+  // decoded and never published.
+  if (h->d.kind == B200VQA_MODEL_FA && lens == h->ws.lens) B = std::min(h->ws.cap, (B + 127) / 128 * 128);
   GraphKey key{B, io.steps, io.start_token, const_len, static_cast<const void*>(memory), static_cast<const void*>(lens)};
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
