@@ -61,6 +61,46 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
+def _parse_cpulist(text: str) -> list[int]:
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pins this process (and therefore its first-touch pinned host allocations) to the CPUs of the NUMA node its GPU
+    hangs off, so that every rank's host->device copies read node-local memory instead of crossing the socket link.
+    Returns what was found / done; a box that reports no topology (numa_node -1, one node) is left alone."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["nodes"] = len(nodes)
+        if node < 0 or len(nodes) < 2:
+            return info
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except Exception as e:  # pragma: no cover - topology files differ between hosts; never fatal
+        info["error"] = repr(e)
+    return info
+
+
 def gather_varlen(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
     """All-gathers row blocks of different lengths (counts[r] rows from rank r) into one tensor ordered by
     rank - the single collective of the executor path (answers, programs or step caches)."""
@@ -98,7 +138,8 @@ class JobGather:
         """[world, steps, rows, width] on every rank; call after the producing streams have been joined."""
         if self.world == 1:
             return self.local[None]
-        dist.all_gather_into_tensor(self.full, self.local, group=self.group)
+        # concatenation form (output = the ranks' blocks along dim 0): accepted by NCCL and gloo alike
+        dist.all_gather_into_tensor(self.full.view(-1, *self.local.shape[1:]), self.local, group=self.group)
         return self.full
 
 

@@ -132,6 +132,15 @@ mine = full[lo:hi].clone()                       # this rank's "programs"
 counts = [sharding.shard_range(N, r, world)[1] - sharding.shard_range(N, r, world)[0] for r in range(world)]
 got = sharding.gather_varlen(mine, counts)
 assert torch.equal(got, full), (rank, got)
+# the job-level gather: every step's rows stay local, ONE collective at the end
+jg = sharding.JobGather(steps=3, rows=4, width=2, dtype=torch.int64, device="cpu")
+for st in range(3):
+    jg.put(st, torch.full((4, 2), 100 * rank + st, dtype=torch.int64))
+allr = jg.finish()
+assert tuple(allr.shape) == (world, 3, 4, 2)
+for r in range(world):
+    for st in range(3):
+        assert bool((allr[r, st] == 100 * r + st).all()), (rank, r, st)
 assert sharding.max_over_ranks(float(rank + 1)) == float(world)
 assert sharding.sum_over_ranks(1.0) == float(world)
 dist.barrier()
@@ -190,3 +199,10 @@ def test_oracle_tally_follows_reference_loop():
     counts, preds = orc.iqap_tally(logits, progs, gt_a, gt_p)
     assert preds == [1, 0, 2, 0]
     assert counts == [1, 1, 1, 1]
+
+
+def test_cpulist_parsing_and_numa_binding_is_harmless_without_a_gpu():
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding._parse_cpulist("") == []
+    info = sharding.bind_to_gpu_numa(0)   # no GPU here: reports the failure instead of raising
+    assert info["bound"] is False
