@@ -21,6 +21,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects the NVTX library
+
 #include "host_util.h"
 #include "kernels.h"
 
@@ -83,6 +85,18 @@ struct Workspace {
   __nv_bfloat16** kc_dev = nullptr;  // device copies of the kc / vc pointer tables (persistent decode kernel)
   __nv_bfloat16** vc_dev = nullptr;
   size_t drows = 0;                // decode rows (cap rounded up to 128)
+};
+
+// NVTX ranges around the phases of a call (encoder, decode, image projection, ...) when B200VQA_NVTX=1: they name the
+// spans of a profiler timeline; costs nothing when no tool is attached and is compiled to one branch otherwise.
+struct NvtxRange {
+  bool on;
+  NvtxRange(bool enabled, const char* name) : on(enabled) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
 };
 
 using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>;
@@ -148,6 +162,7 @@ struct b200vqa_handle {
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
+  bool nvtx = false;                  // B200VQA_NVTX=1
   int iqap_start_token = 1;           // Config.SPECIAL_TOKEN_ID (IQAP:24,205); b200vqa_set_start_token
   // persistent decode kernel (decode_persist.cu): all positions x layers in one launch
   bool decode_persist = false;        // B200VQA_DECODE=persist|chain
@@ -581,6 +596,7 @@ int gemm_res_ln(b200vqa_handle* h, const __nv_bfloat16* A, int M, int K, const _
 // ---------------------------------------------------------------------------------------------
 int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __nv_bfloat16** memory,
                 cudaStream_t s) {
+  NvtxRange nvtx_range(h->nvtx, "b200vqa encoder");
   Workspace& w = h->ws;
   const auto& d = h->d;
   const int M = B * kLP;
@@ -961,6 +977,7 @@ int enqueue_decoder_branched(b200vqa_handle* h, int B, const __nv_bfloat16* memo
 // CUDA graph on first use and replayed afterwards: ~20 launches per position collapse into one graph launch.
 int run_decoder(b200vqa_handle* h, int B, const __nv_bfloat16* memory, const int32_t* lens, int const_len,
                 const DecodeIO& io, cudaStream_t s) {
+  NvtxRange nvtx_range(h->nvtx, "b200vqa greedy decode");
   const bool plain = !io.logits && !io.forced && !io.start_tokens;
   // the persistent kernel is two launches (start embedding + decode): nothing for a graph to collapse
   if (!plain || h->profiling || !h->use_graphs || persist_eligible(h, io))
@@ -1166,6 +1183,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
     const char* g = getenv("B200VQA_NO_PDL");
     set_pdl_enabled(!(g && g[0] && g[0] != '0'));
   }
+  if (const char* g = getenv("B200VQA_NVTX")) h->nvtx = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_DECODE")) h->decode_persist = g[0] == 'p';
   if (const char* g = getenv("B200VQA_PERSIST_STAGGER_US")) h->persist_stagger_us = std::max(0, atoi(g));
   if (const char* g = getenv("B200VQA_PERSIST_DBG_STOP")) h->persist_dbg_stop = atoi(g);
