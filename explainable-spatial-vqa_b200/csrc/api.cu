@@ -158,6 +158,7 @@ struct b200vqa_handle {
                                // (one launch fewer per layer and position, but four CTAs stream 4x the weight bytes:
                                // measured 4.57 vs 4.47 ms per step, so off by default)
   bool enc_attn_whole_head = false;  // B200VQA_ENC_ATTN_WHOLE_HEAD=1: dh = 64 encoder attention with one CTA per (question, head)
+  bool no_fused_final_ln = false;  // B200VQA_NO_FUSED_FINAL_LN=1: nn.Transformer's final encoder norm as its own kernel (A/B runs)
   bool no_warp_self_attn = false;  // B200VQA_NO_WARP_SELF_ATTN=1: decoder self-attention with one CTA per question (A/B runs)
   bool no_fused_head = false;  // B200VQA_NO_FUSED_HEAD=1: vocabulary head as its own tf32 tensor-core GEMM even for vocabularies
                                // of up to 64 entries (A/B runs)
@@ -576,9 +577,12 @@ int gemm_bias(b200vqa_handle* h, bool relu, const __nv_bfloat16* A, int M, int K
 
 int gemm_res_ln(b200vqa_handle* h, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, const float* bias,
                 const __nv_bfloat16* residual, const float* gamma, const float* beta, __nv_bfloat16* out,
-                float* out_f32, cudaStream_t s, bool decode = false) {
+                float* out_f32, cudaStream_t s, bool decode = false, const float* gamma2 = nullptr,
+                const float* beta2 = nullptr) {
   GemmParams p;
   p.ln_cluster = decode;
+  p.gamma2 = gamma2;
+  p.beta2 = beta2;
   p.bias = bias;
   p.out = out;
   p.ldc = kD;
@@ -626,12 +630,16 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
     h->cur_tag = kTagEncFfn1;
     RC_OK(gemm_bias(h, true, w.x1, M, kD, L.w1, d.dim_ff, L.b1, w.hid, s));
     h->cur_tag = kTagEncFfn2Ln;
-    RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s));
+    // the last layer's norm2 also applies nn.Transformer's final encoder norm (FA:42) when there is one
+    const bool fuse_final = l == d.n_enc_layers - 1 && h->enc_fn_w && !h->no_fused_final_ln;
+    RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s, false,
+                      fuse_final ? h->enc_fn_w : nullptr, fuse_final ? h->enc_fn_b : nullptr));
     std::swap(in, out);
   }
   // `in` now holds the last layer's output
   h->cur_tag = kTagEncFinalLn;
-  if (h->enc_fn_w) LAUNCH_OK(h, launch_layernorm_rows(in, in, h->enc_fn_w, h->enc_fn_b, d.layer_norm_eps, M, s));
+  if (h->enc_fn_w && h->no_fused_final_ln)
+    LAUNCH_OK(h, launch_layernorm_rows(in, in, h->enc_fn_w, h->enc_fn_b, d.layer_norm_eps, M, s));
   *memory = in;
   return B200VQA_OK;
 }
@@ -1176,6 +1184,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_BRANCH_STAGGER_MOD")) h->stagger_mod = std::max(2, atoi(g));
   if (const char* g = getenv("B200VQA_ABSORB_OV")) h->absorb_ov = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_ENC_ATTN_WHOLE_HEAD")) h->enc_attn_whole_head = g[0] && g[0] != '0';
+  if (const char* g = getenv("B200VQA_NO_FUSED_FINAL_LN")) h->no_fused_final_ln = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_WARP_SELF_ATTN")) h->no_warp_self_attn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_HEAD")) h->no_fused_head = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_LN_CLUSTER")) h->no_ln_cluster = g[0] && g[0] != '0';

@@ -525,40 +525,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
         // row statistics over all BN columns: the kSplit warps of this quarter exchange partial sums (two-pass)
         const int xbase = (ew & 3) * 32 + lane;  // slot of warp (ew & 3) + 4*j is xchf[xbase + 128*j]
-        float s = 0.f;
+        float mean, rstd;
+        auto row_stats = [&]() {
+          float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMyChunks; ++i)
+          for (int i = 0; i < kMyChunks; ++i)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += v[i][j];
-        xchf[ew * 32 + lane] = s;
-        named_bar_sync(1 + quarter, kSplit * 32);
-        float tot = 0.f;
+            for (int j = 0; j < 32; ++j) s += v[i][j];
+          xchf[ew * 32 + lane] = s;
+          named_bar_sync(1 + quarter, kSplit * 32);
+          float tot = 0.f;
 #pragma unroll
-        for (int j = 0; j < kSplit; ++j) tot += xchf[xbase + 128 * j];
-        const float mean = tot * (1.f / BN);
-        float sq = 0.f;
+          for (int j = 0; j < kSplit; ++j) tot += xchf[xbase + 128 * j];
+          mean = tot * (1.f / BN);
+          float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMyChunks; ++i)
+          for (int i = 0; i < kMyChunks; ++i)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = v[i][j] - mean;
-            sq = fmaf(d, d, sq);
+            for (int j = 0; j < 32; ++j) {
+              const float d = v[i][j] - mean;
+              sq = fmaf(d, d, sq);
+            }
+          named_bar_sync(1 + quarter, kSplit * 32);  // every partner has read the sums before they are overwritten
+          xchf[ew * 32 + lane] = sq;
+          named_bar_sync(1 + quarter, kSplit * 32);
+          float tsq = 0.f;
+#pragma unroll
+          for (int j = 0; j < kSplit; ++j) tsq += xchf[xbase + 128 * j];
+          rstd = rsqrtf(tsq * (1.f / BN) + p.eps);
+          named_bar_sync(1 + quarter, kSplit * 32);  // ... and the squares before the next sums
+        };
+        row_stats();
+        const float* gamma = p.gamma;
+        const float* beta = p.beta;
+        if (p.gamma2) {
+          // a second LayerNorm on top (nn.Transformer's final encoder norm, FA:42): normalise in registers, then take the
+          // statistics of the result - one kernel and one 512-byte-per-row round trip through HBM fewer
+#pragma unroll
+          for (int i = 0; i < kMyChunks; ++i) {
+            const int c = half + kSplit * i;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = ldg4(gamma + c * 32 + j), t4 = ldg4(beta + c * 32 + j);
+              v[i][j] = (v[i][j] - mean) * rstd * g4.x + t4.x;
+              v[i][j + 1] = (v[i][j + 1] - mean) * rstd * g4.y + t4.y;
+              v[i][j + 2] = (v[i][j + 2] - mean) * rstd * g4.z + t4.z;
+              v[i][j + 3] = (v[i][j + 3] - mean) * rstd * g4.w + t4.w;
+            }
           }
-        named_bar_sync(1 + quarter, kSplit * 32);  // every partner has read the sums before they are overwritten
-        xchf[ew * 32 + lane] = sq;
-        named_bar_sync(1 + quarter, kSplit * 32);
-        float tsq = 0.f;
-#pragma unroll
-        for (int j = 0; j < kSplit; ++j) tsq += xchf[xbase + 128 * j];
-        const float rstd = rsqrtf(tsq * (1.f / BN) + p.eps);
-        named_bar_sync(1 + quarter, kSplit * 32);  // ... and the squares before the next tile's sums
+          row_stats();
+          gamma = p.gamma2;
+          beta = p.beta2;
+        }
 
         float* frow = (p.out_f32 && valid) ? p.out_f32 + size_t(row) * BN : nullptr;
 #pragma unroll
         for (int i = 0; i < kMyChunks; ++i) {
           const int c = half + kSplit * i;
-          const float* gptr = p.gamma + c * 32;
-          const float* btptr = p.beta + c * 32;
+          const float* gptr = gamma + c * 32;
+          const float* btptr = beta + c * 32;
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {

@@ -66,6 +66,8 @@ struct GemmParams {
   const float* beta = nullptr;
   float eps = 1e-5f;
   float* out_f32 = nullptr;          // optional fp32 copy of the LN output, leading dim N
+  const float* gamma2 = nullptr;     // optional second LayerNorm applied to the first one's output (persistent kernel
+  const float* beta2 = nullptr;      // only): nn.Transformer's final encoder norm fused into the last layer's norm2
   // kEpiBiasPeRemap
   int rows_in = 1;                   // GEMM rows per item (196 image tokens)
   int rows_out = 1;                  // output rows per item (kLP, or 196 for the FA image-token store)

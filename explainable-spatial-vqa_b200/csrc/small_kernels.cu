@@ -277,6 +277,10 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
 // a program in PREFIX order becomes chain elements in execution order (= post-order: inputs before consumers, root
 // last, exactly tree_to_list's numbering) with dependency pointers.  One thread per question; malformed programs
 // (a terminator before the tree closes, more than S nodes) are truncated, never out of bounds.
+// (nvcc's "used before its value is set" on tokv / child / nchild is a false positive: emit(node) only ever sees nodes
+//  whose three entries were written when the node was pushed; zero-filling 320 ints per thread would cost more than
+//  the kernel)
+#pragma nv_diag_suppress 549
 __global__ void programs_to_chain_kernel(const ProgToChainParams p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
@@ -329,6 +333,7 @@ __global__ void programs_to_chain_kernel(const ProgToChainParams p) {
   }
   p.n_steps[b] = cnt;
 }
+#pragma nv_diag_default 549
 
 // Holds the stream busy for `cycles` SM clocks: lets the host enqueue a whole step behind it so that the
 // profiler's event timestamps see back-to-back kernels instead of host launch latency.
