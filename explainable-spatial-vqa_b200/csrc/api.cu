@@ -592,7 +592,7 @@ int gemm_res_ln(b200vqa_handle* h, const __nv_bfloat16* A, int M, int K, const _
   p.beta = beta;
   p.eps = h->d.layer_norm_eps;
   p.out_f32 = out_f32;
-  return gemm(h, kEpiBiasResLN, false, A, M, K, K, W, kD, p, s);
+  return gemm(h, gamma2 ? kEpiBiasResLN2 : kEpiBiasResLN, false, A, M, K, K, W, kD, p, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -36,7 +36,8 @@ constexpr int kKBytes = 128;      // bytes of K per k-block = one 128B swizzle r
 constexpr int kUmmaKBytes = 32;   // bytes of K per tcgen05.mma (16 bf16 / 8 tf32)
 // epilogue warps: 8 (two per TMEM lane quarter); the LayerNorm epilogue is instruction-latency-bound with two warps per
 // scheduler, so it runs 16 (four per quarter, 64 of the 256 columns each)
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == kEpiBiasResLN ? 16 : 8; }
+__host__ __device__ constexpr bool is_ln_epi(int epi) { return epi == kEpiBiasResLN || epi == kEpiBiasResLN2; }
+__host__ __device__ constexpr int epi_warps(int epi) { return is_ln_epi(epi) ? 16 : 8; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + epi_warps(epi) * 32; }
 constexpr int kMaxEpiWarps = 16;
 constexpr int kAccStages = 2;
@@ -86,7 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   using L = GemmSmem<BN>;
   constexpr uint32_t kTmemCols = kAccStages * BN;
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
-  static_assert(EPI != kEpiBiasResLN || BN == 256, "LN epilogue needs the whole row in one tile");
+  static_assert(!is_ln_epi(EPI) || BN == 256, "LN epilogue needs the whole row in one tile");
   constexpr int kChunks = BN / 32;            // 32-column chunks per tile
   constexpr int kEpiWarps = epi_warps(EPI);
   constexpr int kSplit = kEpiWarps / 4;           // warps sharing a TMEM lane quarter (they split the columns)
@@ -283,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       // LayerNorm epilogue: while the operands / MMAs of this tile are still in flight, pull bias | gamma | beta
       // into L1 and request the first residual chunk, so no L2 round trip sits inside the dependent chunk loops
       [[maybe_unused]] uint4 rnext[4];
-      if constexpr (EPI == kEpiBiasResLN) {
+      if constexpr (is_ln_epi(EPI)) {
         if (ew == 0 && lane < 24) {
           const float* src = lane < 8 ? p.bias + n0 : (lane < 16 ? p.gamma : p.beta);
           prefetch_l1(src + (lane & 7) * 32);
@@ -558,7 +559,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         row_stats();
         const float* gamma = p.gamma;
         const float* beta = p.beta;
-        if (p.gamma2) {
+        if constexpr (EPI == kEpiBiasResLN2) {
           // a second LayerNorm on top (nn.Transformer's final encoder norm, FA:42): normalise in registers, then take the
           // statistics of the result - one kernel and one 512-byte-per-row round trip through HBM fewer
 #pragma unroll
@@ -926,7 +927,8 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
     if (p.N != 256 || (p.K != 256 && p.K != 512 && p.K != 1024) || tf32) return cudaErrorInvalidValue;
     return launch_ln_cluster(tm_a, tm_w, p, stream);
   }
-  if (epilogue == kEpiBiasResLN && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
+  if (is_ln_epi(epilogue) && (p.N != 256 || block_n != 256)) return cudaErrorInvalidValue;
+  if (epilogue == kEpiBiasResLN2 && (!p.gamma2 || !p.beta2)) return cudaErrorInvalidValue;
 #define B200VQA_GEMM_CASE(BN_, EPI_, TF_)                                                   \
   if (block_n == BN_ && epilogue == EPI_ && tf32 == TF_)                                    \
     return launch_one<BN_, EPI_, TF_>(tm_a, tm_w, p, num_sms, stream);
@@ -937,6 +939,7 @@ cudaError_t launch_gemm(int epilogue, bool tf32, int block_n, const CUtensorMap&
   B200VQA_GEMM_CASE(128, kEpiBiasRelu, false)
   B200VQA_GEMM_CASE(64, kEpiBiasRelu, false)
   B200VQA_GEMM_CASE(256, kEpiBiasResLN, false)
+  B200VQA_GEMM_CASE(256, kEpiBiasResLN2, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, false)
   B200VQA_GEMM_CASE(256, kEpiBiasPeRemap, true)
   B200VQA_GEMM_CASE(256, kEpiLstm, false)

@@ -44,8 +44,11 @@ enum GemmEpilogue : int {
   kEpiBiasPeRemap = 3,// bf16 out[row'] = acc + bias + pe[p]; row' = item*rows_out + off + p
   kEpiHead = 4,       // vocabulary head of one decode position: logits = acc + bias (N = padded vocabulary), argmax ->
                       // tok[row, t+1], next input x_next[row] = emb[next] + pe[t+1]   (IQAP:230-236, FA:142-145)
-  kEpiLstm = 5        // one LSTM time step of the program generator: gates = acc (h_prev . W_hh^T) + table[token]
+  kEpiLstm = 5,       // one LSTM time step of the program generator: gates = acc (h_prev . W_hh^T) + table[token]
                       // (embedding . W_ih^T + biases, precomputed per vocabulary entry); c, h updated in the epilogue
+  kEpiBiasResLN2 = 6  // kEpiBiasResLN followed by a second LayerNorm (gamma2 / beta2) of its output: nn.Transformer's final
+                      // encoder norm fused into the last layer's norm2 (its own instantiation: the common epilogue keeps
+                      // its register budget)
 };
 
 struct GemmParams {
@@ -66,8 +69,8 @@ struct GemmParams {
   const float* beta = nullptr;
   float eps = 1e-5f;
   float* out_f32 = nullptr;          // optional fp32 copy of the LN output, leading dim N
-  const float* gamma2 = nullptr;     // optional second LayerNorm applied to the first one's output (persistent kernel
-  const float* beta2 = nullptr;      // only): nn.Transformer's final encoder norm fused into the last layer's norm2
+  const float* gamma2 = nullptr;     // kEpiBiasResLN2: the second LayerNorm's weight / bias
+  const float* beta2 = nullptr;
   // kEpiBiasPeRemap
   int rows_in = 1;                   // GEMM rows per item (196 image tokens)
   int rows_out = 1;                  // output rows per item (kLP, or 196 for the FA image-token store)
