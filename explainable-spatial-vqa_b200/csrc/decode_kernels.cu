@@ -297,7 +297,8 @@ constexpr int kMemWarps = 4;                                // small CTAs: six f
 constexpr int kMemKSplit = kMemWarps / kMemRowGroups;       // warps sharing a row group split the 256 channels
 constexpr int kMemMTiles = kD / kMemWarps / 16;             // 16-channel output tiles per warp in the value product
 constexpr int kMemKSteps = 16 / kMemKSplit;                 // 16-channel MMA steps per warp in the score phase
-constexpr int kMemCtasPerSm = 6;
+constexpr int kMemCtasPerSm = 6;                            // occupancy the kernel is compiled for (registers, 33 KB of ring each)
+constexpr int kMemLaunchCtasPerSm = 4;                      // ... and the persistent CTAs actually launched per SM (see launch_mem_attn)
 constexpr int kMemStages = 2;
 constexpr int kMemBlockBytes = kMemTileRows * 128;          // one 64-channel column block of a tile (TMA box)
 constexpr int kMemStageBytes = 4 * kMemBlockBytes;
@@ -543,8 +544,13 @@ cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, c
   int num_sms = 0;
   cudaError_t e = current_device_sms(&num_sms);
   if (e != cudaSuccess) return e;
-  // persistent: kMemCtasPerSm CTAs per SM, each streaming its questions back to back
-  const int grid = p.B < kMemCtasPerSm * num_sms ? p.B : kMemCtasPerSm * num_sms;
+  // persistent CTAs, each streaming its questions back to back.  FOUR per SM although six would fit: 592 concurrent
+  // streams reach 0.90 of the measured copy peak at 4096 questions where 888 reach 0.78 (0.79 / 0.73 at 2048, 0.69 / 0.65
+  // at 1024; 3 and 5 per SM, one CTA per question and a three-stage ring all measure in between or below:
+  // tools/microbench_mem_attn.py, profiles/r2_microbench_mem_attn_grid.txt) - fewer, longer streams
+  int per_sm = kMemLaunchCtasPerSm;
+  if (const char* g = getenv("B200VQA_MEM_ATTN_CTAS_PER_SM")) per_sm = std::min(kMemCtasPerSm, std::max(1, atoi(g)));  // A/B runs
+  const int grid = p.B < per_sm * num_sms ? p.B : per_sm * num_sms;
   e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<4>), kMemAttnSmem);
   if (e == cudaSuccess) e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<2>), kMemAttnSmem);
   if (e != cudaSuccess) return e;
