@@ -338,3 +338,39 @@ def test_warp_self_attention_equals_cta_form(monkeypatch):
     assert torch.equal(a1, a2)
     assert common.rel_err(l1, l2) < 4e-3
     assert cta.native_launch_count() == warp.native_launch_count()
+
+
+def test_host_pipeline_reuses_a_slot_with_different_data(model):
+    """back-to-back asynchronous host calls on ONE slot with different inputs - the second call's uploads
+    must not overwrite staging that the first call's (still running) compute reads, and the host tensors of both calls
+    stay alive until drain_host()."""
+    imgs, qs = orc.iqap_inputs(96, seed=33)
+    want_a, want_p = model(imgs.cuda(), qs.cuda())
+    outs = []
+    for i in range(3):   # depth=1: every call lands on the same (handle, stream) slot
+        lo, hi = 32 * i, 32 * (i + 1)
+        # temporaries on purpose: .clone().pin_memory() results are only referenced by the library call
+        outs.append(model.submit_host(imgs[lo:hi].clone().pin_memory(), qs[lo:hi].clone().pin_memory(), chunk=16, depth=1))
+    model.drain_host()
+    assert torch.equal(torch.cat([o[0] for o in outs]), want_a.cpu())
+    assert torch.equal(torch.cat([o[1] for o in outs]), want_p.cpu())
+
+
+def test_start_token_follows_config_at_decode_time(model):
+    """The reference reads Config.SPECIAL_TOKEN_ID when it decodes (IQAP:205), not when the model is built."""
+    from explainable_spatial_vqa_b200 import inference_transformer_iqap as iqap
+    img, q = orc.iqap_inputs(6, seed=12)
+    sd = cpu_sd(model)
+    memory = orc.iqap_encode(sd, img, q)
+    saved = iqap.Config.SPECIAL_TOKEN_ID
+    try:
+        iqap.Config.SPECIAL_TOKEN_ID = 2
+        ref_tok, ref_lg = orc.iqap_decode(sd, memory, 27, start_token=2)
+        _, prog, lg, _ = model.forward_detailed(img.cuda(), q.cuda(), forced_programs=ref_tok.cuda(), want_logits=True)
+        assert common.rel_err(lg, ref_lg) < common.LOGIT_REL_TOL
+    finally:
+        iqap.Config.SPECIAL_TOKEN_ID = saved
+    ref1_tok, ref1_lg = orc.iqap_decode(sd, memory, 27, start_token=1)
+    _, _, lg1, _ = model.forward_detailed(img.cuda(), q.cuda(), forced_programs=ref1_tok.cuda(), want_logits=True)
+    assert common.rel_err(lg1, ref1_lg) < common.LOGIT_REL_TOL
+    assert common.rel_err(lg1[:, 0], ref_lg[:, 0]) > 1e-2   # the first position really depends on the start token

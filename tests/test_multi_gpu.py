@@ -61,3 +61,30 @@ def test_two_gpu_results_are_bitwise_equal_to_one_gpu(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_two_handles_on_two_devices_in_one_process():
+    """kernel attributes (dynamic shared memory opt-in) and the SM count are per device - a second handle on
+    another GPU of the SAME process must work, and both devices must give identical results."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import common
+    from explainable_spatial_vqa_b200 import synthetic as syn
+    img, q = syn.iqap_inputs(40, seed=3)
+    m0 = common.seeded_iqap().to("cuda:0")
+    m1 = common.seeded_iqap().to("cuda:1")
+    a0, p0 = m0(img.to("cuda:0"), q.to("cuda:0"))
+    a1, p1 = m1(img.to("cuda:1"), q.to("cuda:1"))
+    a0b, p0b = m0(img.to("cuda:0"), q.to("cuda:0"))   # and back on the first device
+    torch.cuda.synchronize("cuda:0")
+    torch.cuda.synchronize("cuda:1")
+    assert torch.equal(a0.cpu(), a1.cpu()) and torch.equal(p0.cpu(), p1.cpu())
+    assert torch.equal(a0, a0b) and torch.equal(p0, p0b)
+    f0 = common.seeded_fa().to("cuda:1")
+    func, deps, n_steps = syn.fa_programs(8, seed=5, max_steps=3)
+    fimg = torch.randn(8, 1024, 14, 14).relu_()
+    from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
+    c1 = fa.run_inference_chain_batched(f0, fimg.to("cuda:1"), func, deps, n_steps, 0, 20)
+    assert int(c1[:, 0, 0].max()) == 0
