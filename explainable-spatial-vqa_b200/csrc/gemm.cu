@@ -43,15 +43,23 @@ constexpr int kMaxEpiWarps = 16;
 constexpr int kAccStages = 2;
 constexpr int kStages = 4;
 constexpr int kWstatMaxKb = 4;    // W-stationary when the whole K fits in 4 k-blocks
+constexpr int kWstatKb = 4;
 
 template <int BN>
 struct GemmSmem {
   static constexpr int kStageA = kBM * kKBytes;             // 16 KB
   static constexpr int kStageB = BN * kKBytes;              // 8 / 16 / 32 KB
-  static constexpr int kRing = kStages * (kStageA + kStageB);  // streaming ring == W (4 blocks) + A ring
-  // staging: 32 KB = 8 warps x two 32-row x 64-byte tiles (double-buffered) or 16 warps x one tile
+  // BN = 64 serves the decode chain (M = one branch of questions, K = 256, a single tile per CTA): two A stages and a
+  // single-buffered epilogue staging bring the CTA from 130 KB to 82 KB, so that two of them - or one beside the
+  // memory-attention CTAs of another branch - share an SM instead of each holding one
+  static constexpr int kNSt = BN == 64 ? 2 : kStages;
+  static constexpr int kStg = BN == 64 ? 16384 : 32768;
+  static constexpr int kRingW = kWstatKb * kStageB + kNSt * kStageA;      // W-stationary: W (4 blocks) + A ring
+  static constexpr int kRingS = kNSt * (kStageA + kStageB);               // streaming: stage = [A | W]
+  static constexpr int kRing = kRingW > kRingS ? kRingW : kRingS;
+  // staging: 8 warps x two 32-row x 64-byte tiles (double-buffered), 16 warps x one tile, or 8 x one tile (BN = 64)
   static constexpr int kOffStg = kRing;
-  static constexpr int kOffXch = kOffStg + 32768;           // LayerNorm / argmax exchange between the warps of a quarter
+  static constexpr int kOffXch = kOffStg + kStg;            // LayerNorm / argmax exchange between the warps of a quarter
   static constexpr int kOffBar = kOffXch + 2048;
   static constexpr int kBytes = kOffBar + 128 /*barriers + tmem ptr*/;
 };
@@ -82,7 +90,7 @@ __device__ __forceinline__ void store_chunk_bf16(uint8_t* buf, const uint32_t (&
 }
 
 template <int BN, int EPI, bool TF32>
-__global__ void __launch_bounds__(gemm_threads(EPI), 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), BN == 64 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const GemmParams p) {
   using L = GemmSmem<BN>;
   constexpr uint32_t kTmemCols = kAccStages * BN;
@@ -92,7 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   constexpr int kEpiWarps = epi_warps(EPI);
   constexpr int kSplit = kEpiWarps / 4;           // warps sharing a TMEM lane quarter (they split the columns)
   constexpr int kMyChunks = kChunks / kSplit;     // per epilogue warp
-  constexpr int kStgPerWarp = 32768 / kEpiWarps;  // 4 KB (two buffers) or 2 KB (one buffer)
+  constexpr int kNSt = L::kNSt;
+  constexpr int kStgPerWarp = L::kStg / kEpiWarps;  // 4 KB (two buffers) or 2 KB (one buffer)
   constexpr uint32_t kStgMask = kStgPerWarp == 4096 ? 1u : 0u;
   static_assert(kChunks % kSplit == 0, "column chunks must divide among the warps of a quarter");
 
@@ -194,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk + a_koff, m0);
             tma_load_2d(&tm_w, &full_bar[stage], sa + L::kStageA, kb * bk, n0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNSt) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -239,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             else      umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNSt) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[as]);        // accumulator ready for the epilogue
         if (wstat) {
