@@ -430,9 +430,19 @@ def run_ours(args):
         if generator is not None:
             q_h, p_h = questions.cpu().pin_memory(), synth_programs.cpu().pin_memory()
 
+        host_out_no = [0]
+        host_out = [torch.empty(B, func.shape[1], 20, dtype=torch.int32).pin_memory() for _ in range(depth)] \
+            if generator is None and depth > 1 else []
+
         def step_e2e():
             if generator is None:
-                # the library's host-buffer entry: sub-batches uploaded + projected while the previous one executes
+                # the library's host-buffer entry: sub-batches uploaded + projected while the previous one executes;
+                # with several steps in flight the upload of a step also runs under the chains of the previous step
+                if depth > 1:
+                    k = host_out_no[0] % depth
+                    host_out_no[0] += 1
+                    return fa.submit_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk,
+                                                          depth=depth, out=host_out[k])
                 return fa.run_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk,
                                                    parts=args.fa_host_parts)
             else:
@@ -443,7 +453,7 @@ def run_ours(args):
 
         h2d = B * 1024 * 196 * 4 + (f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4 if generator is None
                                       else q_h.numel() * 8 + p_h.numel() * 8)
-        drain_host = torch.cuda.synchronize
+        drain_host = model.drain_host if generator is None else torch.cuda.synchronize
         d2h = B * func.shape[1] * 20 * 4
 
     def barrier():
@@ -682,7 +692,9 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=None,
                     help="independent batches in flight (1 = strictly serial steps); default 2 (iqap) / 3 (fa, e2e)")
     ap.add_argument("--blocks", type=int, default=5, help="timed K-step blocks (the first gives `value`; the median is reported too)")
-    ap.add_argument("--fa-host-chunk", type=int, default=1024, help="questions per sub-batch of the FA host-buffer call")
+    ap.add_argument("--fa-host-chunk", type=int, default=None,
+                    help="questions per sub-batch of the FA host-buffer call (default: the whole batch when steps are "
+                         "pipelined - uploads of consecutive steps queue on one ingest stream - else 1024)")
     ap.add_argument("--fa-host-parts", type=int, default=4, help="concurrent parts (handle + stream slots) of the FA host-buffer call")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -694,6 +706,8 @@ def main():
         args.batch = 1024 if args.workload == "iqap" else 4096
     if args.pipeline_depth is None:
         args.pipeline_depth = 2 if args.workload == "iqap" else 3
+    if args.fa_host_chunk is None:
+        args.fa_host_chunk = args.batch if args.pipeline_depth > 1 else 1024
     # every pipeline slot allocates its workspace and captures its graphs on first use: all of them warm up
     args.warmup = max(args.warmup, 3, args.pipeline_depth) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <tuple>
 #include <vector>
@@ -188,6 +189,10 @@ struct b200vqa_handle {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
+  int32_t* h_tables = nullptr;  // pinned: the sorted program tables of one fa_run_chain_host call
+  size_t h_tables_ints = 0;
+  cudaEvent_t ev_tables = nullptr;
+  bool tables_pending = false;
 };
 
 namespace {
@@ -1269,6 +1274,8 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_tables) cudaEventDestroy(h->ev_tables);
+  if (h->h_tables) cudaFreeHost(h->h_tables);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int i = 0; i < 7; ++i) {
     if (h->br_stream[i]) cudaStreamDestroy(h->br_stream[i]);
@@ -1852,6 +1859,20 @@ B200VQA_API int b200vqa_fa_run_chain_indexed(b200vqa_handle* h, const void* img_
                            cache, h_active, opt_logits, opt_forced, stream);
 }
 
+static int shared_ingest_stream(int device, cudaStream_t* out) {
+  static std::mutex mu;
+  static std::map<int, cudaStream_t> streams;  // lives as long as the process (like the context it belongs to)
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = streams.find(device);
+  if (it == streams.end()) {
+    cudaStream_t st = nullptr;
+    B200VQA_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    it = streams.emplace(device, st).first;
+  }
+  *out = it->second;
+  return B200VQA_OK;
+}
+
 // Host buffers in, host cache out: the reference's driver loop does one H2D and one D2H PER PROGRAM STEP
 // (FA:193-206 -> 109-121); here a sub-batch of questions is uploaded once (double-buffered, projected as it lands),
 // executed longest-program-first with the cache resident in HBM, and its cache rows are downloaded once - while the
@@ -1879,7 +1900,12 @@ static int fa_run_chain_host_impl(b200vqa_handle* h, const float* h_img, const i
       B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
     }
   }
-  cudaStream_t ingest = h->copy_stream;  // upload + image projection of sub-batch k+1 run here while k executes on `s`
+  // upload + image projection of sub-batch k+1 run on the ingest stream while k executes on `s`.  ONE ingest stream per
+  // device, shared by every handle: with several calls in flight on different (handle, stream) slots their uploads
+  // queue up in submission order instead of splitting the PCIe link (three concurrent 60-ms uploads would all land
+  // after 180 ms and none of the chains could start earlier)
+  cudaStream_t ingest = nullptr;
+  RC_OK(shared_ingest_stream(h->device, &ingest));
   auto up = [](size_t n) { return (n + 255) & ~size_t(255); };
   const size_t per_img = size_t(d.n_img_tokens) * d.img_feat_dim;
   const size_t img_b = up(size_t(ichunk) * per_img * sizeof(float));
@@ -1931,71 +1957,96 @@ static int fa_run_chain_host_impl(b200vqa_handle* h, const float* h_img, const i
     tr_name.push_back(name);
   };
   mark("start (compute stream)", s);
-  std::vector<int32_t> order, func_s, deps_s, ns_s, active(S);
-  // ingest stream: features of sub-batch k in caller order, projected as they land (image_proj + PE once per question).
-  // Enqueued one sub-batch AHEAD of the chains on the host as well: enqueueing a chain (hundreds of launches) can block
-  // the host on the launch queue, and the next upload must already be behind it
+  // ---- host: every sub-batch longest program first (stable), so that finished questions drop out of the later
+  // steps.  The sorted tables of the WHOLE call are written to pinned memory up front: a copy from pageable memory would
+  // make the host wait for everything queued before it on the stream, i.e. for the previous sub-batch's chains
+  const int n_sub = (B + chunk - 1) / chunk;
+  const size_t tab_ints = size_t(B) * (size_t(S) * 3 + 2);
+  if (h->tables_pending) {  // the previous call on this handle may still be uploading from the table buffer
+    B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_tables));
+    h->tables_pending = false;
+  }
+  if (h->h_tables_ints < tab_ints) {
+    if (h->h_tables) B200VQA_CUDA_OK(cudaFreeHost(h->h_tables));
+    h->h_tables = nullptr;
+    h->h_tables_ints = 0;
+    B200VQA_CUDA_OK(cudaMallocHost(&h->h_tables, tab_ints * sizeof(int32_t)));
+    h->h_tables_ints = tab_ints;
+  }
+  if (!h->ev_tables) B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming));
+  std::vector<int32_t> active(size_t(n_sub) * S);
+  auto tab_func = [&](int k) { return h->h_tables + size_t(k) * chunk * (size_t(S) * 3 + 2); };
+  for (int k = 0; k < n_sub; ++k) {
+    const int b0 = k * chunk;
+    const int nb = std::min(chunk, B - b0);
+    int32_t* t_func = tab_func(k);
+    int32_t* t_deps = t_func + size_t(nb) * S;
+    int32_t* t_ns = t_deps + size_t(nb) * S * 2;
+    int32_t* t_order = t_ns + nb;
+    for (int i = 0; i < nb; ++i) t_order[i] = i;
+    std::stable_sort(t_order, t_order + nb, [&](int a, int b) { return h_n_steps[b0 + a] > h_n_steps[b0 + b]; });
+    for (int i = 0; i < nb; ++i) {
+      const size_t src = size_t(b0) + t_order[i];
+      std::memcpy(t_func + size_t(i) * S, h_func + src * S, size_t(S) * sizeof(int32_t));
+      std::memcpy(t_deps + size_t(i) * S * 2, h_deps + src * S * 2, size_t(S) * 2 * sizeof(int32_t));
+      t_ns[i] = h_n_steps[src];
+    }
+    for (int i = 0; i < S; ++i) {
+      int a = 0;
+      while (a < nb && t_ns[a] > i) ++a;
+      active[size_t(k) * S + i] = a;
+    }
+  }
+  // ingest stream: features of sub-batch k in caller order, projected as they land (image_proj + PE once per question),
+  // then its program tables.  Enqueued one sub-batch AHEAD of the chains on the host as well, so that the next upload
+  // is already queued when the host is held up on the launch queue by a chain (hundreds of launches)
   auto enqueue_ingest = [&](int k) -> int {
     const int b0 = k * chunk;
     const int nb = std::min(chunk, B - b0);
     const int par = k & 1;
-    if (k >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));  // chain k-2 has released d_tok[par]
+    // chain k-2 (and the scatter + download behind it) has released d_tok / the tables / the caches of this parity
+    if (k >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));
     for (int i0 = 0; i0 < nb; i0 += ichunk) {
       const int ni = std::min(ichunk, nb - i0);
       B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, h_img + (size_t(b0) + i0) * per_img, size_t(ni) * per_img * sizeof(float),
                                       cudaMemcpyHostToDevice, ingest));
       RC_OK(b200vqa_fa_project_images(h, d_img, ni, d_tok[par] + size_t(i0) * d.n_img_tokens * kD, ingest));
     }
+    const int32_t* t_func = tab_func(k);
+    const int32_t* t_deps = t_func + size_t(nb) * S;
+    const int32_t* t_ns = t_deps + size_t(nb) * S * 2;
+    const int32_t* t_order = t_ns + nb;
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_func[par], t_func, size_t(nb) * S * 4, cudaMemcpyHostToDevice, ingest));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_deps[par], t_deps, size_t(nb) * S * 8, cudaMemcpyHostToDevice, ingest));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_ns[par], t_ns, size_t(nb) * 4, cudaMemcpyHostToDevice, ingest));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_order[par], t_order, size_t(nb) * 4, cudaMemcpyHostToDevice, ingest));
+    B200VQA_CUDA_OK(cudaMemsetAsync(d_cache_sorted[par], 0xff, size_t(nb) * S * max_len * sizeof(int32_t), ingest));
     B200VQA_CUDA_OK(cudaEventRecord(h->ev_in[par], ingest));
     mark("ingest done", ingest);
     return B200VQA_OK;
   };
-  const int n_sub = (B + chunk - 1) / chunk;
   RC_OK(enqueue_ingest(0));
   int sub = 0;
   for (int b0 = 0; b0 < B; b0 += chunk, ++sub) {
     const int nb = std::min(chunk, B - b0);
     const int par = sub & 1;
-    // sub-batch sub+1 may be uploaded as soon as chain sub-1 (which reads the same d_tok buffer) has been ENQUEUED: its
+    // sub-batch sub+1 may be uploaded as soon as chain sub-1 (which uses the same buffers) has been ENQUEUED: its
     // release event exists by then
     if (sub + 1 < n_sub) RC_OK(enqueue_ingest(sub + 1));
-    // ---- host: longest program first (stable), so that finished questions drop out of the later steps
-    order.resize(nb);
-    for (int i = 0; i < nb; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int a, int b) { return h_n_steps[b0 + a] > h_n_steps[b0 + b]; });
-    func_s.resize(size_t(nb) * S);
-    deps_s.resize(size_t(nb) * S * 2);
-    ns_s.resize(nb);
-    for (int i = 0; i < nb; ++i) {
-      const size_t src = size_t(b0) + order[i];
-      std::memcpy(&func_s[size_t(i) * S], h_func + src * S, size_t(S) * sizeof(int32_t));
-      std::memcpy(&deps_s[size_t(i) * S * 2], h_deps + src * S * 2, size_t(S) * 2 * sizeof(int32_t));
-      ns_s[i] = h_n_steps[src];
-    }
-    for (int i = 0; i < S; ++i) {
-      int a = 0;
-      while (a < nb && ns_s[a] > i) ++a;
-      active[i] = a;
-    }
-    // ---- compute stream (pageable sources: these small copies are staged before the call returns)
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_func[par], func_s.data(), func_s.size() * 4, cudaMemcpyHostToDevice, s));
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_deps[par], deps_s.data(), deps_s.size() * 4, cudaMemcpyHostToDevice, s));
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_ns[par], ns_s.data(), ns_s.size() * 4, cudaMemcpyHostToDevice, s));
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_order[par], order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
-    B200VQA_CUDA_OK(cudaMemsetAsync(d_cache_sorted[par], 0xff, size_t(nb) * S * max_len * sizeof(int32_t), s));
     B200VQA_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[par], 0));
     mark("chain start", s);
     // question i of the sorted batch uses the image tokens of question order[i]
     RC_OK(fa_run_chain_impl(h, d_tok[par], d_order[par], nb, d_func[par], d_deps[par], d_ns[par], nb, S, start_token,
-                            max_len, d_cache_sorted[par], active.data(), nullptr, nullptr, s));
-    B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[par], s));
+                            max_len, d_cache_sorted[par], &active[size_t(sub) * S], nullptr, nullptr, s));
     h->cur_tag = kTagMisc;
     LAUNCH_OK(h, launch_scatter_rows_i32(d_cache_sorted[par], d_order[par], nb, S * max_len, d_cache[par], s));
     B200VQA_CUDA_OK(cudaMemcpyAsync(h_cache + size_t(b0) * S * max_len, d_cache[par],
                                     size_t(nb) * S * max_len * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[par], s));
     mark("chain + download done", s);
   }
+  B200VQA_CUDA_OK(cudaEventRecord(h->ev_tables, ingest));
+  h->tables_pending = true;
   if (sync || trace) B200VQA_CUDA_OK(cudaStreamSynchronize(s));
   if (trace) {
     B200VQA_CUDA_OK(cudaStreamSynchronize(ingest));

@@ -123,6 +123,13 @@ class MultiModalTransformer(nn.Module):
         """Results of every pipelined call (`slot > 0`) become valid on the caller's current stream."""
         self._pool.drain()
 
+    def drain_host(self):
+        """Blocks the host until every `submit_inference_chain_host` has delivered its cache."""
+        for st in list(self._pool._streams.values()):
+            st.synchronize()
+        if hasattr(self, "_host_inflight"):
+            self._host_inflight.clear()
+
     # ------------------------------------------------------------------ reference surface
     @torch.no_grad()
     def forward(self, image_features, src_text, tgt_text, src_len=None):
@@ -374,6 +381,45 @@ def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, sta
                 C.c_void_p(st.cuda_stream)), "b200vqa_fa_run_chain_host_async")
         for st in streams:
             st.synchronize()   # img / f / d / n / cache are referenced by this frame until every part has finished
+    return cache
+
+
+@torch.no_grad()
+def submit_inference_chain_host(model, image_features_cpu, func, deps, n_steps, start_token=0, max_infer_len=20,
+                                chunk=1024, depth=2, out=None):
+    """`run_inference_chain_host` without the final synchronisation, on a round-robin (handle, stream) slot: the upload
+    of this batch runs under the chains of the previous one.  Returns the pinned host cache (`out` when given: a
+    pinned int32 (B,S,max_infer_len) tensor the caller recycles), valid after `model.drain_host()`; the host inputs are
+    kept alive until then."""
+    img = image_features_cpu.to(torch.float32).contiguous()
+    f = func.to(torch.int32).contiguous()
+    d = deps.to(torch.int32).contiguous()
+    n = n_steps.to(torch.int32).contiguous()
+    if img.is_cuda or f.is_cuda or d.is_cuda or n.is_cuda:
+        raise ValueError("submit_inference_chain_host takes CPU tensors")
+    B, S = f.shape
+    if tuple(d.shape) != (B, S, MAX_DEPS) or tuple(n.shape) != (B,) or img.shape[0] != B:
+        raise ValueError("expected image_features (B,1024,14,14), func (B,S), deps (B,S,2), n_steps (B,)")
+    if B and img[0].numel() != model.image_proj.in_features * model.max_img_tokens:
+        raise ValueError(f"image_features must hold {model.image_proj.in_features} x {model.max_img_tokens} values per question")
+    if not hasattr(model, "_host_inflight"):
+        model._host_inflight, model._next_host_slot = [], 0
+    slot = 1 + model._next_host_slot % max(1, int(depth))
+    model._next_host_slot += 1
+    h = model._native(slot)
+    st = model._pool.stream(slot)
+    if out is None:
+        cache = torch.empty(B, S, max_infer_len, dtype=torch.int32).pin_memory()
+    else:
+        cache = out
+        if cache.dtype != torch.int32 or tuple(cache.shape) != (B, S, max_infer_len) or not cache.is_pinned() \
+                or not cache.is_contiguous():
+            raise ValueError("out must be a pinned contiguous int32 tensor of shape (B, S, max_infer_len)")
+    with torch.cuda.device(st.device):
+        nat.check(nat.lib().b200vqa_fa_run_chain_host_async(
+            h.raw, nat.ptr(img), nat.ptr(f), nat.ptr(d), nat.ptr(n), B, S, int(start_token), int(max_infer_len),
+            nat.ptr(cache), int(min(chunk, B)), C.c_void_p(st.cuda_stream)), "b200vqa_fa_run_chain_host_async")
+    model._host_inflight.append((img, f, d, n, cache))
     return cache
 
 

@@ -120,3 +120,9 @@ def test_fa_host_entry_equals_device_entry():
     want = fa.run_inference_chain_batched(model, img.cuda(), func, deps, n_steps, 0, 20).cpu()
     got = fa.run_inference_chain_host(model, img.pin_memory(), func, deps, n_steps, 0, 20, chunk=128, parts=2)
     assert torch.equal(got, want)
+    # asynchronous submission on round-robin slots: three batches in flight on two slots, valid after drain_host()
+    outs = [fa.submit_inference_chain_host(model, img[i * 200:(i + 1) * 200].pin_memory(), func[i * 200:(i + 1) * 200],
+                                           deps[i * 200:(i + 1) * 200], n_steps[i * 200:(i + 1) * 200], 0, 20, chunk=64,
+                                           depth=2) for i in range(3)]
+    model.drain_host()
+    assert torch.equal(torch.cat(outs), want)
