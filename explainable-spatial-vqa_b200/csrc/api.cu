@@ -104,12 +104,12 @@ using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint3
 
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
-  kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFinalLn,
+  kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFfnFused, kTagEncFinalLn,
   kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagDecPersist, kTagMisc, kNumTags
 };
 const char* const kTagNames[kNumTags] = {
     "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
-    "enc_ffn2_ln_gemm", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_proj_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
+    "enc_ffn2_ln_gemm", "enc_ffn_fused", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_proj_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
     "dec_cross_attention", "dec_head_argmax", "dec_persistent", "misc"};
 
 struct ProfRec {
@@ -189,6 +189,10 @@ struct b200vqa_handle {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
+  int dbg_skip = 0;  // B200VQA_DBG_SKIP: timing decomposition only (results are garbage): 1 cross-attention, 2 self-
+                     // attention, 4 feed-forward, 8 out_proj+LN GEMMs, 16 plain GEMMs of the decode chain, 32 encoder
+  bool no_fused_enc_ffn = false;  // B200VQA_NO_FUSED_ENC_FFN=1: linear1 / linear2 as two GEMMs through HBM
+  int small_bn = 64;  // narrowest n-tile of the plain GEMMs (B200VQA_SMALL_BN=128: A/B of fewer, wider decode CTAs)
   int32_t* h_tables = nullptr;  // pinned: the sorted program tables of one fa_run_chain_host call
   size_t h_tables_ints = 0;
   cudaEvent_t ev_tables = nullptr;
@@ -550,7 +554,7 @@ int gemm(b200vqa_handle* h, int epi, bool tf32, const void* A, int M, int K, int
   if (epi == kEpiBias || epi == kEpiBiasRelu) {
     const int tiles_m = (M + 127) / 128;
     if (tiles_m * (N / 256) < h->num_sms / 2 && N % 128 == 0) bn = 128;
-    if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0) bn = 64;
+    if (tiles_m * (N / 128) < h->num_sms / 2 && N % 64 == 0 && h->small_bn <= 64) bn = 64;
   }
   if (p.a_group_cols > 0) bn = 64;  // grouped GEMM: an n-tile must not straddle two heads
   if (epi == kEpiHead) bn = N;  // N = padded vocabulary (one n-tile); rows >= V of W are zero-filled by TMA
@@ -612,6 +616,7 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
   __nv_bfloat16* in = w.x;
   __nv_bfloat16* out = w.mem;
   for (int l = 0; l < d.n_enc_layers; ++l) {
+    if (h->dbg_skip & 32) break;
     const LayerPacked& L = h->enc[l];
     h->cur_tag = kTagEncQkv;
     RC_OK(gemm_bias(h, false, in, M, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, w.qkv, s));
@@ -632,13 +637,35 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
     }
     h->cur_tag = kTagEncOutLn;
     RC_OK(gemm_res_ln(h, w.attn, M, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, w.x1, nullptr, s));
-    h->cur_tag = kTagEncFfn1;
-    RC_OK(gemm_bias(h, true, w.x1, M, kD, L.w1, d.dim_ff, L.b1, w.hid, s));
-    h->cur_tag = kTagEncFfn2Ln;
     // the last layer's norm2 also applies nn.Transformer's final encoder norm (FA:42) when there is one
     const bool fuse_final = l == d.n_enc_layers - 1 && h->enc_fn_w && !h->no_fused_final_ln;
-    RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s, false,
-                      fuse_final ? h->enc_fn_w : nullptr, fuse_final ? h->enc_fn_b : nullptr));
+    if (!h->no_fused_enc_ffn && d.dim_ff % 128 == 0) {
+      // linear1 -> ReLU -> linear2 -> + residual -> LayerNorm in one kernel: the hidden rows never leave the SM
+      CUtensorMap tx, tw1, tw2;
+      RC_OK(get_tmap(h, w.x1, TmapType::kBF16, uint64_t(M), kD, kD, 128, &tx));
+      RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 128, &tw1));
+      RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 256, &tw2));
+      EncFfnParams fp;
+      fp.M = M;
+      fp.n_slices = d.dim_ff / 128;
+      fp.b1 = L.b1;
+      fp.b2 = L.b2;
+      fp.residual = w.x1;
+      fp.gamma = L.n2w;
+      fp.beta = L.n2b;
+      fp.gamma2 = fuse_final ? h->enc_fn_w : nullptr;
+      fp.beta2 = fuse_final ? h->enc_fn_b : nullptr;
+      fp.eps = d.layer_norm_eps;
+      fp.out = out;
+      h->cur_tag = kTagEncFfnFused;
+      LAUNCH_OK(h, launch_enc_ffn_fused(tx, tw1, tw2, fp, s));
+    } else {
+      h->cur_tag = kTagEncFfn1;
+      RC_OK(gemm_bias(h, true, w.x1, M, kD, L.w1, d.dim_ff, L.b1, w.hid, s));
+      h->cur_tag = kTagEncFfn2Ln;
+      RC_OK(gemm_res_ln(h, w.hid, M, d.dim_ff, L.w2, L.b2, w.x1, L.n2w, L.n2b, out, nullptr, s, false,
+                        fuse_final ? h->enc_fn_w : nullptr, fuse_final ? h->enc_fn_b : nullptr));
+    }
     std::swap(in, out);
   }
   // `in` now holds the last layer's output
@@ -704,7 +731,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       __nv_bfloat16* vc = w.vc[l] + r0 * w.t_max * kD;
       const __nv_bfloat16* ckv = h->absorb ? nullptr : w.ckv[l] + r0 * kLP * 2 * kD;
       h->cur_tag = kTagDecGemm;
-      RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, dqkv, s));
+      if (!(h->dbg_skip & 16)) RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, dqkv, s));
       RowAttnParams sp;
       sp.B = B;
       sp.nhead = d.nhead;
@@ -725,15 +752,16 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       sp.out = dattn;
       sp.pdl = true;
       h->cur_tag = kTagDecSelfAttn;
-      LAUNCH_OK(h, launch_row_attn(sp, s));
+      if (!(h->dbg_skip & 2)) LAUNCH_OK(h, launch_row_attn(sp, s));
       h->cur_tag = kTagDecGemmLn;
-      RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s, true));
+      if (!(h->dbg_skip & 8))
+        RC_OK(gemm_res_ln(h, dattn, B, kD, L.self_attn.w_out, L.self_attn.b_out, in, L.n1w, L.n1b, dx1, nullptr, s, true));
       if (h->absorb) {
         // cross-attention on the encoder memory itself: absorbed queries (N = nhead*256), one pass over the memory
         // rows for all heads, then the per-head value projection as a grouped GEMM
         const int NHD = d.nhead * kD;
         h->cur_tag = kTagDecGemm;
-        RC_OK(gemm_bias(h, false, dx1, B, kD, L.w_qk, NHD, L.b_qk, dq, s));
+        if (!(h->dbg_skip & 16)) RC_OK(gemm_bias(h, false, dx1, B, kD, L.w_qk, NHD, L.b_qk, dq, s));
         MemAttnParams mp;
         mp.B = B;
         mp.nhead = d.nhead;
@@ -746,8 +774,8 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         h->cur_tag = kTagDecCrossAttn;
         CUtensorMap tmem_map;
         RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
-        LAUNCH_OK(h, launch_mem_attn(tmem_map, mp, s));
-        if (!h->absorb_ov) {
+        if (!(h->dbg_skip & 1)) LAUNCH_OK(h, launch_mem_attn(tmem_map, mp, s));
+        if (!h->absorb_ov && !(h->dbg_skip & 16)) {
           GemmParams vp;
           vp.bias = L.cross_attn.b_in + 2 * kD;
           vp.out = dattn;
@@ -778,7 +806,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       h->cur_tag = kTagDecGemmLn;
       if (h->absorb && h->absorb_ov)  // x2 = LN2(x1 + W_ov u + b_ov): K = nhead * 256 streamed through the cluster kernel
         RC_OK(gemm_res_ln(h, du, B, d.nhead * kD, L.w_ov, L.b_ov, dx1, L.n2w, L.n2b, dx2, nullptr, s, true));
-      else
+      else if (!(h->dbg_skip & 8))
         RC_OK(gemm_res_ln(h, dattn, B, kD, L.cross_attn.w_out, L.cross_attn.b_out, dx1, L.n2w, L.n2b, dx2, nullptr, s,
                           true));
       {
@@ -821,8 +849,10 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
           fp.x_next = dx;
         }
         h->cur_tag = kTagDecFfn;
-        LAUNCH_OK(h, launch_ffn_small(tx, tw1, tw2, fp, s));
-        ++h->launches;  // two kernels
+        if (!(h->dbg_skip & 4)) {
+          LAUNCH_OK(h, launch_ffn_small(tx, tw1, tw2, fp, s));
+          ++h->launches;  // two kernels
+        }
       }
       in = out;
     }
@@ -1205,6 +1235,9 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
     if (g[0] && g[0] != '0' && cudaMalloc(&h->persist_clk, 8 * 24 * sizeof(long long)) == cudaSuccess)
       cudaMemset(h->persist_clk, 0, 8 * 24 * sizeof(long long));
   }
+  if (const char* g = getenv("B200VQA_NO_FUSED_ENC_FFN")) h->no_fused_enc_ffn = g[0] && g[0] != '0';
+  if (const char* g = getenv("B200VQA_DBG_SKIP")) h->dbg_skip = atoi(g);
+  if (const char* g = getenv("B200VQA_SMALL_BN")) h->small_bn = atoi(g);
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);

@@ -550,7 +550,12 @@ cudaError_t launch_mem_attn(const CUtensorMap& tm_mem, const MemAttnParams& p, c
   // tools/microbench_mem_attn.py, profiles/r2_microbench_mem_attn_grid.txt) - fewer, longer streams
   int per_sm = kMemLaunchCtasPerSm;
   if (const char* g = getenv("B200VQA_MEM_ATTN_CTAS_PER_SM")) per_sm = std::min(kMemCtasPerSm, std::max(1, atoi(g)));  // A/B runs
-  const int grid = p.B < per_sm * num_sms ? p.B : per_sm * num_sms;
+  // ... and every CTA the same number of questions: 1024 questions on 592 CTAs would leave 432 CTAs with two questions
+  // and 160 with one (the launch lasts as long as two), 512 CTAs get exactly two each
+  const int max_ctas = per_sm * num_sms;
+  const int per_cta = (p.B + max_ctas - 1) / max_ctas;
+  int grid = (p.B + per_cta - 1) / per_cta;
+  if (getenv("B200VQA_MEM_ATTN_UNBALANCED")) grid = p.B < max_ctas ? p.B : max_ctas;  // A/B runs
   e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<4>), kMemAttnSmem);
   if (e == cudaSuccess) e = ensure_dyn_smem(reinterpret_cast<const void*>(mem_attn_kernel<2>), kMemAttnSmem);
   if (e != cudaSuccess) return e;

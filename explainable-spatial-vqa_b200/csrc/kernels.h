@@ -316,6 +316,24 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+// Encoder feed-forward block + norm2 (+ the final encoder norm) in one persistent kernel (enc_ffn_fused.cu): the
+// hidden activations stay in TMEM / shared memory.  tm_x: [M, 256] box 64 x 128 (also the residual), tm_w1: [ff, 256]
+// box 64 x 128, tm_w2: [256, ff] box 64 x 256.
+struct EncFfnParams {
+  int M = 0, n_slices = 0;  // ff = 128 * n_slices
+  const float* b1 = nullptr;
+  const float* b2 = nullptr;
+  const __nv_bfloat16* residual = nullptr;  // = the input rows, row pitch 256
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  const float* gamma2 = nullptr;  // optional second LayerNorm
+  const float* beta2 = nullptr;
+  float eps = 1e-5f;
+  __nv_bfloat16* out = nullptr;
+};
+cudaError_t launch_enc_ffn_fused(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
+                                 const EncFfnParams& p, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------
 // Persistent decode (decode_persist.cu): ALL positions x layers of a greedy decode in one launch.
 //

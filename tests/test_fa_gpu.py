@@ -71,6 +71,24 @@ def test_forward_teacher_forced_matches_golden(model):
     assert common.rel_err(logits, g["fw_logits"]) < common.LOGIT_REL_TOL
 
 
+@pytest.mark.parametrize("switch", ["B200VQA_NO_FUSED_ENC_FFN", "B200VQA_NO_FUSED_FINAL_LN"])
+def test_forward_golden_with_the_unfused_encoder_kernels(monkeypatch, switch):
+    """The encoder feed-forward block as two GEMMs through HBM / the final encoder norm as its own kernel: the same
+    golden gate as the fused default."""
+    monkeypatch.setenv(switch, "1")
+    m = common.seeded_fa().cuda()
+    g = common.load_golden("fa_nhead2.npz")
+    if not common.weights_match_golden(cpu_sd(m), g):
+        pytest.skip("seeded init differs from the golden run")
+    gen = torch.Generator().manual_seed(77)
+    torch.randn(1, 1024, 14, 14, generator=gen)
+    for s in (1, 21, 41):
+        torch.randint(0, 170, (1, s), generator=gen)
+    img2 = torch.randn(2, 1024, 14, 14, generator=gen).relu_()
+    logits = m(img2.cuda(), torch.from_numpy(g["fw_src"]).cuda(), torch.from_numpy(g["fw_tgt"]).cuda())
+    assert common.rel_err(logits, g["fw_logits"]) < common.LOGIT_REL_TOL
+
+
 def test_chain_golden_teacher_forced_cache(model):
     """run_inference_chain with the HBM cache, fed the reference's tokens: every step's logits match and the
     cache holds exactly the reference's cache (dependency pointers gather the right rows)."""

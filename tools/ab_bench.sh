@@ -14,7 +14,7 @@ try:
     k = j.get("kernels") or {}
     top = ", ".join(f"{n}={v['ms_per_step']:.3f}" for n, v in list(k.items())[:7])
     print(f"{name}: ms/step {j['ms_per_step']:.3f} serial {j['pipeline']['serial_ms_per_step']} value {j['value']/1e6:.2f}M "
-          f"e2e {j['e2e']['value']/1e6:.2f}M launches {j['gpu_launches']} | {top}")
+          f"e2e {(j.get('e2e') or {}).get('value', 0)/1e6:.2f}M launches {j['gpu_launches']} | {top}")
 except Exception as e:
     print(name, "FAILED", e)
     print(open(f"gpurun_out/ab_{name}.err").read()[-1500:])
