@@ -643,8 +643,9 @@ int run_encoder(b200vqa_handle* h, int B, const int32_t* lens, int const_len, __
       // linear1 -> ReLU -> linear2 -> + residual -> LayerNorm in one kernel: the hidden rows never leave the SM
       CUtensorMap tx, tw1, tw2;
       RC_OK(get_tmap(h, w.x1, TmapType::kBF16, uint64_t(M), kD, kD, 128, &tx));
-      RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 128, &tw1));
-      RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 256, &tw2));
+      // each CTA of the pair loads half of a weight tile: 64 of a slice's 128 hidden units / 128 of the 256 outputs
+      RC_OK(get_tmap(h, L.w1, TmapType::kBF16, uint64_t(d.dim_ff), kD, kD, 64, &tw1));
+      RC_OK(get_tmap(h, L.w2, TmapType::kBF16, kD, uint64_t(d.dim_ff), uint64_t(d.dim_ff), 128, &tw2));
       EncFfnParams fp;
       fp.M = M;
       fp.n_slices = d.dim_ff / 128;

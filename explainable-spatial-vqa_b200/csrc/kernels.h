@@ -318,7 +318,7 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
 
 // Encoder feed-forward block + norm2 (+ the final encoder norm) in one persistent kernel (enc_ffn_fused.cu): the
 // hidden activations stay in TMEM / shared memory.  tm_x: [M, 256] box 64 x 128 (also the residual), tm_w1: [ff, 256]
-// box 64 x 128, tm_w2: [256, ff] box 64 x 256.
+// box 64 x 64, tm_w2: [256, ff] box 64 x 128 (a CTA pair splits every weight tile).
 struct EncFfnParams {
   int M = 0, n_slices = 0;  // ff = 128 * n_slices
   const float* b1 = nullptr;
@@ -330,6 +330,7 @@ struct EncFfnParams {
   const float* beta2 = nullptr;
   float eps = 1e-5f;
   __nv_bfloat16* out = nullptr;
+  long long* dbg = nullptr;  // optional: wait-cycle counters of CTA 0 (B200VQA_ENC_FFN_DBG)
 };
 cudaError_t launch_enc_ffn_fused(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                                  const EncFfnParams& p, cudaStream_t stream);
