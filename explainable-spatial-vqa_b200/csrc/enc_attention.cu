@@ -330,29 +330,36 @@ enc_attention_tile_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       tma_load_2d(&tm_kv, bar_v, sV, 2 * kD + h * DH, int(row0));
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(bar_qk, 0);
-      tc_fence_after_sync();
-      const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
+    // The whole warp waits and one elected lane issues: the descriptors stay in uniform registers (see gemm_tc_kernel;
+    // the 16 N = 64 MMAs of P V take 32 cycles each, issued from vector registers ~100)
+    const bool el = elect_one();
+    const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 32768, 1024);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
+    if (el) {
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
-                  make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k != 0);
+      for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base, dq0 + uint64_t((k * 32) >> 4), dk0 + uint64_t((k * 32) >> 4), idesc_s, k != 0);
       umma_commit(bar_s);
-      // O = P V overwrites the score accumulator's first 64 columns: every thread has read its scores (twice) and
-      // published P before bar_p completes
-      const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
-      const int nkk = keys16 / 16;
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after_sync();
-      for (int kk = 0; kk < nkk; ++kk) {
-        const uint32_t pa = smem_u32(sP) + (kk / 4) * 16384 + (kk % 4) * 32;
-        const uint32_t va = smem_u32(sV) + kk * 2048;
-        umma_bf16(tmem_base, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 32768, 1024), idesc_o, kk != 0);
-      }
+    }
+    __syncwarp();
+    // O = P V overwrites the score accumulator's first 64 columns: every thread has read its scores (twice) and
+    // published P before bar_p completes
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
+    const int nkk = keys16 / 16;
+    mbar_wait(bar_v, 0);
+    mbar_wait(bar_p, 0);
+    tc_fence_after_sync();
+    if (el) {
+      for (int kk = 0; kk < nkk; ++kk)
+        umma_bf16(tmem_base, dp0 + uint64_t(((kk / 4) * 16384 + (kk % 4) * 32) >> 4), dv0 + uint64_t((kk * 2048) >> 4), idesc_o,
+                  kk != 0);
       umma_commit(bar_o);
     }
+    __syncwarp();
   } else {
     const int hc = ((warp - 2) >> 2) & 1;   // which half of the row's 32-column chunks (alternating) this thread takes
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access

@@ -88,31 +88,38 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tm_x, bar_in1, sX + kb * 16384, kb * 64, m0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- H = X . W1_slice^T : M=128, N=128, K=256
-      mbar_wait(bar_in1, 0);
-      tc_fence_after_sync();
+    // The whole warp waits and one elected lane issues: the descriptors stay in uniform registers (see gemm_tc_kernel)
+    const bool el = elect_one();
+    const uint64_t dx0 = make_smem_desc_sw128(smem_u32(sX), 16, 1024);
+    const uint64_t dw1 = make_smem_desc_sw128(smem_u32(sW1), 16, 1024);
+    const uint64_t dh0 = make_smem_desc_sw128(smem_u32(sH), 16, 1024);
+    const uint64_t dw2 = make_smem_desc_sw128(smem_u32(sW2), 16, 1024);
+    // ---- H = X . W1_slice^T : M=128, N=128, K=256
+    mbar_wait(bar_in1, 0);
+    tc_fence_after_sync();
+    if (el) {
       constexpr uint32_t idesc1 = make_idesc(kFmtBF16, 128, 128, 0, 0);
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const uint32_t a = smem_u32(sX) + (k / 4) * 16384 + (k % 4) * 32;
-        const uint32_t b = smem_u32(sW1) + (k / 4) * 16384 + (k % 4) * 32;
-        umma_bf16(d1, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc1, k != 0);
+        const uint64_t off = uint64_t(((k / 4) * 16384 + (k % 4) * 32) >> 4);
+        umma_bf16(d1, dx0 + off, dw1 + off, idesc1, k != 0);
       }
       umma_commit(bar_d1);
-      // ---- P = H . W2_slice^T : M=128, N=256, K=128
-      mbar_wait(bar_h, 0);
-      mbar_wait(bar_in2, 0);
-      tc_fence_after_sync();
+    }
+    __syncwarp();
+    // ---- P = H . W2_slice^T : M=128, N=256, K=128
+    mbar_wait(bar_h, 0);
+    mbar_wait(bar_in2, 0);
+    tc_fence_after_sync();
+    if (el) {
       constexpr uint32_t idesc2 = make_idesc(kFmtBF16, 128, 256, 0, 0);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t a = smem_u32(sH) + (k / 4) * 16384 + (k % 4) * 32;
-        const uint32_t b = smem_u32(sW2) + (k / 4) * 32768 + (k % 4) * 32;
-        umma_bf16(d2, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(b, 16, 1024), idesc2, k != 0);
-      }
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(d2, dh0 + uint64_t(((k / 4) * 16384 + (k % 4) * 32) >> 4),
+                  dw2 + uint64_t(((k / 4) * 32768 + (k % 4) * 32) >> 4), idesc2, k != 0);
       umma_commit(bar_d2);
     }
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane

@@ -209,7 +209,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (waits included) and one elected lane issues: with warp-uniform control flow the
+    // descriptors are computed in uniform registers.  Under `if (lane == 0)` every tcgen05.mma is wrapped in an
+    // elect / R2UR.BROADCAST loop - ~16 instructions and ~100 cycles per MMA, as long as a BN = 256 MMA itself and three
+    // times a BN = 64 one (the decode chain's GEMMs).
+    {
+      const bool el = elect_one();
       const uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : (p.f16 ? kFmtF16 : kFmtBF16), kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -230,8 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          if (kb == 0) B200VQA_STAMP(4);
-          if (kb == num_kb - 1) B200VQA_STAMP(5);
+          if (kb == 0 && el) B200VQA_STAMP(4);
+          if (kb == num_kb - 1 && el) B200VQA_STAMP(5);
           uint32_t sa, sb;
           if (wstat) {
             sa = smem_u32(sAring + stage * L::kStageA);
@@ -240,21 +245,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             sa = smem_u32(smem + stage * (L::kStageA + L::kStageB));
             sb = sa + L::kStageA;
           }
+          // descriptor = base + (byte offset >> 4): tiles are 1024-byte aligned, the 14-bit address field never carries
+          const uint64_t da0 = make_smem_desc_sw128(sa, 16, 1024), db0 = make_smem_desc_sw128(sb, 16, 1024);
+          if (el) {
 #pragma unroll
-          for (int k = 0; k < kKBytes / kUmmaKBytes; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaKBytes, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaKBytes, 16, 1024);
-            if (TF32) umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0);
-            else      umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            for (int k = 0; k < kKBytes / kUmmaKBytes; ++k) {
+              const uint64_t da = da0 + uint64_t((k * kUmmaKBytes) >> 4);
+              const uint64_t db = db0 + uint64_t((k * kUmmaKBytes) >> 4);
+              if (TF32) umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0);
+              else      umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == kNSt) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);        // accumulator ready for the epilogue
+        if (el) umma_commit(&acc_full[as]);        // accumulator ready for the epilogue
         if (wstat) {
           const bool last_with_w = (tile + 1 == t_end) || ((tile + 1) / tiles_m != nt);
-          if (last_with_w) umma_commit(w_empty);
+          if (last_with_w && el) umma_commit(w_empty);
         }
+        __syncwarp();
         if (++as == kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -739,41 +750,53 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   if (threadIdx.x == 0) B200VQA_STAMP(1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      pdl_wait();  // A belongs to the previous kernel until here
+    // producer + MMA issuer.  The whole warp walks the loop and one elected lane issues, so that the descriptors stay in
+    // uniform registers (see gemm_tc_kernel): 16 to 64 MMAs of 32 cycles each are issue-bound otherwise.
+    const bool el = elect_one();
+    pdl_wait();  // A belongs to the previous kernel until here
+    if (el) {
       B200VQA_STAMP(2);
       for (int kb = 0; kb < NS; ++kb) {
         mbar_expect_tx(&full_bar[kb], kBM * kKBytes);
         tma_load_2d(&tm_a, &full_bar[kb], smem + L::kOffA + kb * kBM * kKBytes, kb * 64, m0);
       }
-      constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, kLnBN, 0, 0);
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int st = kb % NS;
-        if (kb < NS) mbar_wait(&w_full[st], 0);
-        mbar_wait(&full_bar[st], uint32_t(kb / NS) & 1u);
-        tc_fence_after_sync();
+    }
+    __syncwarp();
+    constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, kLnBN, 0, 0);
+    const uint64_t da_base = make_smem_desc_sw128(smem_u32(smem + L::kOffA), 16, 1024);
+    const uint64_t db_base = make_smem_desc_sw128(smem_u32(smem + L::kOffW), 16, 1024);
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int st = kb % NS;
+      if (kb < NS) mbar_wait(&w_full[st], 0);
+      mbar_wait(&full_bar[st], uint32_t(kb / NS) & 1u);
+      tc_fence_after_sync();
+      if (el) {
         if (kb == 0) B200VQA_STAMP(4);
         if (kb == NKB - 1) B200VQA_STAMP(5);
-        const uint32_t sa = smem_u32(smem + L::kOffA + st * kBM * kKBytes);
-        const uint32_t sb = smem_u32(smem + L::kOffW + st * kLnBN * kKBytes);
+        const uint64_t da0 = da_base + uint64_t((st * kBM * kKBytes) >> 4);
+        const uint64_t db0 = db_base + uint64_t((st * kLnBN * kKBytes) >> 4);
 #pragma unroll
         for (int k = 0; k < kKBytes / kUmmaKBytes; ++k)
-          umma_bf16(tmem_base, make_smem_desc_sw128(sa + k * kUmmaKBytes, 16, 1024),
-                    make_smem_desc_sw128(sb + k * kUmmaKBytes, 16, 1024), idesc, (kb | k) != 0);
-        if constexpr (NKB > NS) {
-          if (kb + NS < NKB) umma_commit(&empty_bar[st]);
-          // refill the previous k-block's stage (its MMAs retire while this k-block's run): k-block kb - 1 + NS
-          if (kb >= 1 && kb - 1 + NS < NKB) {
-            const int sp = (kb - 1) % NS, nk = kb - 1 + NS;
-            mbar_wait(&empty_bar[sp], uint32_t((kb - 1) / NS) & 1u);
+          umma_bf16(tmem_base, da0 + uint64_t((k * kUmmaKBytes) >> 4), db0 + uint64_t((k * kUmmaKBytes) >> 4), idesc,
+                    (kb | k) != 0);
+      }
+      __syncwarp();
+      if constexpr (NKB > NS) {
+        if (kb + NS < NKB && el) umma_commit(&empty_bar[st]);
+        // refill the previous k-block's stage (its MMAs retire while this k-block's run): k-block kb - 1 + NS
+        if (kb >= 1 && kb - 1 + NS < NKB) {
+          const int sp = (kb - 1) % NS, nk = kb - 1 + NS;
+          mbar_wait(&empty_bar[sp], uint32_t((kb - 1) / NS) & 1u);
+          if (el) {
             mbar_expect_tx(&full_bar[sp], (kBM + kLnBN) * kKBytes);
             tma_load_2d(&tm_a, &full_bar[sp], smem + L::kOffA + sp * kBM * kKBytes, nk * 64, m0);
             tma_load_2d(&tm_w, &full_bar[sp], smem + L::kOffW + sp * kLnBN * kKBytes, nk * 64, n0);
           }
+          __syncwarp();
         }
       }
-      umma_commit(acc_full);
     }
+    if (el) umma_commit(acc_full);
     __syncwarp();
     cluster_wait_acquire();
   } else {
