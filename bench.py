@@ -360,14 +360,18 @@ def run_ours(args):
             img_host.copy_(img)
             q_host = q_cpu.pin_memory()
 
+        # fp32 host features; with enough host cores per rank the library rounds them to fp16 on host threads before
+        # they cross PCIe ("auto", VQAModel.resolve_upload) - conversion inside the timed region
+        e2e_upload = iqap.VQAModel.resolve_upload(args.e2e_upload)
+
         def step_e2e():
             if depth <= 1:
-                return model.forward_host(img_host, q_host, chunk=args.e2e_chunk)
-            return model.submit_host(img_host, q_host, chunk=args.e2e_chunk, depth=depth)
+                return model.forward_host(img_host, q_host, chunk=args.e2e_chunk, upload=e2e_upload)
+            return model.submit_host(img_host, q_host, chunk=args.e2e_chunk, depth=depth, upload=e2e_upload)
 
         drain_host = model.drain_host
 
-        h2d = B * 196 * 1024 * 4 + B * 46 * 8
+        h2d = B * 196 * 1024 * (2 if e2e_upload == "fp16" else 4) + B * 46 * 8
         d2h = B * 32 * 4 + B * T_PROG * 8
     else:
         from explainable_spatial_vqa_b200 import inference_transformer_full_annotation_new as fa
@@ -670,7 +674,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": None if e2e_value is None else
                    {"value": e2e_value, "unit": "program-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / max(1, args.steps // 2)},
+                    "ms_per_step": ms_e2e / max(1, args.steps // 2),
+                    **({"upload": e2e_upload, "host_input_bytes_per_step": B * 196 * 1024 * 4 + B * 46 * 8}
+                       if args.workload == "iqap" else {})},
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "context": extra,
         }
@@ -692,6 +698,9 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=None,
                     help="independent batches in flight (1 = strictly serial steps); default 2 (iqap) / 3 (fa, e2e)")
     ap.add_argument("--blocks", type=int, default=5, help="timed K-step blocks (the first gives `value`; the median is reported too)")
+    ap.add_argument("--e2e-upload", default="auto", choices=["auto", "fp32", "fp16"],
+                    help="IQAP e2e: how the fp32 host features cross PCIe (auto: fp16 rounded on host threads when the rank "
+                         "has >= 8 CPUs to itself)")
     ap.add_argument("--fa-host-chunk", type=int, default=None,
                     help="questions per sub-batch of the FA host-buffer call (default: the whole batch when steps are "
                          "pipelined - uploads of consecutive steps queue on one ingest stream - else 1024)")

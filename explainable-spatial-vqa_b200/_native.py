@@ -117,6 +117,8 @@ SIGNATURES = {
     "b200vqa_dbg_gemm_check": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b200vqa_dbg_workspace": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200vqa_host_f32_to_f16": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
+    "b200vqa_set_host_upload": (C.c_int, [_vp, C.c_int]),
     "b200vqa_dbg_mem_attn": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
 }
 
@@ -201,6 +203,9 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._lib.b200vqa_launch_count(self._h))
+
+    def set_host_upload(self, fp16: bool) -> None:
+        check(self._lib.b200vqa_set_host_upload(self._h, 1 if fp16 else 0), "b200vqa_set_host_upload")
 
     def set_start_token(self, token: int) -> None:
         check(self._lib.b200vqa_set_start_token(self._h, int(token)), "b200vqa_set_start_token")

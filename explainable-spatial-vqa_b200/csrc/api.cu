@@ -166,6 +166,12 @@ struct b200vqa_handle {
   bool no_ln_cluster = false;  // B200VQA_NO_LN_CLUSTER=1: decode LayerNorm GEMMs on the persistent kernel (A/B runs)
   bool nvtx = false;                  // B200VQA_NVTX=1
   int iqap_start_token = 1;           // Config.SPECIAL_TOKEN_ID (IQAP:24,205); b200vqa_set_start_token
+  // b200vqa_set_host_upload(1): fp32 host features are rounded to fp16 on host threads before they cross PCIe
+  bool host_upload_f16 = false;
+  void* pin16[2] = {nullptr, nullptr};  // pinned fp16 staging of one chunk each
+  size_t pin16_bytes = 0;
+  cudaEvent_t ev_pin[2] = {nullptr, nullptr};  // the upload out of pin16[i] has completed
+  bool pin_pending[2] = {false, false};
   // persistent decode kernel (decode_persist.cu): all positions x layers in one launch
   bool decode_persist = false;        // B200VQA_DECODE=persist|chain
   int persist_stagger_us = 0;         // B200VQA_PERSIST_STAGGER_US: start delay of odd question tiles
@@ -1308,6 +1314,10 @@ B200VQA_API void b200vqa_destroy(b200vqa_handle* h) {
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+    if (h->pin16[i]) cudaFreeHost(h->pin16[i]);
+  }
   if (h->ev_tables) cudaEventDestroy(h->ev_tables);
   if (h->h_tables) cudaFreeHost(h->h_tables);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -1328,6 +1338,13 @@ B200VQA_API size_t b200vqa_workspace_bytes(const b200vqa_handle* h, int B) {
 }
 
 B200VQA_API uint64_t b200vqa_launch_count(const b200vqa_handle* h) { return h ? h->launches : 0; }
+
+B200VQA_API int b200vqa_set_host_upload(b200vqa_handle* h, int mode) {
+  B200VQA_REQUIRE(h != nullptr, "handle is NULL");
+  B200VQA_REQUIRE(mode == 0 || mode == 1, "upload mode %d: 0 = bytes as given, 1 = fp32 rounded to fp16 on the host", mode);
+  h->host_upload_f16 = mode == 1;
+  return B200VQA_OK;
+}
 
 B200VQA_API int b200vqa_set_start_token(b200vqa_handle* h, int start_token) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
@@ -1511,12 +1528,16 @@ B200VQA_API int b200vqa_iqap_decode(b200vqa_handle* h, const float* memory, int 
 static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16, const int64_t* h_q, int B,
                                   int program_len, float* h_answer, int64_t* h_programs, int chunk, void* stream,
                                   bool sync) {
-  const size_t esz = f16 ? 2 : 4;  // bytes per feature element
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_IQAP, "handle was not created for the IQAP model");
   B200VQA_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return B200VQA_OK;
   B200VQA_REQUIRE(h_img && h_q && h_answer && h_programs, "a required buffer is NULL");
+  // fp32 features rounded to fp16 on the host (b200vqa_set_host_upload): half the bytes on the wire, and the device path
+  // of a caller-provided fp16 feature store from there on
+  const bool convert = !f16 && h->host_upload_f16;
+  if (convert) f16 = true;
+  const size_t esz = f16 ? 2 : 4;  // bytes per feature element on the device
   RC_OK(check_decode_len(h, program_len));
   RC_OK(set_device(h));
   const auto& d = h->d;
@@ -1558,6 +1579,24 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16
   float* d_ans = reinterpret_cast<float*>(p); p += ans_b;
   int64_t* d_prog = reinterpret_cast<int64_t*>(p);
 
+  const size_t per_q = size_t(d.n_img_tokens) * d.img_feat_dim;  // feature elements per question
+  if (convert) {
+    const size_t pin_b = size_t(chunk) * per_q * 2;
+    if (h->pin16_bytes < pin_b) {
+      for (int i = 0; i < 2; ++i) {
+        if (h->pin_pending[i]) B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_pin[i]));
+        h->pin_pending[i] = false;
+        if (h->pin16[i]) B200VQA_CUDA_OK(cudaFreeHost(h->pin16[i]));
+        h->pin16[i] = nullptr;
+      }
+      h->pin16_bytes = 0;
+      for (int i = 0; i < 2; ++i) B200VQA_CUDA_OK(cudaMallocHost(&h->pin16[i], pin_b));
+      h->pin16_bytes = pin_b;
+    }
+    for (int i = 0; i < 2; ++i)
+      if (!h->ev_pin[i]) B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming));
+  }
+
   // the copy stream must not overwrite staging that earlier, still unsynchronised work of `s` may read (a previous
   // *_host_async call on this handle): everything enqueued on `s` so far precedes the first upload
   B200VQA_CUDA_OK(cudaEventRecord(h->ev_free[0], s));
@@ -1566,11 +1605,23 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16
   for (int b0 = 0; b0 < B; b0 += chunk, ++it) {
     const int nb = std::min(chunk, B - b0);
     const int slot = it & 1;
+    const void* src = static_cast<const uint8_t*>(h_img) + size_t(b0) * per_q * (convert ? 4 : esz);
+    if (convert) {
+      // the host rounds chunk `it` while chunk it - 1 is on the wire; the staging is free once its own upload (two
+      // chunks ago, or a previous call's) has completed
+      if (h->pin_pending[slot]) {
+        B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_pin[slot]));
+        h->pin_pending[slot] = false;
+      }
+      host_f32_to_f16(static_cast<const float*>(src), h->pin16[slot], size_t(nb) * per_q, 0);
+      src = h->pin16[slot];
+    }
     if (it >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));
-    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot],
-                                    static_cast<const uint8_t*>(h_img) + size_t(b0) * d.n_img_tokens * d.img_feat_dim * esz,
-                                    size_t(nb) * d.n_img_tokens * d.img_feat_dim * esz, cudaMemcpyHostToDevice,
-                                    h->copy_stream));
+    B200VQA_CUDA_OK(cudaMemcpyAsync(d_img[slot], src, size_t(nb) * per_q * esz, cudaMemcpyHostToDevice, h->copy_stream));
+    if (convert) {
+      B200VQA_CUDA_OK(cudaEventRecord(h->ev_pin[slot], h->copy_stream));
+      h->pin_pending[slot] = true;
+    }
     B200VQA_CUDA_OK(cudaMemcpyAsync(d_q[slot], h_q + size_t(b0) * d.max_q_len,
                                     size_t(nb) * d.max_q_len * sizeof(int64_t), cudaMemcpyHostToDevice,
                                     h->copy_stream));

@@ -316,6 +316,10 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+// Host side (host_convert.cu): fp32 -> fp16 (round to nearest even) on a pool of worker threads; dst 32-byte aligned.
+void host_f32_to_f16(const float* src, void* dst, size_t n, int threads);
+int host_convert_threads();
+
 // Encoder feed-forward block + norm2 (+ the final encoder norm) in one persistent kernel (enc_ffn_fused.cu): the
 // hidden activations stay in TMEM / shared memory.  tm_x: [M, 256] box 64 x 128 (also the residual), tm_w1: [ff, 256]
 // box 64 x 64, tm_w2: [256, ff] box 64 x 128 (a CTA pair splits every weight tile).

@@ -217,11 +217,27 @@ class VQAModel(nn.Module):
                                                     None, None, nat.stream_ptr(mem.device)), "b200vqa_iqap_decode")
         return programs
 
+    @staticmethod
+    def resolve_upload(upload):
+        """"fp32": the feature bytes cross PCIe as given (results bit-identical to `forward`).  "fp16": the library
+        rounds them to fp16 on host threads while the previous chunk is on the wire - half the bytes (the upload, not
+        the GPU, bounds the host-buffer calls: 803 KB per question), results bit-identical to passing `features.half()`.
+        "auto": "fp16" when this process has at least 8 CPUs to itself (CPUs it may run on / ranks on the node)."""
+        if upload == "auto":
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+            return "fp16" if cpus // ranks >= 8 else "fp32"
+        if upload not in ("fp32", "fp16"):
+            raise ValueError('upload must be "fp32", "fp16" or "auto"')
+        return upload
+
     @torch.no_grad()
-    def forward_host(self, image_features_cpu, questions_cpu, chunk=512):
+    def forward_host(self, image_features_cpu, questions_cpu, chunk=512, upload="fp32"):
         """End-to-end call with HOST tensors (pinned for full PCIe speed): upload, compute and download are
-        pipelined inside the library; returns CPU tensors.  This is what bench.py times as `e2e`."""
+        pipelined inside the library; returns CPU tensors.  `upload`: see `resolve_upload`.  This is what bench.py
+        times as `e2e`."""
         h = self._native()
+        h.set_host_upload(self.resolve_upload(upload) == "fp16")
         f16 = image_features_cpu.dtype == torch.float16   # fp16 feature store: half the PCIe bytes
         img = image_features_cpu.to(torch.float16 if f16 else torch.float32).contiguous()
         q = questions_cpu.to(torch.int64).contiguous()
@@ -336,12 +352,13 @@ class VQAModel(nn.Module):
         return answer, programs
 
     @torch.no_grad()
-    def submit_host(self, image_features_cpu, questions_cpu, chunk=512, depth=2):
+    def submit_host(self, image_features_cpu, questions_cpu, chunk=512, depth=2, upload="fp32"):
         """`forward_host` without the final synchronisation, on a round-robin slot: the upload of this batch overlaps
         the decode tail of the previous one.  Returns pinned CPU tensors that are valid after `drain_host()`."""
         slot = 1 + self._next_slot % depth
         self._next_slot += 1
         h = self._native(slot)
+        h.set_host_upload(self.resolve_upload(upload) == "fp16")
         st = self._pool.stream(slot)
         img = image_features_cpu.to(torch.float32).contiguous()
         q = questions_cpu.to(torch.int64).contiguous()

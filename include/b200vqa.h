@@ -372,6 +372,18 @@ B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const i
  * 10 tok (int64 [cap, 65]).  Used by tests / tools to compare the persistent decode kernel with the per-kernel chain. */
 B200VQA_API int b200vqa_dbg_workspace(b200vqa_handle* h, int which, void* dst, size_t dst_bytes, size_t* bytes);
 
+/* Upload mode of b200vqa_iqap_forward_host[_async] for fp32 host features: 0 (default) = the bytes as given, 1 = rounded
+ * to fp16 (nearest even) on host threads, chunk by chunk, while the previous chunk is on the wire - half the PCIe bytes,
+ * then the device path of a caller-provided fp16 feature store (b200vqa_iqap_forward_host_f16): results equal those of
+ * that call on the rounded features bit for bit.  Pays when the process has host cores to spare (>= ~8). */
+B200VQA_API int b200vqa_set_host_upload(b200vqa_handle* h, int mode);
+
+/* Host helper (no GPU involved): n fp32 values -> fp16, round to nearest even (what torch's .half() gives), on `threads`
+ * host threads (<= 0: every CPU this process may run on, at most 32).  dst must be 32-byte aligned.  The *_host entry
+ * points use it for the "fp16" upload mode (b200vqa_set_host_upload): the feature rows that the reference uploads as
+ * fp32 per sample (IQAP:288-296) cross PCIe at half the size. */
+B200VQA_API int b200vqa_host_f32_to_f16(const float* src, void* dst, long long n, int threads);
+
 #ifdef __cplusplus
 }
 #endif

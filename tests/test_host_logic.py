@@ -206,3 +206,28 @@ def test_cpulist_parsing_and_numa_binding_is_harmless_without_a_gpu():
     assert sharding._parse_cpulist("") == []
     info = sharding.bind_to_gpu_numa(0)   # no GPU here: reports the failure instead of raising
     assert info["bound"] is False
+
+
+def test_host_fp32_to_fp16_conversion_is_numpy_exact():
+    """b200vqa_host_f32_to_f16 (the "fp16" upload mode of the host entry points): round to nearest even like numpy /
+    torch .half(), including ties, subnormals, overflow to inf and the scalar tail; any thread count."""
+    import ctypes as C
+
+    import numpy as np
+
+    from explainable_spatial_vqa_b200 import _native as nat
+
+    rng = np.random.default_rng(5)
+    n = (1 << 19) + 37  # several pool tasks + a tail that is not a multiple of the vector width
+    x = (rng.standard_normal(n) * np.exp(rng.uniform(-14, 12, n))).astype(np.float32)
+    x[:8] = [0.0, -0.0, 65504.0, 65520.0, 1e-8, 5.96e-8, 1.0009765625, 2049.0]  # max, overflow tie, subnormals, ties
+    want = x.astype(np.float16)
+    lib = nat.lib()
+    for threads in (1, 3, 0):
+        raw = np.empty(n + 16, dtype=np.uint16)
+        off = (-raw.ctypes.data % 32) // 2  # 32-byte aligned start inside the buffer
+        out = raw[off:off + n]
+        assert out.ctypes.data % 32 == 0
+        nat.check(lib.b200vqa_host_f32_to_f16(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, threads), "convert")
+        assert np.array_equal(out.view(np.float16).view(np.uint16), want.view(np.uint16)), threads
+    assert lib.b200vqa_host_f32_to_f16(x.ctypes.data_as(C.c_void_p), C.c_void_p(raw.ctypes.data + 2), 4, 1) < 0  # misaligned

@@ -108,6 +108,27 @@ def test_chunked_batch_and_host_entry(model):
     assert torch.equal(a_small, a_dev[520:530]) and torch.equal(p_small, p_dev[520:530])
 
 
+def test_host_entry_with_fp16_upload(model):
+    """upload="fp16": the library rounds the fp32 host features to fp16 on host threads (chunk by chunk, staging reused
+    across chunks and calls) - bit-identical to handing it `features.half()`, within the oracle gate of the fp32 call."""
+    img, q = orc.iqap_inputs(300, seed=12)
+    a16, p16 = model.forward_host(img.half().pin_memory(), q.pin_memory(), chunk=64)
+    for _ in range(2):
+        a_up, p_up = model.forward_host(img.pin_memory(), q.pin_memory(), chunk=64, upload="fp16")
+        assert torch.equal(a_up, a16) and torch.equal(p_up, p16)
+    a32, _ = model.forward_host(img.pin_memory(), q.pin_memory(), chunk=64)  # back to the exact mode on the same handle
+    assert torch.equal(a32, model(img.cuda(), q.cuda())[0].cpu())
+    assert common.rel_err(a_up, a32) < common.LOGIT_REL_TOL
+    # pipelined submissions on two slots
+    outs = [model.submit_host(img[i * 100:(i + 1) * 100].clone().pin_memory(), q[i * 100:(i + 1) * 100].clone().pin_memory(),
+                              chunk=32, depth=2, upload="fp16") for i in range(3)]
+    model.drain_host()
+    assert torch.equal(torch.cat([o[0] for o in outs]), a16) and torch.equal(torch.cat([o[1] for o in outs]), p16)
+    assert model.resolve_upload("auto") in ("fp16", "fp32")
+    with pytest.raises(ValueError):
+        model.resolve_upload("bf16")
+
+
 def test_state_dict_roundtrip_and_refresh(model):
     m2 = common.seeded_iqap(seed=5).cuda()
     img, q = orc.iqap_inputs(2, seed=1)
