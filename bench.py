@@ -506,7 +506,10 @@ def run_ours(args):
     if args.skip_host_e2e:  # a job too large to hold a second, pinned copy of its features on the host of an 8-GPU box
         ms_e2e, e2e_value = float("nan"), None
     else:
-        ms_e2e, _ = timed(step_e2e, max(1, args.steps // 2), max(3, depth), drain_host)
+        # as many warm-up steps as timed ones: every result buffer of the timed loop (pinned host tensors, kept alive until
+        # the drain) then comes out of torch's pinned-memory cache - a cudaHostAlloc inside the loop costs the host
+        # thread 5-15 ms, and with the fp16 upload mode the host thread is the critical path
+        ms_e2e, _ = timed(step_e2e, max(1, args.steps // 2), max(3, depth, args.steps // 2), drain_host)
         e2e_value = world * units_per_step * max(1, args.steps // 2) / (ms_e2e * 1e-3)
 
     # live per-kernel-class timing (CUDA events on the launch stream) over a few extra steps -> roofline

@@ -13,6 +13,7 @@
 //   kc[l], vc[l]       bf16 [cap, T, 256]    decoder self-attention KV cache
 //   d*                 bf16 [cap, *]         one decode position per question
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1609,11 +1610,23 @@ static int iqap_forward_host_impl(b200vqa_handle* h, const void* h_img, bool f16
     if (convert) {
       // the host rounds chunk `it` while chunk it - 1 is on the wire; the staging is free once its own upload (two
       // chunks ago, or a previous call's) has completed
+      const bool trace = getenv("B200VQA_HOST_TRACE") != nullptr;
+      const auto t0 = std::chrono::steady_clock::now();
       if (h->pin_pending[slot]) {
         B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_pin[slot]));
         h->pin_pending[slot] = false;
       }
+      const auto t1 = std::chrono::steady_clock::now();
       host_f32_to_f16(static_cast<const float*>(src), h->pin16[slot], size_t(nb) * per_q, 0);
+      if (trace) {
+        const auto t2 = std::chrono::steady_clock::now();
+        static const auto t_first = t0;
+        fprintf(stderr,
+                "b200vqa host upload: t = %.2f ms, chunk %d (%d questions): waited %.2f ms for the staging, converted in %.2f ms\n",
+                std::chrono::duration<double, std::milli>(t0 - t_first).count(), it, nb,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(t2 - t1).count());
+      }
       src = h->pin16[slot];
     }
     if (it >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));

@@ -21,6 +21,12 @@
 namespace b200vqa {
 namespace {
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int kAttnThreads = 64 + 512;  // TMA warp, MMA warp, 2 tiles x 8 softmax warps
 constexpr int kKeysMax = 256;
 
@@ -376,14 +382,20 @@ enc_attention_tile_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     __syncwarp();
     tc_fence_after_sync();
     const int nchunks = (len + 31) / 32;
+    const int nfull = len / 32;  // chunks without masked keys: the per-element length test is paid by the last one only
     float mx = -INFINITY;
     for (int c = hc; c < nchunks; c += 2) {
       uint32_t v[32];
       tmem_ld32(taddr + c * 32, v);
       tmem_ld_wait();
+      if (c < nfull) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
     }
     mine->x = mx;
     named_bar_sync(pair_bar, 64);
@@ -395,14 +407,21 @@ enc_attention_tile_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       tmem_ld32(taddr + c * 32, v);
       tmem_ld_wait();
       uint32_t o[16];
+      const bool full = c < nfull;
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float p0 = (c * 32 + j < len) ? exp2f(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
-        const float p1 = (c * 32 + j + 1 < len) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - mxs) : 0.f;
-        const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-        const float2 pr = __bfloat1622float2(pb);
-        sum += pr.x + pr.y;  // normalise by what the tensor core will actually sum
-        o[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        // scores are <= the row maximum: the argument is <= 0, ex2.approx needs no range handling
+        float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mxs));
+        float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mxs));
+        if (!full) {
+          p0 = (c * 32 + j < len) ? p0 : 0.f;
+          p1 = (c * 32 + j + 1 < len) ? p1 : 0.f;
+        }
+        const uint32_t pb = pack_bf16x2(p0, p1);
+        // normalise by what the tensor core will actually sum: the bf16-rounded weights (a bf16 is the upper half of
+        // the fp32 with the same value)
+        sum += __uint_as_float(pb << 16) + __uint_as_float(pb & 0xffff0000u);
+        o[j >> 1] = pb;
       }
       uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
 #pragma unroll

@@ -1,12 +1,14 @@
-timeout 200 python -m pytest tests/test_iqap_gpu.py -m gpu -x -q 2>&1 | tail -2
-for m in auto fp32; do python bench.py --blocks 2 --no-cpu-baseline --e2e-upload $m > gpurun_out/e2e_$m.json 2> gpurun_out/e2e_$m.err; done
-python bench.py --blocks 2 --no-cpu-baseline --pipeline-depth 3 > gpurun_out/e2e_auto_d3.json 2>&1
-python bench.py --blocks 2 --no-cpu-baseline --pipeline-depth 1 > gpurun_out/e2e_auto_d1.json 2>&1
+for cfg in "16 1024" "8 1024" "4 1024" "8 512" "12 512" "16 512" "6 512"; do set -- $cfg
+B200VQA_HOST_THREADS=$1 python bench.py --steps 20 --blocks 1 --no-cpu-baseline --e2e-chunk $2 > gpurun_out/up_$1_$2.json 2>/dev/null
+python - "$1" "$2" <<PY
+import json, sys
+j=json.loads([l for l in open(f"gpurun_out/up_{sys.argv[1]}_{sys.argv[2]}.json") if l.startswith("{")][-1])
+print("threads", sys.argv[1], "chunk", sys.argv[2], "e2e", round(j["e2e"]["value"]), "ms", round(j["e2e"]["ms_per_step"],2), j["e2e"]["upload"])
+PY
+done
+python bench.py --steps 20 --blocks 1 --no-cpu-baseline --e2e-upload fp32 > gpurun_out/up_fp32.json 2>/dev/null
 python - <<PY
 import json
-for n in ["e2e_auto","e2e_fp32","e2e_auto_d3","e2e_auto_d1"]:
-    try:
-        j=json.loads([l for l in open(f"gpurun_out/{n}.json") if l.startswith("{")][-1])
-        print(n, "ms/step", round(j["ms_per_step"],3), "value", round(j["value"]), "e2e", j["e2e"])
-    except Exception as e: print(n, "FAILED", e)
+j=json.loads([l for l in open("gpurun_out/up_fp32.json") if l.startswith("{")][-1])
+print("fp32", "e2e", round(j["e2e"]["value"]), "ms", round(j["e2e"]["ms_per_step"],2))
 PY

@@ -36,3 +36,33 @@ if torch.cuda.is_available():
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / 4
         print(f"H2D {name}: {1e3 * dt:.2f} ms per chunk = {h.numel() * h.element_size() / dt / 1e9:.1f} GB/s")
+
+# ---- the two together: does the conversion starve the DMA engine of host memory bandwidth?
+if torch.cuda.is_available():
+    import threading
+
+    for threads in (4, 8, 12, 16):
+        stop = False
+        done = [0]
+
+        def conv_loop():
+            while not stop:
+                nat.check(lib.b200vqa_host_f32_to_f16(src.data_ptr(), dst.data_ptr(), n, threads), "convert")
+                done[0] += 1
+
+        h16 = pin(torch.empty(n, dtype=torch.float16))
+        th = threading.Thread(target=conv_loop)
+        th.start()
+        time.sleep(0.05)
+        torch.cuda.synchronize()
+        c0 = done[0]
+        t0 = time.perf_counter()
+        for _ in range(8):
+            d16.copy_(h16, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 8
+        c1 = done[0]
+        stop = True
+        th.join()
+        print(f"conversion on {threads:2d} threads running: H2D fp16 {1e3 * dt:.2f} ms per chunk = {h16.numel() * 2 / dt / 1e9:.1f} GB/s; "
+              f"conversions completed meanwhile: {c1 - c0} ({(c1 - c0) * n * 4 / (8 * dt) / 1e9:.0f} GB/s of fp32 in)", flush=True)
