@@ -340,25 +340,32 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
     return l > kLP ? kLP : (l < 1 ? 1 : l);  // producer and consumer must agree on >= 1 tile per question
   };
 
-  // Producer cursor (thread 0): the CTA walks questions blockIdx.x, + gridDim.x, ... and the tiles inside each; loads
-  // run kMemStages - 1 tiles ahead of the consumers across question boundaries.
+  // Producer cursor: the CTA walks questions blockIdx.x, + gridDim.x, ... and the tiles inside each; loads run
+  // kMemStages - 1 tiles ahead of the consumers across question boundaries.  EVERY thread keeps the cursor (it only
+  // ever changes in CTA-uniform control flow, so the compiler keeps it in uniform registers) and one elected lane of
+  // warp 0 issues: from a single thread's vector registers every TMA / bulk-copy costs an elect / R2UR.BROADCAST loop
+  // of ~100 cycles, four to eight of them per tile on the warp the whole CTA waits for at the next barrier.
   int pq = blockIdx.x, pt = 0, p_len = 0, issued = 0, p_questions = 0;
+  const bool p_el = warp == 0 ? elect_one() : false;
   auto issue_next = [&]() {
     if (pq < p.B) {
-      if (pt == 0) p_len = len_of(pq);
+      if (pt == 0) p_len = __shfl_sync(0xffffffffu, len_of(pq), 0);  // (tells the compiler the value is warp-uniform)
       const int st = issued % kMemStages;
       const uint32_t dst = ring_u32 + st * kMemStageBytes;
       const int row = pq * int(p.rows_per_q) + pt * kMemTileRows;
-      mbar_expect_tx(&full_bar[st], kMemStageBytes + (pt == 0 ? NH * kD * 2 : 0));
-      if (pt == 0) {
+      if (warp == 0 && p_el) {
+        mbar_expect_tx(&full_bar[st], kMemStageBytes + (pt == 0 ? NH * kD * 2 : 0));
+        if (pt == 0) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h)
-          bulk_load_u32(smem_u32(&s_q[p_questions & 1][h][0]), p.qp + (size_t(pq) * NH + h) * kD, kD * 2,
-                        &full_bar[st]);
-        ++p_questions;
+          for (int h = 0; h < NH; ++h)
+            bulk_load_u32(smem_u32(&s_q[p_questions & 1][h][0]), p.qp + (size_t(pq) * NH + h) * kD, kD * 2,
+                          &full_bar[st]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) tma_load_2d_u32(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row);
       }
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) tma_load_2d_u32(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row);
+      __syncwarp();
+      if (pt == 0) ++p_questions;
       if ((++pt) * kMemTileRows >= p_len) {
         pt = 0;
         pq += gridDim.x;
@@ -366,8 +373,7 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
     }
     ++issued;
   };
-  if (threadIdx.x == 0)
-    for (int i = 0; i < kMemStages - 1; ++i) issue_next();
+  for (int i = 0; i < kMemStages - 1; ++i) issue_next();
   const float sl2 = rsqrtf(float(kD / NH)) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e): softmax via exp2
   int consumed = 0, questions = 0;
 
@@ -388,7 +394,7 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
 
     for (int i = 0; i < n_tiles; ++i) {
       __syncthreads();  // everyone is done with the previous tile: its stage, s_part, s_p and s_alpha are free
-      if (threadIdx.x == 0) issue_next();
+      issue_next();
       const int st = consumed % kMemStages;
       mbar_wait(&full_bar[st], uint32_t(consumed / kMemStages) & 1u);
       const uint32_t tile_u32 = ring_u32 + st * kMemStageBytes;

@@ -328,13 +328,14 @@ enc_attention_tile_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // uniform control flow up to here: the TMA operands come from uniform registers
       mbar_expect_tx(bar_qk, 32768 + 16384);
       tma_load_2d(&tm_kv, bar_qk, sK, kD + h * DH, int(row0));
       tma_load_2d(&tm_q, bar_qk, sQ, h * DH, int(row0) + t * 128);
       mbar_expect_tx(bar_v, 32768);
       tma_load_2d(&tm_kv, bar_v, sV, 2 * kD + h * DH, int(row0));
     }
+    __syncwarp();
   } else if (warp == 1) {
     // The whole warp waits and one elected lane issues: the descriptors stay in uniform registers (see gemm_tc_kernel;
     // the 16 N = 64 MMAs of P V take 32 cycles each, issued from vector registers ~100)

@@ -240,14 +240,16 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   // (setmaxnreg sits at the top of each role's branch: that is where ptxas takes the branch's register budget from)
   if (warp == 0) {
     setmaxnreg_dec<40>();
-    if (lane == 0) {
+    {
+      // (whole warp walks the loop, one elected lane issues: the TMA operands stay in uniform registers)
+      const bool el = elect_one();
       uint32_t u = 0, t = 0;
       const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
       long long w_empty = 0;
       auto slot_wait = [&]() -> uint32_t {
         const uint32_t slot = u % kEfRing;
         ef_wait_t(&ring_empty[slot], ((u / kEfRing) & 1) ^ 1, w_empty, dbg);
-        if (leader) mbar_expect_tx(&ring_full[slot], 2 * kEfUnit);
+        if (leader && el) mbar_expect_tx(&ring_full[slot], 2 * kEfUnit);
         ++u;
         return slot;
       };
@@ -255,20 +257,27 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       auto put_w1 = [&](int j, int half) {
         const uint32_t slot = slot_wait();
         const int row = j * 128 + int(rank) * 64;
-        tma_load_2d_pair(&tm_w1, &ring_full[slot], sRing + slot * kEfUnit, (2 * half) * 64, row);
-        tma_load_2d_pair(&tm_w1, &ring_full[slot], sRing + slot * kEfUnit + 8192, (2 * half + 1) * 64, row);
+        if (el) {
+          tma_load_2d_pair(&tm_w1, &ring_full[slot], sRing + slot * kEfUnit, (2 * half) * 64, row);
+          tma_load_2d_pair(&tm_w1, &ring_full[slot], sRing + slot * kEfUnit + 8192, (2 * half + 1) * 64, row);
+        }
+        __syncwarp();
       };
       // GEMM2 unit: this CTA's 128 of the 256 output columns x 64 hidden units
       auto put_w2 = [&](int j, int half) {
         const uint32_t slot = slot_wait();
-        tma_load_2d_pair(&tm_w2, &ring_full[slot], sRing + slot * kEfUnit, j * 128 + half * 64, int(rank) * 128);
+        if (el) tma_load_2d_pair(&tm_w2, &ring_full[slot], sRing + slot * kEfUnit, j * 128 + half * 64, int(rank) * 128);
+        __syncwarp();
       };
       for (int sup = sup0; sup < n_sup; sup += sup_step, ++t) {
         ef_wait(x_free, (t & 1) ^ 1);
-        if (leader) mbar_expect_tx(x_full, 2 * 65536);
+        if (el) {
+          if (leader) mbar_expect_tx(x_full, 2 * 65536);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d_pair(&tm_x, x_full, sX + kb * 16384, kb * 64, sup * 256 + int(rank) * 128);
+          for (int kb = 0; kb < 4; ++kb)
+            tma_load_2d_pair(&tm_x, x_full, sX + kb * 16384, kb * 64, sup * 256 + int(rank) * 128);
+        }
+        __syncwarp();
         // the order the MMA thread consumes them in
         put_w1(0, 0);
         put_w1(0, 1);
@@ -281,7 +290,7 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           put_w2(j, 1);
         }
       }
-      if (dbg) p.dbg[15] = w_empty;
+      if (dbg && lane == 0) p.dbg[15] = w_empty;
     }
   } else if (warp == 1) {
     setmaxnreg_dec<40>();

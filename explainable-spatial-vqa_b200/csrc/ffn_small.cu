@@ -75,7 +75,9 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const uint32_t d2 = tmem_base + 128;  // 256 columns
 
   if (warp == 0) {
-    if (lane == 0) {
+    // (whole warp, one elected lane issues: the TMA operands stay in uniform registers - see gemm_tc_kernel's producer)
+    const bool el = elect_one();
+    if (el) {
       // weights first (independent of the previous kernel), activations after the dependency wait
       mbar_expect_tx(bar_in1, L::kX + L::kW1);
 #pragma unroll
@@ -83,10 +85,14 @@ ffn_partial_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_expect_tx(bar_in2, L::kW2);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) tma_load_2d(&tm_w2, bar_in2, sW2 + kb * 32768, slice * kSlice + kb * 64, 0);
-      pdl_wait();
+    }
+    __syncwarp();
+    pdl_wait();
+    if (el) {
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tm_x, bar_in1, sX + kb * 16384, kb * 64, m0);
     }
+    __syncwarp();
   } else if (warp == 1) {
     // The whole warp waits and one elected lane issues: the descriptors stay in uniform registers (see gemm_tc_kernel)
     const bool el = elect_one();

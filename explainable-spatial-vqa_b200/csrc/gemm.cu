@@ -165,7 +165,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp walks the loop, one elected lane issues: UTMALDG takes its operands from uniform registers too, and
+    // under `if (lane == 0)` every load costs an elect / R2UR.BROADCAST loop of ~100 cycles)
+    {
+      const bool el = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1;
@@ -173,13 +176,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (wstat && t_begin < t_end) {
         // weights do not depend on the previous kernel: fetch the first W tile before waiting for it
         const int nt = t_begin / tiles_m;
-        mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, nt * BN);
+        if (el) {
+          mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
+          for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, nt * BN);
+        }
+        __syncwarp();
         cur_n = nt;
         wphase = 1;
       }
       pdl_wait();  // A (and everything the epilogue reads / overwrites) belongs to the previous kernel until here
-      B200VQA_STAMP(2);
+      if (el) B200VQA_STAMP(2);
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int nt = tile / tiles_m;
         const int m0 = (tile - nt * tiles_m) * kBM;
@@ -187,22 +193,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int a_koff = p.a_group_cols > 0 ? (n0 / p.a_group_cols) * p.K : 0;  // grouped GEMM: A columns of this head
         if (wstat && nt != cur_n) {
           mbar_wait(w_empty, wphase ^ 1);  // every MMA that read the previous W has retired
-          mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
-          for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, n0);
+          if (el) {
+            mbar_expect_tx(w_full, uint32_t(num_kb) * L::kStageB);
+            for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tm_w, w_full, sW + kb * L::kStageB, kb * bk, n0);
+          }
+          __syncwarp();
           cur_n = nt;
           wphase ^= 1;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (wstat) {
-            mbar_expect_tx(&full_bar[stage], L::kStageA);
-            tma_load_2d(&tm_a, &full_bar[stage], sAring + stage * L::kStageA, kb * bk + a_koff, m0);
-          } else {
-            uint8_t* sa = smem + stage * (L::kStageA + L::kStageB);
-            mbar_expect_tx(&full_bar[stage], L::kStageA + L::kStageB);
-            tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk + a_koff, m0);
-            tma_load_2d(&tm_w, &full_bar[stage], sa + L::kStageA, kb * bk, n0);
+          if (el) {
+            if (wstat) {
+              mbar_expect_tx(&full_bar[stage], L::kStageA);
+              tma_load_2d(&tm_a, &full_bar[stage], sAring + stage * L::kStageA, kb * bk + a_koff, m0);
+            } else {
+              uint8_t* sa = smem + stage * (L::kStageA + L::kStageB);
+              mbar_expect_tx(&full_bar[stage], L::kStageA + L::kStageB);
+              tma_load_2d(&tm_a, &full_bar[stage], sa, kb * bk + a_koff, m0);
+              tma_load_2d(&tm_w, &full_bar[stage], sa + L::kStageA, kb * bk, n0);
+            }
           }
+          __syncwarp();
           if (++stage == kNSt) { stage = 0; phase ^= 1; }
         }
       }
@@ -722,12 +734,16 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       mbar_init(stat_full, 1);
       fence_mbar_init();
       mbar_expect_tx(stat_full, 2 * kLnCl * kBM * 8);
-      // weights do not depend on the previous kernel
+    }
+    __syncwarp();
+    // weights do not depend on the previous kernel (issued from uniform registers: see gemm_tc_kernel's producer)
+    if (elect_one()) {
       for (int kb = 0; kb < NS; ++kb) {
         mbar_expect_tx(&w_full[kb], kLnBN * kKBytes);
         tma_load_2d(&tm_w, &w_full[kb], smem + L::kOffW + kb * kLnBN * kKBytes, kb * 64, n0);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     tmem_alloc<kLnBN>(tmem_slot);
   }
