@@ -65,6 +65,7 @@ def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
         "enc_outproj_ln_gemm": ("tensor", 2 * S * d * d),
         "enc_ffn1_gemm": ("tensor", 2 * S * d * ff),
         "enc_ffn2_ln_gemm": ("tensor", 2 * S * d * ff),
+        "enc_ffn_fused": ("tensor", 4 * S * d * ff),            # linear1 + linear2 in one kernel (the default)
         "dec_cross_kv_gemm": ("tensor", n_dec * 2 * S * d * 2 * d),
         "dec_proj_gemm": ("tensor", n_dec * T * (2 * d * 3 * d + 2 * d * d)),     # self in_proj + cross q-proj
         "dec_outproj_ln_gemm": ("tensor", n_dec * T * 2 * 2 * d * d),            # two out-proj + LayerNorm
@@ -541,7 +542,8 @@ def run_ours(args):
             work = {
                 "enc_qkv_gemm": ("tensor", 2 * d_ * 3 * d_ * Lsum), "enc_attention": ("tensor", 4 * d_ * L2sum),
                 "enc_outproj_ln_gemm": ("tensor", 2 * d_ * d_ * Lsum), "enc_ffn1_gemm": ("tensor", 2 * d_ * ff_ * Lsum),
-                "enc_ffn2_ln_gemm": ("tensor", 2 * d_ * ff_ * Lsum), "dec_cross_kv_gemm": ("tensor", 2 * d_ * 2 * d_ * Lsum),
+                "enc_ffn2_ln_gemm": ("tensor", 2 * d_ * ff_ * Lsum), "enc_ffn_fused": ("tensor", 4 * d_ * ff_ * Lsum),
+                "dec_cross_kv_gemm": ("tensor", 2 * d_ * 2 * d_ * Lsum),
                 "enc_final_ln": ("hbm", Lsum * d_ * 2 * 2), "embed_gather": ("hbm", Lsum * d_ * 2 * 2),
                 "dec_proj_gemm": ("tensor", nstep * T_ * (2 * d_ * 3 * d_ + 2 * d_ * d_)),
                 "dec_outproj_ln_gemm": ("tensor", nstep * T_ * 4 * d_ * d_),
