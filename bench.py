@@ -364,6 +364,8 @@ def run_ours(args):
         # fp32 host features; with enough host cores per rank the library rounds them to fp16 on host threads before
         # they cross PCIe ("auto", VQAModel.resolve_upload) - conversion inside the timed region
         e2e_upload = iqap.VQAModel.resolve_upload(args.e2e_upload)
+        if args.e2e_chunk is None:
+            args.e2e_chunk = 512 if e2e_upload == "fp16" else 1024
 
         def step_e2e():
             if depth <= 1:
@@ -435,6 +437,9 @@ def run_ours(args):
         if generator is not None:
             q_h, p_h = questions.cpu().pin_memory(), synth_programs.cpu().pin_memory()
 
+        # fp32 host features; with enough host cores per rank they are rounded to bf16 on host threads before the upload
+        # (what the device does to them anyway: identical results, half the PCIe bytes)
+        fa_upload = fa.resolve_upload({"fp16": "bf16"}.get(args.e2e_upload, args.e2e_upload))
         host_out_no = [0]
         host_out = [torch.empty(B, func.shape[1], 20, dtype=torch.int32).pin_memory() for _ in range(depth)] \
             if generator is None and depth > 1 else []
@@ -447,16 +452,17 @@ def run_ours(args):
                     k = host_out_no[0] % depth
                     host_out_no[0] += 1
                     return fa.submit_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk,
-                                                          depth=depth, out=host_out[k])
+                                                          depth=depth, out=host_out[k], upload=fa_upload)
                 return fa.run_inference_chain_host(model, img_host, f_h, d_h, n_h, 0, 20, chunk=args.fa_host_chunk,
-                                                   parts=args.fa_host_parts)
+                                                   parts=args.fa_host_parts, upload=fa_upload)
             else:
                 generator(q_h.to(dev, non_blocking=True))
                 f, d, n = qp.programs_to_chain(p_h.to(dev, non_blocking=True), arity, fmap)
                 cache = fa.run_inference_chain_batched(model, img_host.to(dev, non_blocking=True), f, d, n, 0, 20)
             return cache.cpu()
 
-        h2d = B * 1024 * 196 * 4 + (f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4 if generator is None
+        h2d = B * 1024 * 196 * (2 if generator is None and fa_upload == "bf16" else 4) + (
+            f_h.numel() * 4 + d_h.numel() * 4 + n_h.numel() * 4 if generator is None
                                       else q_h.numel() * 8 + p_h.numel() * 8)
         drain_host = model.drain_host if generator is None else torch.cuda.synchronize
         d2h = B * func.shape[1] * 20 * 4
@@ -681,7 +687,7 @@ def run_ours(args):
                    {"value": e2e_value, "unit": "program-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / max(1, args.steps // 2),
                     **({"upload": e2e_upload, "host_input_bytes_per_step": B * 196 * 1024 * 4 + B * 46 * 8}
-                       if args.workload == "iqap" else {})},
+                       if args.workload == "iqap" else ({"upload": fa_upload} if args.workload == "fa" else {}))},
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "context": extra,
         }
@@ -699,7 +705,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="iqap", choices=["iqap", "fa", "e2e"])
     ap.add_argument("--batch", type=int, default=None, help="questions per GPU per step (default 1024 iqap / 4096 fa)")
-    ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--e2e-chunk", type=int, default=None,
+                    help="questions per upload chunk of the IQAP host-buffer call (default 512 with the fp16 upload mode: the "
+                         "conversion of a chunk runs under the upload of the previous one; else 1024)")
     ap.add_argument("--pipeline-depth", type=int, default=None,
                     help="independent batches in flight (1 = strictly serial steps); default 2 (iqap) / 3 (fa, e2e)")
     ap.add_argument("--blocks", type=int, default=5, help="timed K-step blocks (the first gives `value`; the median is reported too)")

@@ -118,6 +118,7 @@ SIGNATURES = {
     "b200vqa_dbg_enc_attention": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b200vqa_dbg_workspace": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200vqa_host_f32_to_f16": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
+    "b200vqa_host_f32_to_bf16": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
     "b200vqa_set_host_upload": (C.c_int, [_vp, C.c_int]),
     "b200vqa_dbg_mem_attn": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
 }

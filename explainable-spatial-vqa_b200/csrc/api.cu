@@ -1755,8 +1755,10 @@ B200VQA_API int b200vqa_iqap_forward_host_async(b200vqa_handle* h, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ FA
-B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_features, int B, void* img_tokens_bf16,
-                              void* stream) {
+// src_bf16: the features were rounded to bf16 on the host (the host-buffer entry's bf16 upload mode) - the rounding the
+// transpose does anyway, so both forms give identical image tokens
+static int fa_project_images_impl(b200vqa_handle* h, const void* image_features, bool src_bf16, int B,
+                                  void* img_tokens_bf16, void* stream) {
   B200VQA_REQUIRE(h != nullptr, "handle is NULL");
   B200VQA_REQUIRE(h->d.kind == B200VQA_MODEL_FA, "handle was not created for the FA model");
   B200VQA_REQUIRE(B >= 0, "negative batch");
@@ -1772,8 +1774,13 @@ B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_
     const int nb = std::min(cap, B - b0);
     // channel-major fp32 [nb,1024,196] -> token-major bf16 [nb*196,1024] (the reference's view+permute, FA:47,130)
     h->cur_tag = kTagMisc;
-    LAUNCH_OK(h, launch_transpose_cast(image_features + size_t(b0) * d.img_feat_dim * d.n_img_tokens, h->ws.img_t, nb,
-                                       d.img_feat_dim, d.n_img_tokens, s));
+    const size_t off = size_t(b0) * d.img_feat_dim * d.n_img_tokens;
+    if (src_bf16)
+      LAUNCH_OK(h, launch_transpose_bf16(static_cast<const __nv_bfloat16*>(image_features) + off, h->ws.img_t, nb,
+                                         d.img_feat_dim, d.n_img_tokens, s));
+    else
+      LAUNCH_OK(h, launch_transpose_cast(static_cast<const float*>(image_features) + off, h->ws.img_t, nb, d.img_feat_dim,
+                                         d.n_img_tokens, s));
     h->cur_tag = kTagImgProj;
     GemmParams p;
     p.bias = h->img_b;
@@ -1788,6 +1795,11 @@ B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_
                h->img_w_bf16, kD, p, s));
   }
   return B200VQA_OK;
+}
+
+B200VQA_API int b200vqa_fa_project_images(b200vqa_handle* h, const float* image_features, int B, void* img_tokens_bf16,
+                              void* stream) {
+  return fa_project_images_impl(h, image_features, false, B, img_tokens_bf16, stream);
 }
 
 static int fa_one_step(b200vqa_handle* h, const __nv_bfloat16* img_tokens, FaBuildSrcParams bp, int B, DecodeIO io,
@@ -2055,6 +2067,24 @@ static int fa_run_chain_host_impl(b200vqa_handle* h, const float* h_img, const i
     tr_name.push_back(name);
   };
   mark("start (compute stream)", s);
+  const bool convert = h->host_upload_f16;  // b200vqa_set_host_upload(1): for this model the half-width format is bf16
+  int pin_turn = 0;
+  if (convert) {
+    const size_t pin_b = size_t(ichunk) * per_img * 2;
+    if (h->pin16_bytes < pin_b) {
+      for (int i = 0; i < 2; ++i) {
+        if (h->pin_pending[i]) B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_pin[i]));
+        h->pin_pending[i] = false;
+        if (h->pin16[i]) B200VQA_CUDA_OK(cudaFreeHost(h->pin16[i]));
+        h->pin16[i] = nullptr;
+      }
+      h->pin16_bytes = 0;
+      for (int i = 0; i < 2; ++i) B200VQA_CUDA_OK(cudaMallocHost(&h->pin16[i], pin_b));
+      h->pin16_bytes = pin_b;
+    }
+    for (int i = 0; i < 2; ++i)
+      if (!h->ev_pin[i]) B200VQA_CUDA_OK(cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming));
+  }
   // ---- host: every sub-batch longest program first (stable), so that finished questions drop out of the later
   // steps.  The sorted tables of the WHOLE call are written to pinned memory up front: a copy from pageable memory would
   // make the host wait for everything queued before it on the stream, i.e. for the previous sub-batch's chains
@@ -2106,9 +2136,23 @@ static int fa_run_chain_host_impl(b200vqa_handle* h, const float* h_img, const i
     if (k >= 2) B200VQA_CUDA_OK(cudaStreamWaitEvent(ingest, h->ev_free[par], 0));
     for (int i0 = 0; i0 < nb; i0 += ichunk) {
       const int ni = std::min(ichunk, nb - i0);
-      B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, h_img + (size_t(b0) + i0) * per_img, size_t(ni) * per_img * sizeof(float),
-                                      cudaMemcpyHostToDevice, ingest));
-      RC_OK(b200vqa_fa_project_images(h, d_img, ni, d_tok[par] + size_t(i0) * d.n_img_tokens * kD, ingest));
+      const float* src = h_img + (size_t(b0) + i0) * per_img;
+      if (convert) {
+        // the host rounds these images to bf16 (what the transpose on the device does anyway: identical tokens) while
+        // the previous group is on the wire; the pinned staging is free once its own upload has completed
+        const int ps = pin_turn++ & 1;
+        if (h->pin_pending[ps]) {
+          B200VQA_CUDA_OK(cudaEventSynchronize(h->ev_pin[ps]));
+          h->pin_pending[ps] = false;
+        }
+        host_f32_to_bf16(src, h->pin16[ps], size_t(ni) * per_img, 0);
+        B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, h->pin16[ps], size_t(ni) * per_img * 2, cudaMemcpyHostToDevice, ingest));
+        B200VQA_CUDA_OK(cudaEventRecord(h->ev_pin[ps], ingest));
+        h->pin_pending[ps] = true;
+      } else {
+        B200VQA_CUDA_OK(cudaMemcpyAsync(d_img, src, size_t(ni) * per_img * sizeof(float), cudaMemcpyHostToDevice, ingest));
+      }
+      RC_OK(fa_project_images_impl(h, d_img, convert, ni, d_tok[par] + size_t(i0) * d.n_img_tokens * kD, ingest));
     }
     const int32_t* t_func = tab_func(k);
     const int32_t* t_deps = t_func + size_t(nb) * S;

@@ -1,4 +1,4 @@
-// fp32 -> fp16 on the HOST, on a pool of worker threads: the host-buffer entry points can halve the bytes that cross
+// fp32 -> fp16 (IQAP) / bf16 (FA) on the HOST, on a pool of worker threads: the host-buffer entry points can halve the bytes that cross
 // PCIe (803 KB of fp32 ResNet features per question: the upload, not the GPU, bounds end-to-end throughput) by rounding
 // the features to fp16 while the previous chunk is on the wire.  Round-to-nearest-even, as torch's .half(); the device
 // path consumes them exactly like a caller-provided fp16 feature store (b200vqa_iqap_forward_host_f16).
@@ -57,7 +57,37 @@ void cvt_scalar(const float* src, uint16_t* dst, size_t n) {
   }
 }
 
+// fp32 -> bf16, round to nearest even (finite inputs: bit-identical to the device's __float2bfloat16_rn)
+inline uint16_t bf16_rne_scalar(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return uint16_t((u >> 16) | 0x40u);  // NaN stays a (quiet) NaN
+  return uint16_t((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+__attribute__((target("avx512f,avx512bw"))) void cvt_bf16_avx512(const float* src, uint16_t* dst, size_t n) {
+  size_t i = 0;
+  const __m512i bias = _mm512_set1_epi32(0x7fff), one = _mm512_set1_epi32(1);
+  for (; i + 32 <= n; i += 32) {
+    __m512i a = _mm512_loadu_si512(src + i), b = _mm512_loadu_si512(src + i + 16);
+    a = _mm512_srli_epi32(_mm512_add_epi32(_mm512_add_epi32(a, bias), _mm512_and_si512(_mm512_srli_epi32(a, 16), one)), 16);
+    b = _mm512_srli_epi32(_mm512_add_epi32(_mm512_add_epi32(b, bias), _mm512_and_si512(_mm512_srli_epi32(b, 16), one)), 16);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm512_cvtepi32_epi16(a));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 16), _mm512_cvtepi32_epi16(b));
+  }
+  for (; i < n; ++i) dst[i] = bf16_rne_scalar(src[i]);
+}
+
+void cvt_bf16_scalar(const float* src, uint16_t* dst, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = bf16_rne_scalar(src[i]);
+}
+
 using CvtFn = void (*)(const float*, uint16_t*, size_t);
+CvtFn pick_cvt_bf16() {
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return cvt_bf16_avx512;
+  return cvt_bf16_scalar;
+}
 CvtFn pick_cvt() {
   __builtin_cpu_init();
   if (__builtin_cpu_supports("avx512f")) return cvt_avx512;
@@ -142,8 +172,19 @@ int host_convert_threads() {
   return std::max(1, std::min(n, 32));
 }
 
+static void host_convert(CvtFn cvt, const float* src, void* dst, size_t n, int threads);
+
 void host_f32_to_f16(const float* src, void* dst, size_t n, int threads) {
   static const CvtFn cvt = pick_cvt();
+  host_convert(cvt, src, dst, n, threads);
+}
+
+void host_f32_to_bf16(const float* src, void* dst, size_t n, int threads) {
+  static const CvtFn cvt = pick_cvt_bf16();
+  host_convert(cvt, src, dst, n, threads);
+}
+
+static void host_convert(CvtFn cvt, const float* src, void* dst, size_t n, int threads) {
   uint16_t* out = static_cast<uint16_t*>(dst);
   if (threads <= 0) threads = host_convert_threads();
   constexpr size_t kBlock = size_t(1) << 18;  // elements per task (1 MB of source)
@@ -167,6 +208,15 @@ void host_f32_to_f16(const float* src, void* dst, size_t n, int threads) {
 }
 
 }  // namespace b200vqa
+
+extern "C" B200VQA_API int b200vqa_host_f32_to_bf16(const float* src, void* dst, long long n, int threads) {
+  B200VQA_REQUIRE(n >= 0, "negative element count");
+  if (n == 0) return B200VQA_OK;
+  B200VQA_REQUIRE(src && dst, "a required buffer is NULL");
+  B200VQA_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 31u) == 0, "dst must be 32-byte aligned");
+  b200vqa::host_f32_to_bf16(src, dst, size_t(n), threads);
+  return B200VQA_OK;
+}
 
 extern "C" B200VQA_API int b200vqa_host_f32_to_f16(const float* src, void* dst, long long n, int threads) {
   B200VQA_REQUIRE(n >= 0, "negative element count");

@@ -167,6 +167,8 @@ cudaError_t launch_layernorm_rows(const __nv_bfloat16* in, __nv_bfloat16* out, c
 
 // fp32 [B, C, P] (channel-major, FA:47) -> bf16 [B*P, C]
 cudaError_t launch_transpose_cast(const float* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream);
+// the same from values already rounded to bf16 (the host-buffer entry's bf16 upload mode)
+cudaError_t launch_transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream);
 
 // seq-first fp32 memory [S,B,kD] -> padded bf16 rows [B*kLP, kD] (IQAP:190 entry with caller memory)
 // (ldb = batch size of the full seq-first tensor; `mem` already points at this chunk's first question)
@@ -318,6 +320,7 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
 
 // Host side (host_convert.cu): fp32 -> fp16 (round to nearest even) on a pool of worker threads; dst 32-byte aligned.
 void host_f32_to_f16(const float* src, void* dst, size_t n, int threads);
+void host_f32_to_bf16(const float* src, void* dst, size_t n, int threads);
 int host_convert_threads();
 
 // Encoder feed-forward block + norm2 (+ the final encoder norm) in one persistent kernel (enc_ffn_fused.cu): the

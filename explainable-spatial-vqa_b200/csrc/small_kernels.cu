@@ -157,15 +157,16 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv
   store_bf16x8(out + size_t(row) * kD + lane * 8, v);
 }
 
-// fp32 [B, C, P] -> bf16 [B*P, C] through a padded 32x32 shared tile.
-__global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int P) {
+// fp32 (or bf16: already rounded on the host) [B, C, P] -> bf16 [B*P, C] through a padded 32x32 shared tile.
+template <typename TIn>
+__global__ void transpose_cast_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int P) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, pp = p0 + tx;
-    tile[i][tx] = (c < C && pp < P) ? in[(size_t(b) * C + c) * P + pp] : 0.f;
+    tile[i][tx] = (c < C && pp < P) ? float(in[(size_t(b) * C + c) * P + pp]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -367,7 +368,13 @@ cudaError_t launch_layernorm_rows(const __nv_bfloat16* in, __nv_bfloat16* out, c
 
 cudaError_t launch_transpose_cast(const float* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream) {
   dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B), block(32, 8);
-  transpose_cast_kernel<<<grid, block, 0, stream>>>(in, out, C, P);
+  transpose_cast_kernel<float><<<grid, block, 0, stream>>>(in, out, C, P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int C, int P, cudaStream_t stream) {
+  dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B), block(32, 8);
+  transpose_cast_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(in, out, C, P);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ host round trip between program steps (the reference does one H2D and one D2H pe
 from __future__ import annotations
 
 import ctypes as C
+import os
 import json
 import logging
 import re
@@ -337,9 +338,23 @@ def _chain_batched(model, image_features, func, deps, n_steps, start_token, max_
     return (cache, logits) if want_logits else cache
 
 
+def resolve_upload(upload):
+    """"fp32": the feature bytes cross PCIe as given.  "bf16": the library rounds them to bf16 on host threads while the
+    previous group of images is on the wire - half the bytes, and bit-identical results, because the device path rounds
+    the features to bf16 anyway (the transpose + cast in front of image_proj).  "auto": "bf16" when this process has
+    at least 8 CPUs to itself (CPUs it may run on / ranks on the node)."""
+    if upload == "auto":
+        cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+        return "bf16" if cpus // ranks >= 8 else "fp32"
+    if upload not in ("fp32", "bf16"):
+        raise ValueError('upload must be "fp32", "bf16" or "auto"')
+    return upload
+
+
 @torch.no_grad()
 def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, start_token=0, max_infer_len=20,
-                             chunk=2048, parts=2):
+                             chunk=2048, parts=2, upload="fp32"):
     """`run_inference_chain_batched` with HOST tensors in and out - the library call that replaces the reference's
     driver loop (FA:193-206) with its per-step uploads and downloads (FA:109-121): image_features_cpu (B,1024,14,14) f32
     (pinned for full PCIe speed), func (B,S), deps (B,S,2), n_steps (B,) on the host -> cache (B,S,max_infer_len) i32
@@ -362,9 +377,11 @@ def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, sta
     cache = torch.empty(B, S, max_infer_len, dtype=torch.int32).pin_memory()
     dev = model.image_proj.weight.device
     parts = max(1, min(int(parts), B // 256 if B >= 512 else 1))
+    half = resolve_upload(upload) == "bf16"
     with torch.cuda.device(dev):
         if parts == 1:
             h = model._native(0)
+            h.set_host_upload(half)
             nat.check(nat.lib().b200vqa_fa_run_chain_host(h.raw, nat.ptr(img), nat.ptr(f), nat.ptr(d), nat.ptr(n), B, S,
                                                           int(start_token), int(max_infer_len), nat.ptr(cache), int(chunk),
                                                           nat.stream_ptr(dev)), "b200vqa_fa_run_chain_host")
@@ -373,6 +390,7 @@ def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, sta
         for i in range(parts):
             lo, hi = B * i // parts, B * (i + 1) // parts
             h = model._native(1 + i)
+            h.set_host_upload(half)
             st = model._pool.stream(1 + i)
             streams.append(st)
             nat.check(nat.lib().b200vqa_fa_run_chain_host_async(
@@ -386,7 +404,7 @@ def run_inference_chain_host(model, image_features_cpu, func, deps, n_steps, sta
 
 @torch.no_grad()
 def submit_inference_chain_host(model, image_features_cpu, func, deps, n_steps, start_token=0, max_infer_len=20,
-                                chunk=1024, depth=2, out=None):
+                                chunk=1024, depth=2, out=None, upload="fp32"):
     """`run_inference_chain_host` without the final synchronisation, on a round-robin (handle, stream) slot: the upload
     of this batch runs under the chains of the previous one.  Returns the pinned host cache (`out` when given: a
     pinned int32 (B,S,max_infer_len) tensor the caller recycles), valid after `model.drain_host()`; the host inputs are
@@ -407,6 +425,7 @@ def submit_inference_chain_host(model, image_features_cpu, func, deps, n_steps, 
     slot = 1 + model._next_host_slot % max(1, int(depth))
     model._next_host_slot += 1
     h = model._native(slot)
+    h.set_host_upload(resolve_upload(upload) == "bf16")
     st = model._pool.stream(slot)
     if out is None:
         cache = torch.empty(B, S, max_infer_len, dtype=torch.int32).pin_memory()

@@ -372,7 +372,8 @@ B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const i
  * 10 tok (int64 [cap, 65]).  Used by tests / tools to compare the persistent decode kernel with the per-kernel chain. */
 B200VQA_API int b200vqa_dbg_workspace(b200vqa_handle* h, int which, void* dst, size_t dst_bytes, size_t* bytes);
 
-/* Upload mode of b200vqa_iqap_forward_host[_async] for fp32 host features: 0 (default) = the bytes as given, 1 = rounded
+/* Upload mode of b200vqa_iqap_forward_host[_async] (and b200vqa_fa_run_chain_host[_async]: bf16, see
+ * b200vqa_host_f32_to_bf16) for fp32 host features: 0 (default) = the bytes as given, 1 = rounded
  * to fp16 (nearest even) on host threads, chunk by chunk, while the previous chunk is on the wire - half the PCIe bytes,
  * then the device path of a caller-provided fp16 feature store (b200vqa_iqap_forward_host_f16): results equal those of
  * that call on the rounded features bit for bit.  Pays when the process has host cores to spare (>= ~8). */
@@ -383,6 +384,9 @@ B200VQA_API int b200vqa_set_host_upload(b200vqa_handle* h, int mode);
  * points use it for the "fp16" upload mode (b200vqa_set_host_upload): the feature rows that the reference uploads as
  * fp32 per sample (IQAP:288-296) cross PCIe at half the size. */
 B200VQA_API int b200vqa_host_f32_to_f16(const float* src, void* dst, long long n, int threads);
+/* The same to bf16 (round to nearest even = the device's conversion): upload mode 1 of b200vqa_fa_run_chain_host[_async],
+ * whose device path rounds the features to bf16 anyway (FA:47 transpose + cast) - the results are bit-identical to mode 0. */
+B200VQA_API int b200vqa_host_f32_to_bf16(const float* src, void* dst, long long n, int threads);
 
 #ifdef __cplusplus
 }

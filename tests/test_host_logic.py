@@ -231,3 +231,12 @@ def test_host_fp32_to_fp16_conversion_is_numpy_exact():
         nat.check(lib.b200vqa_host_f32_to_f16(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, threads), "convert")
         assert np.array_equal(out.view(np.float16).view(np.uint16), want.view(np.uint16)), threads
     assert lib.b200vqa_host_f32_to_f16(x.ctypes.data_as(C.c_void_p), C.c_void_p(raw.ctypes.data + 2), 4, 1) < 0  # misaligned
+    # bf16 (the FA host entry's upload mode): the same rounding as torch / the device conversion
+    import torch
+    want16 = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    for threads in (1, 0):
+        raw = np.empty(n + 16, dtype=np.uint16)
+        off = (-raw.ctypes.data % 32) // 2
+        out = raw[off:off + n]
+        nat.check(lib.b200vqa_host_f32_to_bf16(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, threads), "convert")
+        assert np.array_equal(out, want16), threads

@@ -126,3 +126,13 @@ def test_fa_host_entry_equals_device_entry():
                                            depth=2) for i in range(3)]
     model.drain_host()
     assert torch.equal(torch.cat(outs), want)
+    # upload="bf16": features rounded on host threads before the upload - what the device path does to them anyway, so
+    # the caches are identical; several image groups per sub-batch (staging reused), synchronous and pipelined entries
+    got = fa.run_inference_chain_host(model, img.pin_memory(), func, deps, n_steps, 0, 20, chunk=300, parts=1, upload="bf16")
+    assert torch.equal(got, want)
+    outs = [fa.submit_inference_chain_host(model, img[i * 200:(i + 1) * 200].pin_memory(), func[i * 200:(i + 1) * 200],
+                                           deps[i * 200:(i + 1) * 200], n_steps[i * 200:(i + 1) * 200], 0, 20, chunk=64,
+                                           depth=2, upload="bf16") for i in range(3)]
+    model.drain_host()
+    assert torch.equal(torch.cat(outs), want)
+    assert fa.resolve_upload("auto") in ("bf16", "fp32")

@@ -1,15 +1,12 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-$TR bench.py --gpus 8 --no-cpu-baseline > gpurun_out/r2_bench_iqap_8gpu.json 2> gpurun_out/r2_bench_iqap_8gpu.err
-$TR bench.py --gpus 8 --workload e2e --batch 18750 --steps 3 --skip-host-e2e --no-cpu-baseline > gpurun_out/r2_bench_e2e_150k_8gpu.json 2> gpurun_out/r2_bench_e2e_150k_8gpu.err
-$TR bench.py --gpus 8 --workload fa --steps 6 --blocks 3 --no-cpu-baseline > gpurun_out/r2_bench_fa_8gpu.json 2> gpurun_out/r2_bench_fa_8gpu.err
+timeout 600 python -m pytest tests/test_parity_full_size_gpu.py tests/test_fa_gpu.py tests/test_iqap_gpu.py -m gpu -x -q 2>&1 | tail -2
+for m in auto fp32; do python bench.py --workload fa --steps 8 --blocks 2 --no-cpu-baseline --e2e-upload $m > gpurun_out/fa_up_$m.json 2> gpurun_out/fa_up_$m.err; done
+python bench.py --blocks 2 --no-cpu-baseline > gpurun_out/iq_up.json 2>/dev/null
 python - <<'PY'
 import json
-for n in ["r2_bench_iqap_8gpu", "r2_bench_e2e_150k_8gpu", "r2_bench_fa_8gpu"]:
+for n in ["fa_up_auto", "fa_up_fp32", "iq_up"]:
     try:
         j = json.loads([l for l in open(f"gpurun_out/{n}.json") if l.startswith("{")][-1])
-        e = j.get("e2e") or {}
-        print(n, "ms/step", round(j["ms_per_step"], 3), "value", round(j["value"]), "e2e", e.get("value") and round(e["value"]), e.get("upload"),
-              "ms e2e", e.get("ms_per_step"), "h2d", (j.get("context") or {}).get("h2d_gbs_concurrent"))
+        print(n, "ms/step", round(j["ms_per_step"], 2), "value", round(j["value"]), "e2e", j["e2e"])
     except Exception as ex:
         print(n, "FAILED", ex); print(open(f"gpurun_out/{n}.err").read()[-800:])
 PY
