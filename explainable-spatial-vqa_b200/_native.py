@@ -319,10 +319,14 @@ class HandlePool:
         self._handles = {}
         self._versions = {}
         self._streams = {}
+        self._workers = {}   # slot -> single-thread executor (background host-buffer submissions)
+        self.futures = []    # pending background calls
 
     def __getstate__(self):
-        # native handles, streams and packed weights never travel through pickle / deepcopy: they are rebuilt lazily
-        return {"_module": self._module, "_builder": self._builder, "_handles": {}, "_versions": {}, "_streams": {}}
+        # native handles, streams, worker threads and packed weights never travel through pickle / deepcopy: they are
+        # rebuilt lazily
+        return {"_module": self._module, "_builder": self._builder, "_handles": {}, "_versions": {}, "_streams": {},
+                "_workers": {}, "futures": []}
 
     def __setstate__(self, state):
         self.__dict__.update(state)
@@ -350,6 +354,20 @@ class HandlePool:
             st = torch.cuda.Stream(device=dev)
             self._streams[slot] = st
         return st
+
+    def run_in_background(self, slot: int, fn) -> None:
+        """Runs fn() on the slot's own host thread (one per slot: calls on a handle stay in submission order; ctypes
+        releases the GIL inside the library).  `wait_background()` re-raises its exception."""
+        import concurrent.futures
+        ex = self._workers.get(slot)
+        if ex is None:
+            ex = self._workers[slot] = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        self.futures.append(ex.submit(fn))
+
+    def wait_background(self) -> None:
+        futures, self.futures = self.futures, []
+        for f in futures:
+            f.result()
 
     def drain(self):
         """Makes the caller's current stream wait for every slot stream (results of all submits become usable)."""

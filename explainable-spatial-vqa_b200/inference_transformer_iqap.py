@@ -217,6 +217,17 @@ class VQAModel(nn.Module):
                                                     None, None, nat.stream_ptr(mem.device)), "b200vqa_iqap_decode")
         return programs
 
+    def _check_host_inputs(self, img, q):
+        """The library reads exactly B x num_image_tokens x in_features features and B x q_len question tokens."""
+        if img.is_cuda or q.is_cuda:
+            raise ValueError("the host-buffer entry points take CPU tensors; use forward() for device tensors")
+        q_len = self.pos_encoder.pe.shape[0] - 1 - self.num_image_tokens
+        if img.dim() != 3 or tuple(img.shape[1:]) != (self.num_image_tokens, self.image_proj.in_features):
+            raise ValueError(f"image_features must be (B, {self.num_image_tokens}, {self.image_proj.in_features}), "
+                             f"got {tuple(img.shape)}")
+        if tuple(q.shape) != (img.shape[0], q_len):
+            raise ValueError(f"questions must be ({img.shape[0]}, {q_len}), got {tuple(q.shape)}")
+
     @staticmethod
     def resolve_upload(upload):
         """"fp32": the feature bytes cross PCIe as given (results bit-identical to `forward`).  "fp16": the library
@@ -241,8 +252,7 @@ class VQAModel(nn.Module):
         f16 = image_features_cpu.dtype == torch.float16   # fp16 feature store: half the PCIe bytes
         img = image_features_cpu.to(torch.float16 if f16 else torch.float32).contiguous()
         q = questions_cpu.to(torch.int64).contiguous()
-        if img.is_cuda or q.is_cuda:
-            raise ValueError("forward_host takes CPU tensors; use forward() for device tensors")
+        self._check_host_inputs(img, q)
         B, T = img.shape[0], Config.PROGRAM_SEQ_LEN
         answer = torch.empty(B, self.answer_classifier[3].out_features, dtype=torch.float32).pin_memory()
         programs = torch.empty(B, T, dtype=torch.int64).pin_memory()
@@ -352,23 +362,37 @@ class VQAModel(nn.Module):
         return answer, programs
 
     @torch.no_grad()
-    def submit_host(self, image_features_cpu, questions_cpu, chunk=512, depth=2, upload="fp32"):
+    def submit_host(self, image_features_cpu, questions_cpu, chunk=512, depth=2, upload="fp32", background=None):
         """`forward_host` without the final synchronisation, on a round-robin slot: the upload of this batch overlaps
-        the decode tail of the previous one.  Returns pinned CPU tensors that are valid after `drain_host()`."""
+        the decode tail of the previous one.  Returns pinned CPU tensors that are valid after `drain_host()`.
+        `background` (default: on with the fp16 upload mode): the library call runs on the slot's own host thread, so the
+        host-side rounding of this batch overlaps the enqueue work of the previous one and the caller is not held up."""
         slot = 1 + self._next_slot % depth
         self._next_slot += 1
         h = self._native(slot)
-        h.set_host_upload(self.resolve_upload(upload) == "fp16")
+        fp16 = self.resolve_upload(upload) == "fp16"
         st = self._pool.stream(slot)
         img = image_features_cpu.to(torch.float32).contiguous()
         q = questions_cpu.to(torch.int64).contiguous()
+        self._check_host_inputs(img, q)
         B, T = img.shape[0], Config.PROGRAM_SEQ_LEN
         answer = torch.empty(B, self.answer_classifier[3].out_features, dtype=torch.float32).pin_memory()
         programs = torch.empty(B, T, dtype=torch.int64).pin_memory()
-        with torch.cuda.device(st.device):
-            nat.check(nat.lib().b200vqa_iqap_forward_host_async(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
-                                                                nat.ptr(programs), int(chunk), C.c_void_p(st.cuda_stream)),
-                      "b200vqa_iqap_forward_host_async")
+
+        def call():
+            with torch.cuda.device(st.device):
+                h.set_host_upload(fp16)
+                nat.check(nat.lib().b200vqa_iqap_forward_host_async(h.raw, nat.ptr(img), nat.ptr(q), B, T, nat.ptr(answer),
+                                                                    nat.ptr(programs), int(chunk),
+                                                                    C.c_void_p(st.cuda_stream)),
+                          "b200vqa_iqap_forward_host_async")
+
+        if background is None:
+            background = fp16
+        if background:
+            self._pool.run_in_background(slot, call)
+        else:
+            call()
         # the asynchronous upload reads `img` / `q` (possibly temporaries made by .to() / .contiguous() above) and the
         # download writes `answer` / `programs` until the slot stream has drained: keep all four alive until drain_host()
         self._host_inflight.append((img, q, answer, programs))
@@ -380,6 +404,7 @@ class VQAModel(nn.Module):
 
     def drain_host(self):
         """Blocks the host until every `submit_host` has delivered its results."""
+        self._pool.wait_background()  # re-raises a NativeError of a background call
         for st in list(self._pool._streams.values()):
             st.synchronize()
         self._host_inflight.clear()

@@ -124,6 +124,16 @@ def test_host_entry_with_fp16_upload(model):
                               chunk=32, depth=2, upload="fp16") for i in range(3)]
     model.drain_host()
     assert torch.equal(torch.cat([o[0] for o in outs]), a16) and torch.equal(torch.cat([o[1] for o in outs]), p16)
+    # the same in the foreground (the library call on the caller's thread)
+    outs = [model.submit_host(img[i * 100:(i + 1) * 100].clone().pin_memory(), q[i * 100:(i + 1) * 100].clone().pin_memory(),
+                              chunk=32, depth=2, upload="fp16", background=False) for i in range(3)]
+    model.drain_host()
+    assert torch.equal(torch.cat([o[0] for o in outs]), a16)
+    # malformed host inputs are refused before anything is read
+    with pytest.raises(ValueError):
+        model.submit_host(img[:4].pin_memory(), q[:4, :5].contiguous().pin_memory(), upload="fp16")
+    with pytest.raises(ValueError):
+        model.forward_host(img[:4, :100].contiguous().pin_memory(), q[:4].pin_memory())
     assert model.resolve_upload("auto") in ("fp16", "fp32")
     with pytest.raises(ValueError):
         model.resolve_upload("bf16")
