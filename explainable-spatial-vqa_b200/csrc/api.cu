@@ -197,7 +197,8 @@ struct b200vqa_handle {
   uint8_t* stage = nullptr;
   size_t stage_bytes = 0;
   int dbg_skip = 0;  // B200VQA_DBG_SKIP: timing decomposition only (results are garbage): 1 cross-attention, 2 self-
-                     // attention, 4 feed-forward, 8 out_proj+LN GEMMs, 16 plain GEMMs of the decode chain, 32 encoder
+                     // attention, 4 feed-forward, 8 out_proj+LN GEMMs, 16 plain GEMMs of the decode chain, 32 encoder,
+                     // 64 the vocabulary-head GEMM
   bool no_fused_enc_ffn = false;  // B200VQA_NO_FUSED_ENC_FFN=1: linear1 / linear2 as two GEMMs through HBM
   int small_bn = 64;  // narrowest n-tile of the plain GEMMs (B200VQA_SMALL_BN=128: A/B of fewer, wider decode CTAs)
   int32_t* h_tables = nullptr;  // pinned: the sorted program tables of one fa_run_chain_host call
@@ -881,7 +882,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       hp.pe_next = (t + 1 < io.steps) ? h->pe_dec + size_t(t + 1) * kD : nullptr;
       hp.x_next = dx;
       h->cur_tag = kTagDecHead;
-      RC_OK(gemm(h, kEpiHead, true, dout, B, kD, kD, h->head_w, d.dec_vocab <= 64 ? 64 : 256, hp, s));
+      if (!(h->dbg_skip & 64)) RC_OK(gemm(h, kEpiHead, true, dout, B, kD, kD, h->head_w, d.dec_vocab <= 64 ? 64 : 256, hp, s));
     }
   }
   return B200VQA_OK;

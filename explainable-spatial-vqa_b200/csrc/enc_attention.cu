@@ -101,7 +101,7 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // uniform control flow up to here: the TMA operands come from uniform registers
       mbar_expect_tx(bar_qk, 2 * L::kQ + L::kK);
 #pragma unroll
       for (int pn = 0; pn < kPanels; ++pn) {
@@ -114,40 +114,46 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       for (int pn = 0; pn < kPanels; ++pn)
         tma_load_2d(&tm_kv, bar_v, sV + pn * 32768, 2 * kD + h * DH + pn * 64, int(row0));
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- S_t = Q_t K^T : M=128, N=keys16, K=DH
-      mbar_wait(bar_qk, 0);
-      tc_fence_after_sync();
-      const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
-      for (int t = 0; t < 2; ++t) {
+    // The whole warp waits and one elected lane issues: the descriptors stay in uniform registers (see gemm_tc_kernel;
+    // the N = DH MMAs of P V take 32-64 cycles each, issued from one thread's vector registers ~100)
+    const bool el = elect_one();
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(smem_u32(sV), 32768, 1024);
+    // ---- S_t = Q_t K^T : M=128, N=keys16, K=DH
+    mbar_wait(bar_qk, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc_s = make_idesc(kFmtBF16, 128, uint32_t(keys16), 0, 0);
+    for (int t = 0; t < 2; ++t) {
+      const uint64_t dq0 = make_smem_desc_sw128(smem_u32(sQ[t]), 16, 1024);
+      if (el) {
         if (t == 0 || two) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            const uint32_t qa = smem_u32(sQ[t]) + (k / 4) * 16384 + (k % 4) * 32;
-            const uint32_t ka = smem_u32(sK) + (k / 4) * 32768 + (k % 4) * 32;
-            umma_bf16(tmem_base + t * 256, make_smem_desc_sw128(qa, 16, 1024), make_smem_desc_sw128(ka, 16, 1024),
-                      idesc_s, k != 0);
-          }
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem_base + t * 256, dq0 + uint64_t(((k / 4) * 16384 + (k % 4) * 32) >> 4),
+                      dk0 + uint64_t(((k / 4) * 32768 + (k % 4) * 32) >> 4), idesc_s, k != 0);
         }
         umma_commit(&bar_s[t]);  // bar_s[1] also tells the softmax groups that K and Q are no longer read
       }
-      // ---- O_t = P_t V : M=128, N=DH, K=keys16   (V is the MN-major B operand)
-      const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
-      const int nkk = keys16 / 16;
-      mbar_wait(bar_v, 0);
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1 && !two) break;
-        mbar_wait(&bar_p[t], 0);
-        tc_fence_after_sync();
-        for (int kk = 0; kk < nkk; ++kk) {
-          const uint32_t pa = smem_u32(sP[t]) + (kk / 4) * 16384 + (kk % 4) * 32;
-          const uint32_t va = smem_u32(sV) + kk * 2048;  // 16 key rows of 128 B
-          umma_bf16(tmem_base + t * 256, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(va, 32768, 1024),
-                    idesc_o, kk != 0);
-        }
+      __syncwarp();
+    }
+    // ---- O_t = P_t V : M=128, N=DH, K=keys16   (V is the MN-major B operand)
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 128, DH, 0, 1);
+    const int nkk = keys16 / 16;
+    mbar_wait(bar_v, 0);
+    for (int t = 0; t < 2; ++t) {
+      if (t == 1 && !two) break;
+      mbar_wait(&bar_p[t], 0);
+      tc_fence_after_sync();
+      const uint64_t dp0 = make_smem_desc_sw128(smem_u32(sP[t]), 16, 1024);
+      if (el) {
+        for (int kk = 0; kk < nkk; ++kk)  // 16 key rows of 128 B per step of V
+          umma_bf16(tmem_base + t * 256, dp0 + uint64_t(((kk / 4) * 16384 + (kk % 4) * 32) >> 4),
+                    dv0 + uint64_t((kk * 2048) >> 4), idesc_o, kk != 0);
         umma_commit(&bar_o[t]);
       }
+      __syncwarp();
     }
   } else {
     const int t = (warp - 2) >> 3;          // query tile of this softmax group
@@ -172,15 +178,21 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       __syncwarp();
       tc_fence_after_sync();
       const int nchunks = (len + 31) / 32;
+      const int nfull = len / 32;  // chunks without masked keys: the per-element length test is paid by the last one only
 
       float mx = -INFINITY;
       for (int c = hc; c < nchunks; c += 2) {
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (c < nfull) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
       }
       mine->x = mx;
       named_bar_sync(pair_bar, 64);
@@ -194,14 +206,20 @@ enc_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
         uint32_t o[16];
+        const bool full = c < nfull;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float p0 = (c * 32 + j < len) ? exp2f(__uint_as_float(v[j]) * sl2 - mxs) : 0.f;
-          const float p1 = (c * 32 + j + 1 < len) ? exp2f(__uint_as_float(v[j + 1]) * sl2 - mxs) : 0.f;
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          const float2 pr = __bfloat1622float2(pb);
-          sum += pr.x + pr.y;  // normalise by what the tensor core will actually sum
-          o[j >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          // scores are <= the row maximum: the argument is <= 0, ex2.approx needs no range handling
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mxs));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mxs));
+          if (!full) {
+            p0 = (c * 32 + j < len) ? p0 : 0.f;
+            p1 = (c * 32 + j + 1 < len) ? p1 : 0.f;
+          }
+          const uint32_t pb = pack_bf16x2(p0, p1);
+          // normalise by what the tensor core will actually sum: the bf16-rounded weights
+          sum += __uint_as_float(pb << 16) + __uint_as_float(pb & 0xffff0000u);
+          o[j >> 1] = pb;
         }
         uint8_t* prow = sP[t] + (c >> 1) * 16384 + r * 128;
 #pragma unroll
