@@ -45,14 +45,17 @@ constexpr int kStages = 4;
 constexpr int kWstatMaxKb = 4;    // W-stationary when the whole K fits in 4 k-blocks
 constexpr int kWstatKb = 4;
 
-template <int BN>
+template <int BN, bool LN = false>
 struct GemmSmem {
   static constexpr int kStageA = kBM * kKBytes;             // 16 KB
   static constexpr int kStageB = BN * kKBytes;              // 8 / 16 / 32 KB
   // BN = 64 serves the decode chain (M = one branch of questions, K = 256, a single tile per CTA): two A stages and a
   // single-buffered epilogue staging bring the CTA from 130 KB to 82 KB, so that two of them - or one beside the
   // memory-attention CTAs of another branch - share an SM instead of each holding one
-  static constexpr int kNSt = BN == 64 ? 2 : kStages;
+  // The LayerNorm epilogue (BN = 256) runs three stages: the 16 KB it gives up hold bias | gamma | beta (| gamma2 |
+  // beta2) of the row - with ~200 KB of the SM carved out as shared memory there is next to no L1, and every table
+  // look-up in the epilogue's chunk loops was an L2 round trip
+  static constexpr int kNSt = BN == 64 ? 2 : (LN ? 3 : kStages);
   static constexpr int kStg = BN == 64 ? 16384 : 32768;
   static constexpr int kRingW = kWstatKb * kStageB + kNSt * kStageA;      // W-stationary: W (4 blocks) + A ring
   static constexpr int kRingS = kNSt * (kStageA + kStageB);               // streaming: stage = [A | W]
@@ -61,7 +64,8 @@ struct GemmSmem {
   static constexpr int kOffStg = kRing;
   static constexpr int kOffXch = kOffStg + kStg;            // LayerNorm / argmax exchange between the warps of a quarter
   static constexpr int kOffBar = kOffXch + 2048;
-  static constexpr int kBytes = kOffBar + 128 /*barriers + tmem ptr*/;
+  static constexpr int kOffTab = kOffBar + 128 /*barriers + tmem ptr*/;
+  static constexpr int kBytes = kOffTab + (LN ? 5 * BN * 4 : 0);
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -92,7 +96,7 @@ __device__ __forceinline__ void store_chunk_bf16(uint8_t* buf, const uint32_t (&
 template <int BN, int EPI, bool TF32>
 __global__ void __launch_bounds__(gemm_threads(EPI), BN == 64 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const GemmParams p) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, is_ln_epi(EPI)>;
   constexpr uint32_t kTmemCols = kAccStages * BN;
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
   static_assert(!is_ln_epi(EPI) || BN == 256, "LN epilogue needs the whole row in one tile");
@@ -295,6 +299,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     uint32_t nstore = 0;  // chunks written by this warp (staging buffer = nstore & kStgMask)
     [[maybe_unused]] float* btab = reinterpret_cast<float*>(smem + L::kOffXch);  // bias of the current n-tile
     [[maybe_unused]] int btab_nt = -1;
+    [[maybe_unused]] const float* ltab = reinterpret_cast<const float*>(smem + L::kOffTab);
+    [[maybe_unused]] uint4 rnext[4];  // LayerNorm epilogue: the residual chunk requested ahead
+    if constexpr (is_ln_epi(EPI)) {
+      // bias | gamma | beta (| gamma2 | beta2) of the 256 columns (N = BN: one n-tile) into shared memory, once per CTA
+      // (weights: safe before the dependency wait)
+      float* wtab = reinterpret_cast<float*>(smem + L::kOffTab);
+      for (int i = ew * 32 + lane; i < BN; i += kEpiWarps * 32) {
+        wtab[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        wtab[BN + i] = __ldg(p.gamma + i);
+        wtab[2 * BN + i] = __ldg(p.beta + i);
+        if constexpr (EPI == kEpiBiasResLN2) {
+          wtab[3 * BN + i] = __ldg(p.gamma2 + i);
+          wtab[4 * BN + i] = __ldg(p.beta2 + i);
+        }
+      }
+      named_bar_sync(6, kEpiWarps * 32);
+    }
     pdl_wait();
 
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -313,20 +334,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           btab_nt = nt;
         }
       }
-      // LayerNorm epilogue: while the operands / MMAs of this tile are still in flight, pull bias | gamma | beta
-      // into L1 and request the first residual chunk, so no L2 round trip sits inside the dependent chunk loops
-      [[maybe_unused]] uint4 rnext[4];
+      // LayerNorm epilogue: the first residual chunk of a tile is requested while the previous tile is still being
+      // normalised and stored (below), so no HBM round trip sits in front of the dependent chunk loops
       if constexpr (is_ln_epi(EPI)) {
-        if (ew == 0 && lane < 24) {
-          const float* src = lane < 8 ? p.bias + n0 : (lane < 16 ? p.gamma : p.beta);
-          prefetch_l1(src + (lane & 7) * 32);
-        }
+        if (tile == t_begin) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int grow = m0 + quarter * 32 + (lane >> 2) + 8 * k;
-          rnext[k] = grow < p.M ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + half * 32 +
-                                                                    (lane & 3) * 8)
-                                : make_uint4(0, 0, 0, 0);
+          for (int k = 0; k < 4; ++k) {
+            const int grow = m0 + quarter * 32 + (lane >> 2) + 8 * k;
+            rnext[k] = grow < p.M ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + half * 32 +
+                                                                      (lane & 3) * 8)
+                                  : make_uint4(0, 0, 0, 0);
+          }
         }
       }
       mbar_wait(&acc_full[as], aphase);
@@ -532,15 +550,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                                                         (c + kSplit) * 32 + (lane & 3) * 8)
                                     : make_uint4(0, 0, 0, 0);
             }
+          } else if (tile + 1 < t_end) {  // ... and the first chunk of the NEXT tile under this tile's statistics + stores
+            const int m0n = (tile + 1 - ((tile + 1) / tiles_m) * tiles_m) * kBM;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int grow = m0n + quarter * 32 + (lane >> 2) + 8 * k;
+              rnext[k] = grow < p.M ? *reinterpret_cast<const uint4*>(p.residual + size_t(grow) * p.ldr + n0 + half * 32 +
+                                                                        (lane & 3) * 8)
+                                    : make_uint4(0, 0, 0, 0);
+            }
           }
           __syncwarp();
           tmem_ld_wait();
-          const float* bptr = p.bias + n0 + c * 32;
+          const float* bptr = ltab + c * 32;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 rv = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
             const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
-            const float4 b0 = ldg4(bptr + q * 8), b1 = ldg4(bptr + q * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bptr + q * 8),
+                         b1 = *reinterpret_cast<const float4*>(bptr + q * 8 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -589,8 +617,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           named_bar_sync(1 + quarter, kSplit * 32);  // ... and the squares before the next sums
         };
         row_stats();
-        const float* gamma = p.gamma;
-        const float* beta = p.beta;
+        const float* gamma = ltab + BN;
+        const float* beta = ltab + 2 * BN;
         if constexpr (EPI == kEpiBiasResLN2) {
           // a second LayerNorm on top (nn.Transformer's final encoder norm, FA:42): normalise in registers, then take the
           // statistics of the result - one kernel and one 512-byte-per-row round trip through HBM fewer
@@ -599,7 +627,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int c = half + kSplit * i;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 g4 = ldg4(gamma + c * 32 + j), t4 = ldg4(beta + c * 32 + j);
+              const float4 g4 = *reinterpret_cast<const float4*>(gamma + c * 32 + j),
+                           t4 = *reinterpret_cast<const float4*>(beta + c * 32 + j);
               v[i][j] = (v[i][j] - mean) * rstd * g4.x + t4.x;
               v[i][j + 1] = (v[i][j + 1] - mean) * rstd * g4.y + t4.y;
               v[i][j + 2] = (v[i][j + 2] - mean) * rstd * g4.z + t4.z;
@@ -607,8 +636,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
           }
           row_stats();
-          gamma = p.gamma2;
-          beta = p.beta2;
+          gamma = ltab + 3 * BN;
+          beta = ltab + 4 * BN;
         }
 
         float* frow = (p.out_f32 && valid) ? p.out_f32 + size_t(row) * BN : nullptr;
@@ -620,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 g4 = ldg4(gptr + j), t4 = ldg4(btptr + j);
+            const float4 g4 = *reinterpret_cast<const float4*>(gptr + j), t4 = *reinterpret_cast<const float4*>(btptr + j);
             const float y0 = (v[i][j] - mean) * rstd * g4.x + t4.x;
             const float y1 = (v[i][j + 1] - mean) * rstd * g4.y + t4.y;
             const float y2 = (v[i][j + 2] - mean) * rstd * g4.z + t4.z;
@@ -652,7 +681,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 template <int BN, int EPI, bool TF32>
 cudaError_t launch_one(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p, int num_sms,
                        cudaStream_t stream) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, is_ln_epi(EPI)>;
   auto kfn = gemm_tc_kernel<BN, EPI, TF32>;
   {
     cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), L::kBytes);
