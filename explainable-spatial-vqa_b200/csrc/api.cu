@@ -199,6 +199,7 @@ struct b200vqa_handle {
   int dbg_skip = 0;  // B200VQA_DBG_SKIP: timing decomposition only (results are garbage): 1 cross-attention, 2 self-
                      // attention, 4 feed-forward, 8 out_proj+LN GEMMs, 16 plain GEMMs of the decode chain, 32 encoder,
                      // 64 the vocabulary-head GEMM
+  bool no_img_proj_pair = false;  // B200VQA_NO_IMG_PROJ_PAIR=1: image_proj on the one-CTA-per-tile GEMM
   bool no_fused_enc_ffn = false;  // B200VQA_NO_FUSED_ENC_FFN=1: linear1 / linear2 as two GEMMs through HBM
   int small_bn = 64;  // narrowest n-tile of the plain GEMMs (B200VQA_SMALL_BN=128: A/B of fewer, wider decode CTAs)
   int32_t* h_tables = nullptr;  // pinned: the sorted program tables of one fa_run_chain_host call
@@ -1168,13 +1169,23 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
     p.row_off = 1;
     p.pe = h->pe_enc;
     p.pe_off = 1;
-    if (f16) {  // `img` holds fp16 features: kind::f16 MMA against the fp16 copy of the weight
+    const int M_img = B * d.n_img_tokens;
+    if (!h->no_img_proj_pair && d.img_feat_dim % 64 == 0) {
+      // CTA pairs: each CTA loads half of every weight k-block (image_proj_pair.cu)
+      CUtensorMap ta, tw;
+      const TmapType ty = f16 ? TmapType::kBF16 : TmapType::kF32;  // (2-byte elements: the map only moves bytes)
+      RC_OK(get_tmap(h, img, ty, uint64_t(M_img), uint64_t(d.img_feat_dim), uint64_t(d.img_feat_dim), 128, &ta));
+      RC_OK(get_tmap(h, f16 ? static_cast<const void*>(h->img_w_f16) : static_cast<const void*>(h->img_w_f32), ty, kD,
+                     uint64_t(d.img_feat_dim), uint64_t(d.img_feat_dim), 128, &tw));
+      p.M = M_img;
+      p.N = kD;
+      p.K = d.img_feat_dim;
+      LAUNCH_OK(h, launch_image_proj_pair(f16 ? 1 : 0, ta, tw, p, s));
+    } else if (f16) {  // `img` holds fp16 features: kind::f16 MMA against the fp16 copy of the weight
       p.f16 = true;
-      RC_OK(gemm(h, kEpiBiasPeRemap, false, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f16, kD,
-                 p, s));
+      RC_OK(gemm(h, kEpiBiasPeRemap, false, img, M_img, d.img_feat_dim, d.img_feat_dim, h->img_w_f16, kD, p, s));
     } else {
-      RC_OK(gemm(h, kEpiBiasPeRemap, true, img, B * d.n_img_tokens, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD,
-                 p, s));
+      RC_OK(gemm(h, kEpiBiasPeRemap, true, img, M_img, d.img_feat_dim, d.img_feat_dim, h->img_w_f32, kD, p, s));
     }
   }
   __nv_bfloat16* memory = nullptr;
@@ -1244,6 +1255,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
     if (g[0] && g[0] != '0' && cudaMalloc(&h->persist_clk, 8 * 24 * sizeof(long long)) == cudaSuccess)
       cudaMemset(h->persist_clk, 0, 8 * 24 * sizeof(long long));
   }
+  if (const char* g = getenv("B200VQA_NO_IMG_PROJ_PAIR")) h->no_img_proj_pair = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_NO_FUSED_ENC_FFN")) h->no_fused_enc_ffn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_DBG_SKIP")) h->dbg_skip = atoi(g);
   if (const char* g = getenv("B200VQA_SMALL_BN")) h->small_bn = atoi(g);

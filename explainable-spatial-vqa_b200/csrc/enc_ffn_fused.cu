@@ -39,7 +39,6 @@ constexpr int kEfRegE1 = kEfE1PerQuarter == 1 ? 104 : 64;
 constexpr int kEfRegLN = kEfE1PerQuarter == 1 ? 184 : 152;
 constexpr int kEfRing = 6;
 constexpr int kEfUnit = 16384;
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared-window address of the same offset in the pair's even (leader) CTA
 
 struct EfSmem {
   static constexpr int kOffX = 0;                       // this CTA's x rows: 4 k-blocks of [128 rows x 64]
@@ -77,65 +76,6 @@ __device__ __forceinline__ void st_stream16(void* p, uint32_t a, uint32_t b, uin
   asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// ---- cta_group::2 forms of the tcgen05 / TMA helpers in ptx.cuh
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {  // one warp in EACH CTA of the pair
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// D (+)= A . B over the pair: M = 256 (128 rows from each CTA's shared memory into each CTA's TMEM), B split by N across
-// the two CTAs; the descriptors are shared-memory offsets valid in both.  Issued by ONE thread of the leader CTA.
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// the mbarrier at this offset in BOTH CTAs arrives once every MMA issued so far has completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(uint16_t(3))
-      : "memory");
-}
-// tile -> this CTA's shared memory, bytes counted on the LEADER's mbarrier at the same offset
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-// Arrive on an mbarrier of the pair's leader.  Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier
-// does: a cluster-scope release costs ~1200 cycles per arrive here (measured), and nothing it would order is needed -
-// TMEM hazards are ordered by the tcgen05 fences, and the H tile written to this CTA's shared memory is complete and
-// visible to the async proxy when fence.proxy.async returns, before the arrive is even issued.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool ef_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Bounded by the clock (about one second): a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void ef_wait(uint64_t* bar, uint32_t parity) {
   if (ef_try_wait(bar, parity)) return;

@@ -318,6 +318,11 @@ struct FfnSmallParams {
 cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, const CUtensorMap& tm_w2,
                              const FfnSmallParams& p, cudaStream_t stream);
 
+// image_proj on CTA pairs (image_proj_pair.cu): the kEpiBiasPeRemap GEMM with N = 256 where each CTA of a pair loads half
+// of every weight k-block.  fmt: 0 = fp32 features (tf32 MMA), 1 = fp16, 2 = bf16; p as for launch_gemm.
+cudaError_t launch_image_proj_pair(int fmt, const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
+                                   cudaStream_t stream);
+
 // Host side (host_convert.cu): fp32 -> fp16 (round to nearest even) on a pool of worker threads; dst 32-byte aligned.
 void host_f32_to_f16(const float* src, void* dst, size_t n, int threads);
 void host_f32_to_bf16(const float* src, void* dst, size_t n, int threads);
