@@ -125,7 +125,8 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint64_t* ring_full = bars;        // [6] both halves of a weight unit landed (bytes of both CTAs)
   uint64_t* x_full = bars + 6;       // both x tiles landed
   uint64_t* ht_free = bars + 7;      // [2] H accumulator read out by the hidden epilogues of both CTAs (4 warps each)
-  uint64_t* hs_full = bars + 9;      // [2] H (bf16) written to shared memory in both CTAs (4 warps each)
+  uint64_t* hs_full = bars + 9;      // [2] first K panel (64 hidden units) of H (bf16) written to shared memory in both CTAs
+  uint64_t* hs_full2 = bars + 25;    // [2] ... second panel: GEMM2 starts on the first while the epilogue converts the second
   uint64_t* y_free = bars + 11;      // Y read out by the LayerNorm epilogues of both CTAs (4 warps each)
   // signalled in both CTAs by the leader's multicast commits:
   uint64_t* ring_empty = bars + 12;  // [6] the MMAs that read the unit have retired
@@ -157,7 +158,8 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ht_full[i], 1);
       mbar_init(&ht_free[i], 2 * kEfE1Warps);
-      mbar_init(&hs_full[i], 2 * kEfE1Warps);
+      mbar_init(&hs_full[i], 8);   // four warps per panel and CTA
+      mbar_init(&hs_full2[i], 8);
       mbar_init(&hs_free[i], 1);
     }
     mbar_init(y_full, 1);
@@ -283,11 +285,11 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       };
       auto gemm2 = [&](int j, uint32_t sidx) {  // Y += H[sidx & 1] . W2[:, j]^T : M=256, N=256, K=128
         const uint32_t buf = sidx & 1;
-        ef_wait_t(&hs_full[buf], (sidx >> 1) & 1, w_hsfull, dbg);
         if (j == 0) ef_wait_t(y_free, (t & 1) ^ 1, w_yfree, dbg);
-        tc_fence_after_sync();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+          ef_wait_t(half == 0 ? &hs_full[buf] : &hs_full2[buf], (sidx >> 1) & 1, w_hsfull, dbg);
+          tc_fence_after_sync();
           const uint32_t slot = unit_wait();
           const uint64_t da = dh_base + uint64_t((buf * 32768 + half * 16384) >> 4);
           const uint64_t db = dr_base + uint64_t((slot * kEfUnit) >> 4);
@@ -387,14 +389,21 @@ enc_ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const int chunk = (cc & 1) * 4 + q;
             *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = o;
           }
+          if ((cc & 1) && c + 1 < kEfE1Cols / 32) {
+            // the first 64-unit K panel is complete: GEMM2 of this slice starts on it under the conversion of the second
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cluster_map_shared(smem_u32(&hs_full[buf]), 0));
+          }
         }
-        // (the last tcgen05.ld completed above) GEMM1 of slice s + 2 may overwrite H; GEMM2 of this slice may read it
+        // (the last tcgen05.ld completed above) GEMM1 of slice s + 2 may overwrite H; GEMM2 of this slice may read the
+        // panel just finished
         tc_fence_before_sync();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_cluster(cluster_map_shared(smem_u32(&ht_free[buf]), 0));
-          mbar_arrive_cluster(cluster_map_shared(smem_u32(&hs_full[buf]), 0));
+          mbar_arrive_cluster(cluster_map_shared(smem_u32(kEfE1PerQuarter == 2 && ch == 0 ? &hs_full[buf] : &hs_full2[buf]), 0));
         }
         if (dbg) {
           t_top += q1 - q0;
