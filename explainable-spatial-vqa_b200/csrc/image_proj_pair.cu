@@ -34,9 +34,9 @@ struct IpSmem {
 
 // Bounded by the clock (about one second): a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void ip_wait(uint64_t* bar, uint32_t parity) {
-  if (ef_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!ef_try_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 2000000000ll) {
       printf("b200vqa: image_proj_pair wait timed out (block %d thread %d barrier +%d parity %u)\n", blockIdx.x, threadIdx.x,
              int(smem_u32(bar) & 255u), parity);
