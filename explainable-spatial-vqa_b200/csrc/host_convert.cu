@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include <cuda_fp16.h>
 #include <immintrin.h>
 
@@ -160,6 +162,7 @@ class Pool {
 std::mutex g_pool_mu;   // one conversion at a time per process (the pool is shared by every handle)
 Pool* g_pool = nullptr;  // lives as long as the process
 int g_pool_threads = 0;
+pid_t g_pool_pid = 0;    // a forked child inherits the pointer but not the threads: it builds its own pool
 
 }  // namespace
 
@@ -195,10 +198,11 @@ static void host_convert(CvtFn cvt, const float* src, void* dst, size_t n, int t
     return;
   }
   std::lock_guard<std::mutex> lk(g_pool_mu);
-  if (!g_pool || g_pool_threads != threads) {
-    delete g_pool;
+  if (!g_pool || g_pool_threads != threads || g_pool_pid != getpid()) {
+    if (g_pool && g_pool_pid == getpid()) delete g_pool;  // (never joins threads that only existed in the parent)
     g_pool = new Pool(threads - 1);
     g_pool_threads = threads;
+    g_pool_pid = getpid();
   }
   g_pool->run(n_blocks, [&](size_t b) {
     const size_t lo = b * kBlock, len = std::min(kBlock, n - lo);
