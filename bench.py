@@ -67,7 +67,12 @@ def iqap_work_per_question(ff=2048, n_dec=2, S=S_IQAP, T=T_PROG, Vp=44, C=32):
         "enc_ffn2_ln_gemm": ("tensor", 2 * S * d * ff),
         "enc_ffn_fused": ("tensor", 4 * S * d * ff),            # linear1 + linear2 in one kernel (the default)
         "dec_cross_kv_gemm": ("tensor", n_dec * 2 * S * d * 2 * d),
-        "dec_proj_gemm": ("tensor", n_dec * T * (2 * d * 3 * d + 2 * d * d)),     # self in_proj + cross q-proj
+        # the three plain GEMMs of a decode position, one class per call site (each is one kernel at one shape)
+        "dec_self_qkv_gemm": ("tensor", n_dec * T * 2 * d * 3 * d),               # self-attention in_proj
+        "dec_cross_q_gemm": ("tensor", n_dec * T * 2 * d * d),                    # cross-attention query projection
+        # per-head value projection of the attention-weighted memory (absorbed form only; replaces the K|V projection
+        # of the memory, which the algorithmic count lists under dec_cross_kv_gemm)
+        "dec_cross_v_gemm": ("tensor", n_dec * T * 2 * d * d),
         "dec_outproj_ln_gemm": ("tensor", n_dec * T * 2 * 2 * d * d),            # two out-proj + LayerNorm
         "dec_ffn_split": ("tensor", n_dec * T * 4 * d * ff),
         # HBM-bound: every decode position re-reads the encoder memory rows (bf16, 512 B per row) - the absorbed
@@ -551,7 +556,9 @@ def run_ours(args):
                 "enc_ffn2_ln_gemm": ("tensor", 2 * d_ * ff_ * Lsum), "enc_ffn_fused": ("tensor", 4 * d_ * ff_ * Lsum),
                 "dec_cross_kv_gemm": ("tensor", 2 * d_ * 2 * d_ * Lsum),
                 "enc_final_ln": ("hbm", Lsum * d_ * 2 * 2), "embed_gather": ("hbm", Lsum * d_ * 2 * 2),
-                "dec_proj_gemm": ("tensor", nstep * T_ * (2 * d_ * 3 * d_ + 2 * d_ * d_)),
+                "dec_self_qkv_gemm": ("tensor", nstep * T_ * 2 * d_ * 3 * d_),
+                "dec_cross_q_gemm": ("tensor", nstep * T_ * 2 * d_ * d_),
+                "dec_cross_v_gemm": ("tensor", nstep * T_ * 2 * d_ * d_),
                 "dec_outproj_ln_gemm": ("tensor", nstep * T_ * 4 * d_ * d_),
                 "dec_ffn_split": ("tensor", nstep * T_ * 4 * d_ * ff_),
                 "dec_head_argmax": ("tensor", nstep * T_ * 2 * d_ * V_),

@@ -106,11 +106,11 @@ using TmapKey = std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint3
 // kernel classes for the built-in profiler (b200vqa_profile_*)
 enum Tag : int {
   kTagEmbed = 0, kTagImgProj, kTagEncQkv, kTagEncAttn, kTagEncOutLn, kTagEncFfn1, kTagEncFfn2Ln, kTagEncFfnFused, kTagEncFinalLn,
-  kTagAnswer, kTagDecCrossKv, kTagDecGemm, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagDecPersist, kTagMisc, kNumTags
+  kTagAnswer, kTagDecCrossKv, kTagDecSelfQkv, kTagDecCrossQ, kTagDecCrossV, kTagDecGemmLn, kTagDecFfn, kTagDecSelfAttn, kTagDecCrossAttn, kTagDecHead, kTagDecPersist, kTagMisc, kNumTags
 };
 const char* const kTagNames[kNumTags] = {
     "embed_gather", "image_proj_gemm", "enc_qkv_gemm", "enc_attention", "enc_outproj_ln_gemm", "enc_ffn1_gemm",
-    "enc_ffn2_ln_gemm", "enc_ffn_fused", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_proj_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
+    "enc_ffn2_ln_gemm", "enc_ffn_fused", "enc_final_ln", "answer_head", "dec_cross_kv_gemm", "dec_self_qkv_gemm", "dec_cross_q_gemm", "dec_cross_v_gemm", "dec_outproj_ln_gemm", "dec_ffn_split", "dec_self_attention",
     "dec_cross_attention", "dec_head_argmax", "dec_persistent", "misc"};
 
 struct ProfRec {
@@ -185,6 +185,8 @@ struct b200vqa_handle {
   std::map<GraphKey, GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream
   int decode_branches = 8;            // concurrent question ranges inside the decode graph
+  // L2 eviction hints on the two pure streams (decode memory rows, image features): B200VQA_NO_L2_HINTS=1 turns them off
+  bool l2_hints = true;
   cudaStream_t br_stream[7] = {};
   cudaEvent_t br_done[7] = {};
   cudaEvent_t br_fork = nullptr;
@@ -740,7 +742,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
       __nv_bfloat16* kc = w.kc[l] + r0 * w.t_max * kD;
       __nv_bfloat16* vc = w.vc[l] + r0 * w.t_max * kD;
       const __nv_bfloat16* ckv = h->absorb ? nullptr : w.ckv[l] + r0 * kLP * 2 * kD;
-      h->cur_tag = kTagDecGemm;
+      h->cur_tag = kTagDecSelfQkv;
       if (!(h->dbg_skip & 16)) RC_OK(gemm_bias(h, false, in, B, kD, L.self_attn.w_in, 3 * kD, L.self_attn.b_in, dqkv, s));
       RowAttnParams sp;
       sp.B = B;
@@ -770,7 +772,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         // cross-attention on the encoder memory itself: absorbed queries (N = nhead*256), one pass over the memory
         // rows for all heads, then the per-head value projection as a grouped GEMM
         const int NHD = d.nhead * kD;
-        h->cur_tag = kTagDecGemm;
+        h->cur_tag = kTagDecCrossQ;
         if (!(h->dbg_skip & 16)) RC_OK(gemm_bias(h, false, dx1, B, kD, L.w_qk, NHD, L.b_qk, dq, s));
         MemAttnParams mp;
         mp.B = B;
@@ -781,6 +783,7 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
         mp.const_len = const_len;
         mp.out = du;
         mp.pdl = true;
+        mp.l2_evict_first = h->l2_hints;
         h->cur_tag = kTagDecCrossAttn;
         CUtensorMap tmem_map;
         RC_OK(get_tmap(h, mem_b, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows, &tmem_map));
@@ -791,11 +794,11 @@ int enqueue_decode_rows(b200vqa_handle* h, int b_lo, int B, const __nv_bfloat16*
           vp.out = dattn;
           vp.ldc = kD;
           vp.a_group_cols = kD / d.nhead;
-          h->cur_tag = kTagDecGemm;
+          h->cur_tag = kTagDecCrossV;
           RC_OK(gemm(h, kEpiBias, false, du, B, kD, NHD, L.cross_attn.w_in + size_t(2) * kD * kD, kD, vp, s, NHD));
         }
       } else {
-        h->cur_tag = kTagDecGemm;
+        h->cur_tag = kTagDecCrossQ;
         RC_OK(gemm_bias(h, false, dx1, B, kD, L.cross_attn.w_in, kD, L.cross_attn.b_in, dq, s));
         RowAttnParams cp;
         cp.B = B;
@@ -1180,7 +1183,7 @@ int iqap_chunk(b200vqa_handle* h, const float* img, const int64_t* q, int B, int
       p.M = M_img;
       p.N = kD;
       p.K = d.img_feat_dim;
-      LAUNCH_OK(h, launch_image_proj_pair(f16 ? 1 : 0, ta, tw, p, s));
+      LAUNCH_OK(h, launch_image_proj_pair(f16 ? 1 : 0, ta, tw, p, s, h->l2_hints));
     } else if (f16) {  // `img` holds fp16 features: kind::f16 MMA against the fp16 copy of the weight
       p.f16 = true;
       RC_OK(gemm(h, kEpiBiasPeRemap, false, img, M_img, d.img_feat_dim, d.img_feat_dim, h->img_w_f16, kD, p, s));
@@ -1259,6 +1262,7 @@ B200VQA_API int b200vqa_create(const b200vqa_model_desc* desc, int device, b200v
   if (const char* g = getenv("B200VQA_NO_FUSED_ENC_FFN")) h->no_fused_enc_ffn = g[0] && g[0] != '0';
   if (const char* g = getenv("B200VQA_DBG_SKIP")) h->dbg_skip = atoi(g);
   if (const char* g = getenv("B200VQA_SMALL_BN")) h->small_bn = atoi(g);
+  if (const char* g = getenv("B200VQA_NO_L2_HINTS")) h->l2_hints = !(g[0] && g[0] != '0');
   if (const char* g = getenv("B200VQA_DECODE_BRANCHES")) h->decode_branches = std::min(8, std::max(1, atoi(g)));
   h->d = *desc;
   h->enc_src.assign(desc->enc_layers, desc->enc_layers + desc->n_enc_layers);
@@ -2335,6 +2339,7 @@ B200VQA_API int b200vqa_dbg_mem_attn(const void* qp, const void* memory, const i
   mp.lens = lens;
   mp.const_len = const_len;
   mp.out = static_cast<__nv_bfloat16*>(out);
+  if (const char* g = getenv("B200VQA_NO_L2_HINTS")) mp.l2_evict_first = !(g[0] && g[0] != '0');
   B200VQA_REQUIRE(impl == 0 && stamps == nullptr, "only the warp-MMA kernel (impl 0) exists");
   CUtensorMap tm;
   RC_OK(make_tmap_2d(&tm, memory, TmapType::kBF16, uint64_t(B) * kLP, kD, kD, kMemAttnTileRows));

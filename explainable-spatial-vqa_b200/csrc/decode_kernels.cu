@@ -353,6 +353,7 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
       const int st = issued % kMemStages;
       const uint32_t dst = ring_u32 + st * kMemStageBytes;
       const int row = pq * int(p.rows_per_q) + pt * kMemTileRows;
+      const uint64_t pol = p.l2_evict_first ? kL2EvictFirst : kL2EvictNormal;  // MemAttnParams: the stream must not thrash L2
       if (warp == 0 && p_el) {
         mbar_expect_tx(&full_bar[st], kMemStageBytes + (pt == 0 ? NH * kD * 2 : 0));
         if (pt == 0) {
@@ -362,7 +363,8 @@ mem_attn_kernel(const __grid_constant__ CUtensorMap tm_mem, const MemAttnParams 
                           &full_bar[st]);
         }
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) tma_load_2d_u32(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row);
+        for (int cb = 0; cb < 4; ++cb)
+          tma_load_2d_u32_hint(&tm_mem, &full_bar[st], dst + cb * kMemBlockBytes, cb * 64, row, pol);
       }
       __syncwarp();
       if (pt == 0) ++p_questions;

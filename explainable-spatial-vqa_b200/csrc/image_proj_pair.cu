@@ -49,7 +49,7 @@ __device__ __forceinline__ void ip_wait(uint64_t* bar, uint32_t parity) {
 template <uint32_t FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIpThreads, 1)
 image_proj_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-                       const GemmParams p) {
+                       const GemmParams p, const uint64_t a_policy) {
   using L = IpSmem;
   constexpr int kElems = FMT == kFmtTF32 ? 32 : 64;  // elements of K per 128-byte k-block row
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -101,7 +101,9 @@ image_proj_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         ip_wait(&ring_empty[st], ((u / kIpStages) & 1) ^ 1);
         if (el) {
           if (leader) mbar_expect_tx(&ring_full[st], 2 * kIpStage);
-          tma_load_2d_pair(&tm_a, &ring_full[st], ring + st * kIpStage, kb * kElems, sup * 256 + int(rank) * 128);
+          // the features are read exactly once: evict-first keeps 803 KB per question from displacing what the
+          // concurrent decode chains re-use in L2
+          tma_load_2d_pair_hint(&tm_a, &ring_full[st], ring + st * kIpStage, kb * kElems, sup * 256 + int(rank) * 128, a_policy);
           tma_load_2d_pair(&tm_w, &ring_full[st], ring + st * kIpStage + 16384, kb * kElems, int(rank) * 128);
         }
         __syncwarp();
@@ -204,7 +206,7 @@ image_proj_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
 
 // fmt: 0 = fp32 features (tf32 MMA), 1 = fp16, 2 = bf16.  tm_a: [M, K] box 128 B x 128 rows; tm_w: [256, K] box 128 B x 128 rows.
 cudaError_t launch_image_proj_pair(int fmt, const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, bool a_evict_first) {
   if (p.M <= 0) return cudaSuccess;
   const int elems = fmt == 0 ? 32 : 64;
   if (p.N != kD || p.K <= 0 || p.K % elems != 0 || !p.out || !p.pe || p.rows_in <= 0) return cudaErrorInvalidValue;
@@ -214,12 +216,13 @@ cudaError_t launch_image_proj_pair(int fmt, const CUtensorMap& tm_a, const CUten
   const int sups = (p.M + 255) / 256;
   const int pairs = sups < num_sms / 2 ? sups : num_sms / 2;
   const dim3 grid(2 * pairs), block(kIpThreads);
+  const uint64_t a_policy = a_evict_first ? kL2EvictFirst : kL2EvictNormal;
 #define B200VQA_IP_CASE(F)                                                                              \
   {                                                                                                     \
     auto kfn = image_proj_pair_kernel<F>;                                                               \
     e = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), IpSmem::kBytes);                            \
     if (e != cudaSuccess) return e;                                                                     \
-    return launch_kernel(kfn, grid, block, IpSmem::kBytes, stream, false, tm_a, tm_w, p);               \
+    return launch_kernel(kfn, grid, block, IpSmem::kBytes, stream, false, tm_a, tm_w, p, a_policy);     \
   }
   if (fmt == 0) B200VQA_IP_CASE(kFmtTF32)
   if (fmt == 1) B200VQA_IP_CASE(kFmtF16)

@@ -245,6 +245,10 @@ struct MemAttnParams {
   const int32_t* lens = nullptr;     // [B] or null -> const_len
   int const_len = 0;
   __nv_bfloat16* out = nullptr;
+  // the memory rows are fetched evict-first: every decode position of every layer streams the same rows again, but the
+  // rows of all the chains in flight (254 MB at 2 x 1024 questions) never fit L2, so keeping them only displaces what
+  // does get re-used - weights, KV caches, the FFN partials
+  bool l2_evict_first = true;
 };
 constexpr int kMemAttnTileRows = 32;  // memory rows per shared-memory tile of the absorbed cross-attention
 // tm_mem: the memory as a 2D tensor [B * rows_per_q, 256] bf16, 128-byte swizzle, box {64 channels, kMemAttnTileRows}
@@ -320,8 +324,9 @@ cudaError_t launch_ffn_small(const CUtensorMap& tm_x, const CUtensorMap& tm_w1, 
 
 // image_proj on CTA pairs (image_proj_pair.cu): the kEpiBiasPeRemap GEMM with N = 256 where each CTA of a pair loads half
 // of every weight k-block.  fmt: 0 = fp32 features (tf32 MMA), 1 = fp16, 2 = bf16; p as for launch_gemm.
+// a_evict_first: the feature rows (read exactly once) are fetched with the L2 evict-first policy.
 cudaError_t launch_image_proj_pair(int fmt, const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmParams& p,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, bool a_evict_first = true);
 
 // Host side (host_convert.cu): fp32 -> fp16 (round to nearest even) on a pool of worker threads; dst 32-byte aligned.
 void host_f32_to_f16(const float* src, void* dst, size_t n, int threads);

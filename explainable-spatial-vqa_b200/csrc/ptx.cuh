@@ -104,6 +104,22 @@ __device__ __forceinline__ void tma_load_2d_u32(const CUtensorMap* m, uint64_t* 
       : "memory");
 }
 
+// L2 eviction-priority policies for the .L2::cache_hint operand (the fixed encodings `createpolicy` produces for a
+// fraction of 1.0; CUTLASS passes the same constants): lines fetched evict-first leave L2 before anything else does,
+// evict-last lines stay until only evict-last lines are left in their set.
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
+// tma_load_2d_u32 with an L2 policy for the fetched lines
+__device__ __forceinline__ void tma_load_2d_u32_hint(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem, int c0, int c1,
+                                                     uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // 1D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_u32(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -319,6 +335,14 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// ... with an L2 policy for the fetched lines
+__device__ __forceinline__ void tma_load_2d_pair_hint(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 // Arrive on an mbarrier of the pair's leader.  Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier

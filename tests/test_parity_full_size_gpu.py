@@ -76,7 +76,7 @@ def test_fa_4096_programs_64_sampled_against_oracle():
 @pytest.mark.parametrize("switch", ["B200VQA_NO_ABSORB", "B200VQA_ABSORB_OV", "B200VQA_NO_FUSED_HEAD",
                                     "B200VQA_NO_WARP_SELF_ATTN", "B200VQA_NO_LN_CLUSTER", "B200VQA_NO_GRAPH",
                                     "B200VQA_NO_PDL", "B200VQA_NO_FUSED_ENC_FFN", "B200VQA_ENC_ATTN_WHOLE_HEAD",
-                                    "B200VQA_NO_IMG_PROJ_PAIR"])
+                                    "B200VQA_NO_IMG_PROJ_PAIR", "B200VQA_NO_L2_HINTS"])
 def test_every_kernel_switch_against_the_oracle(monkeypatch, switch):
     """Each switch selects a different kernel sequence for the same mathematics: all of them must meet the oracle gate
     themselves (comparing them with the default CUDA path would leave no margin: 5e-3 + 4e-3)."""
