@@ -140,3 +140,92 @@ class VQAModel(nn.Module):
 
     def native_launch_count(self) -> int:
         return self._pool.launch_count()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Evaluation of the bounding-box variant (reference :104-150 IoU utilities, :423-538 `evaluate`).  The reference
+# walks every box and every sample in Python with an `.item()` / `.tolist()` per element; here the IoUs, the
+# four-way program x answer tally and the token accuracy are whole-batch tensor expressions on the device the
+# model's outputs live on, accumulated there, and read back ONCE at the end of the data set.
+# ----------------------------------------------------------------------------------------------------------
+def bbox_iou_2d(pred_box, gt_box):
+    """IoU of two [x_min, y_min, x_max, y_max] boxes (reference :104-124); 0.0 when the union is empty."""
+    iw = max(min(pred_box[2], gt_box[2]) - max(pred_box[0], gt_box[0]), 0.0)
+    ih = max(min(pred_box[3], gt_box[3]) - max(pred_box[1], gt_box[1]), 0.0)
+
+    def area(b):
+        return max(b[2] - b[0], 0.0) * max(b[3] - b[1], 0.0)
+
+    inter = iw * ih
+    union = area(pred_box) + area(gt_box) - inter
+    return inter / union if union > 0.0 else 0.0
+
+
+def batch_iou_sum_count(bbox_preds, bbox_gts):
+    """(sum of IoUs, number of ground-truth boxes) of one batch as 0-d tensors on the inputs' device - no host
+    synchronisation.  Semantics of the reference loop (:126-150): predictions clamped to [0, 1], ground-truth boxes
+    whose four coordinates are all |x| < 1e-8 are padding and skipped, an empty union scores 0."""
+    p = bbox_preds.detach().double().clamp(0.0, 1.0)
+    g = bbox_gts.detach().to(p.device).double()
+    real = ~(g.abs() < 1e-8).all(dim=-1)
+    iw = (torch.minimum(p[..., 2], g[..., 2]) - torch.maximum(p[..., 0], g[..., 0])).clamp_min(0.0)
+    ih = (torch.minimum(p[..., 3], g[..., 3]) - torch.maximum(p[..., 1], g[..., 1])).clamp_min(0.0)
+    inter = iw * ih
+    area_p = (p[..., 2] - p[..., 0]).clamp_min(0.0) * (p[..., 3] - p[..., 1]).clamp_min(0.0)
+    area_g = (g[..., 2] - g[..., 0]).clamp_min(0.0) * (g[..., 3] - g[..., 1]).clamp_min(0.0)
+    union = area_p + area_g - inter
+    iou = torch.where(union > 0.0, inter / union.clamp_min(torch.finfo(torch.float64).tiny), torch.zeros_like(union))
+    return (iou * real).sum(), real.sum()
+
+
+def batch_mean_iou(bbox_preds, bbox_gts):
+    """Mean IoU over the non-padding ground-truth boxes of a (B, 10, 4) batch, 0.0 when there are none (:126-150)."""
+    s, n = batch_iou_sum_count(bbox_preds, bbox_gts)
+    n = int(n)
+    return float(s) / n if n else 0.0
+
+
+def get_data_info(questions_h5_path):
+    """(question vocab, program + answer vocab) = max id + 1 over the H5 arrays (reference :361-369)."""
+    import h5py  # optional dependency: only the dataset helpers need it
+    import numpy as np
+    with h5py.File(questions_h5_path, "r") as f:
+        return (int(np.max(f["questions"])) + 1, max(int(np.max(f["programs"])), int(np.max(f["answers"]))) + 1)
+
+
+@torch.no_grad()
+def evaluate(model, dataloader, criterion_seq, criterion_bbox, device):
+    """The reference's evaluation loop (:423-538) over batches of (image_features, questions, combined_seq (B, 28),
+    bboxes_gt (B, 10, 4)).  Returns the same tuple: (loss per sample, mean over batches of the batch-mean IoU,
+    share of samples with correct program + correct answer, correct + incorrect, incorrect + correct,
+    incorrect + incorrect, program token accuracy).  `criterion_bbox` must have reduction='none' (:616)."""
+    model.eval()
+    dev = torch.device(device)
+    # [loss x batch size, samples, sum of batch-mean IoUs, batches, cpca, cpia, ipca, ipia, tokens right, tokens]
+    acc = torch.zeros(10, dtype=torch.float64, device=dev)
+    for image_features, questions, combined_seq, bboxes_gt in dataloader:
+        image_features, questions = image_features.to(dev), questions.to(dev)
+        combined_seq, bboxes_gt = combined_seq.to(dev), bboxes_gt.to(dev)
+        n = image_features.size(0)
+        seq_logits, bbox_preds = model(image_features, questions)
+        loss_seq = criterion_seq(seq_logits.reshape(-1, seq_logits.size(-1)), combined_seq.reshape(-1))
+        mask = bboxes_gt.sum(dim=2, keepdim=True) > 0                                     # :471
+        loss_bbox = (criterion_bbox(bbox_preds, bboxes_gt) * mask).sum() / mask.sum()     # :472-474
+        iou_sum, iou_n = batch_iou_sum_count(bbox_preds, bboxes_gt)
+        batch_iou = torch.where(iou_n > 0, iou_sum / iou_n.clamp_min(1), torch.zeros_like(iou_sum))
+        predicted = seq_logits.argmax(dim=2)       # lowest index wins ties, as torch.max(…, dim=2) does (:487)
+        tok_ok = predicted[:, :-1] == combined_seq[:, :-1]
+        prog_ok = tok_ok.all(dim=1)
+        ans_ok = predicted[:, -1] == combined_seq[:, -1]
+        step = torch.stack([
+            (loss_seq + loss_bbox).double() * n, acc.new_tensor(n), batch_iou, acc.new_tensor(1.0),
+            (prog_ok & ans_ok).sum().double(), (prog_ok & ~ans_ok).sum().double(),
+            (~prog_ok & ans_ok).sum().double(), (~prog_ok & ~ans_ok).sum().double(),
+            tok_ok.sum().double(), acc.new_tensor(tok_ok.numel())])
+        acc += step
+    a = acc.tolist()  # the only device -> host read of the evaluation
+    total, batches, tokens = a[1], a[3], a[9]
+    if total == 0:
+        raise ZeroDivisionError("evaluate: empty dataloader")  # the reference divides by total == 0 as well (:519)
+    return (a[0] / total, a[2] / batches if batches > 0 else 0.0, a[4] / total, a[5] / total, a[6] / total,
+            a[7] / total, a[8] / tokens if tokens > 0 else 0.0)

@@ -241,10 +241,6 @@ def iqap_bb_forward(sd, image_features, questions, seq_len=28, forced=None, reco
 # ------------------------------------------------------------------------------------------------
 # FA: MultiModalTransformer.forward (FA:45-58), greedy_decode (FA:126-146), run_inference_chain (FA:83-124)
 # ------------------------------------------------------------------------------------------------
-def fa_nhead(sd, nhead):
-    return nhead
-
-
 def fa_encode(sd, image_features, src_text, nhead, src_len=None):
     """image_features (B,1024,14,14) or (B,1024,196); src_text (B,S) -> (memory (B,196+S,d), key_len or None)."""
     B = image_features.shape[0]
@@ -356,6 +352,60 @@ def iqap_tally(answer_output, generated_programs, gt_answers, gt_programs):
         counts[(0 if program_correct else 1) if answer_correct else (2 if program_correct else 3)] += 1
     return counts, preds
 
+
+# ------------------------------------------------------------------------------------------------
+# Evaluation of the bounding-box variant: IoU utilities (BB:104-150) and the bookkeeping of `evaluate` (BB:423-538)
+# ------------------------------------------------------------------------------------------------
+def bb_iou(pred_box, gt_box):
+    """Scalar IoU of two [x_min, y_min, x_max, y_max] lists (BB:104-124)."""
+    ix0, iy0 = max(pred_box[0], gt_box[0]), max(pred_box[1], gt_box[1])             # BB:109-110
+    ix1, iy1 = min(pred_box[2], gt_box[2]), min(pred_box[3], gt_box[3])             # BB:111-112
+    inter = max(ix1 - ix0, 0.0) * max(iy1 - iy0, 0.0)                               # BB:114-116
+    pa = max(pred_box[2] - pred_box[0], 0.0) * max(pred_box[3] - pred_box[1], 0.0)  # BB:118
+    ga = max(gt_box[2] - gt_box[0], 0.0) * max(gt_box[3] - gt_box[1], 0.0)          # BB:119
+    union = pa + ga - inter                                                         # BB:121
+    return 0.0 if union <= 0.0 else inter / union                                   # BB:122-124
+
+
+def bb_batch_mean_iou(bbox_preds, bbox_gts):
+    """Mean IoU over the ground-truth boxes of a (B, 10, 4) batch that are not all-zero padding; predictions clamped
+    to [0, 1]; 0.0 when nothing is left (BB:126-150).  Plain loops, as the reference."""
+    ious = []
+    for i in range(bbox_preds.shape[0]):
+        for j in range(bbox_preds.shape[1]):
+            gt = [float(x) for x in bbox_gts[i, j]]
+            if all(abs(x) < 1e-8 for x in gt):                                      # BB:139-140
+                continue
+            pred = [min(max(float(c), 0.0), 1.0) for c in bbox_preds[i, j]]         # BB:142-144
+            ious.append(bb_iou(pred, gt))
+    return float(sum(ious) / len(ious)) if ious else 0.0                            # BB:148-150
+
+
+def bb_evaluate(batches):
+    """The bookkeeping of `evaluate` (BB:423-538) over `batches` = iterable of (seq_logits (B, 28, V), bbox_preds
+    (B, 10, 4), combined_seq (B, 28), bboxes_gt (B, 10, 4)) with CrossEntropyLoss / masked SmoothL1Loss (BB:615-616):
+    -> (loss, mean IoU, cpca, cpia, ipca, ipia, program token accuracy)."""
+    running, total, iou_cum, iou_batches = 0.0, 0, 0.0, 0
+    counts = [0, 0, 0, 0]
+    tok_ok, tok_n = 0, 0
+    for seq_logits, bbox_preds, combined_seq, bboxes_gt in batches:
+        n = seq_logits.shape[0]
+        total += n
+        loss_seq = F.cross_entropy(seq_logits.reshape(-1, seq_logits.shape[-1]), combined_seq.reshape(-1))  # BB:466-468
+        mask = bboxes_gt.sum(dim=2, keepdim=True) > 0                                                       # BB:471
+        loss_bbox = (F.smooth_l1_loss(bbox_preds, bboxes_gt, reduction="none") * mask).sum() / mask.sum()   # BB:472-474
+        running += (loss_seq + loss_bbox).item() * n                                                        # BB:477-478
+        iou_cum += bb_batch_mean_iou(bbox_preds, bboxes_gt)                                                 # BB:481-483
+        iou_batches += 1
+        _, pred = torch.max(seq_logits, dim=2)                                                              # BB:487
+        for i in range(n):
+            prog = pred[i, :-1].tolist() == combined_seq[i, :-1].tolist()                                   # BB:490-494
+            ans = int(pred[i, -1]) == int(combined_seq[i, -1])                                              # BB:503
+            counts[(0 if ans else 1) if prog else (2 if ans else 3)] += 1                                   # BB:506-517
+            tok_ok += sum(int(a == b) for a, b in zip(pred[i, :-1].tolist(), combined_seq[i, :-1].tolist()))
+            tok_n += pred.shape[1] - 1
+    return (running / total, iou_cum / iou_batches if iou_batches else 0.0, counts[0] / total, counts[1] / total,
+            counts[2] / total, counts[3] / total, tok_ok / float(tok_n) if tok_n else 0.0)
 
 # the seeded input generators live in the product package's neutral module (no model arithmetic there)
 from explainable_spatial_vqa_b200.synthetic import chain_strings, fa_programs, fa_vocab, iqap_inputs  # noqa: E402,F401

@@ -126,6 +126,65 @@ def golden_iqap_bb():
     print("iqap_bb: boxes[0,0] =", boxes[0, 0].tolist())
 
 
+BB_EVAL_BOX_BIAS = torch.tensor([0.15, 0.2, 0.55, 0.65])  # planted into bbox_regressor.2.bias by the evaluation golden
+
+
+def bb_eval_case():
+    """Seeded evaluation data of the bounding-box variant: 11 samples in batches of 4, 4, 3; ground-truth boxes with
+    zero-padded tails; (the sequences are made from the model's own greedy output by the caller)."""
+    img, q = orc.iqap_inputs(11, seed=777)
+    g = torch.Generator().manual_seed(778)
+    xy = torch.rand(11, 10, 2, generator=g) * 0.6
+    wh = torch.rand(11, 10, 2, generator=g) * 0.3 + 0.1
+    gt = torch.cat([xy, xy + wh], dim=-1)
+    n_real = torch.randint(1, 11, (11,), generator=g)
+    gt = gt * (torch.arange(10)[None, :] < n_real[:, None])[..., None]
+    return img, q, gt, [slice(0, 4), slice(4, 8), slice(8, 11)]
+
+
+def golden_iqap_bb_eval():
+    """IoU utilities and `evaluate` of the bounding-box variant (train_transformer_iqap_bb.py:104-150, :423-538), run
+    by the reference itself: (a) batch_mean_iou on random boxes, (b) evaluate() on three batches whose ground-truth
+    sequences are the model's own greedy output with planted errors, so that all four tally classes occur."""
+    import train_transformer_iqap_bb as ref_bb
+    g = torch.Generator().manual_seed(99)
+    preds = torch.rand(6, 10, 4, generator=g) * 1.4 - 0.2          # some coordinates outside [0, 1]: clamped
+    lo = torch.rand(6, 10, 2, generator=g) * 0.7
+    gts = torch.cat([lo, lo + torch.rand(6, 10, 2, generator=g) * 0.3], dim=-1)
+    gts[0, 6:] = 0
+    gts[3] = 0                                                      # a sample without boxes
+    preds[1, :3] = gts[1, :3]                                       # exact hits
+    preds[2, 0] = torch.tensor([0.5, 0.5, 0.4, 0.4])                # degenerate prediction: zero area
+    iou = ref_bb.batch_mean_iou(preds, gts)
+    iou_none = ref_bb.batch_mean_iou(preds[3:4], gts[3:4])
+
+    torch.manual_seed(0)
+    model = ref_bb.VQAModel(85, 256, 256, 44, 27, 196).eval()
+    with torch.no_grad():  # a random-init head predicts boxes around 0: move them into the image so that IoUs are not all 0
+        model.bbox_regressor[2].bias.copy_(BB_EVAL_BOX_BIAS.repeat(10))
+    img, q, gt_boxes, parts = bb_eval_case()
+    with torch.no_grad():
+        seq_logits, boxes = model(img, q)
+    seq = seq_logits.argmax(-1).clone()
+    seq[3, -1] = (seq[3, -1] + 1) % 44                             # correct program, wrong answer
+    seq[4, 5] = (seq[4, 5] + 1) % 44                               # wrong program, correct answer
+    seq[5, 0] = (seq[5, 0] + 3) % 44
+    for i in (6, 7, 9):                                            # both wrong
+        seq[i, 2] = (seq[i, 2] + 1) % 44
+        seq[i, -1] = (seq[i, -1] + 2) % 44
+    loader = [(img[p], q[p], seq[p], gt_boxes[p]) for p in parts]
+    import torch.nn as nn
+    import tqdm as _tqdm  # noqa: F401  (the reference wraps the loader in tqdm)
+    res = ref_bb.evaluate(model, loader, nn.CrossEntropyLoss(), nn.SmoothL1Loss(reduction="none"), torch.device("cpu"))
+    keys, sums, asums = pack_checksums(model.state_dict())
+    np.savez_compressed(os.path.join(OUT, "iqap_bb_eval.npz"), torch_version=torch.__version__, sd_keys=keys, sd_sums=sums,
+                        sd_abs_sums=asums, iou_preds=preds.numpy(), iou_gts=gts.numpy(), iou=np.float64(iou),
+                        iou_none=np.float64(iou_none), img_sum=img.double().sum().item(), questions=q.numpy(),
+                        gt_boxes=gt_boxes.numpy(), combined_seq=seq.numpy(), seq_logits=seq_logits.numpy(),
+                        boxes=boxes.numpy(), evaluate=np.array(res, dtype=np.float64), box_bias=BB_EVAL_BOX_BIAS.numpy())
+    print("iqap_bb_eval: batch_mean_iou =", iou, "evaluate =", res)
+
+
 def golden_lstm():
     import run_model_lstm_qp as ref_qp
     from oracle import lstm_oracle
@@ -151,7 +210,8 @@ def golden_lstm():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for name, fn in (("iqap", golden_iqap), ("fa", golden_fa), ("lstm", golden_lstm), ("iqap_bb", golden_iqap_bb)):
+    for name, fn in (("iqap", golden_iqap), ("fa", golden_fa), ("lstm", golden_lstm), ("iqap_bb", golden_iqap_bb),
+                     ("iqap_bb_eval", golden_iqap_bb_eval)):
         if not only or name in only:
             fn()
     for f in sorted(os.listdir(OUT)):
